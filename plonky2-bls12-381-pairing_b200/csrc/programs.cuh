@@ -1,0 +1,181 @@
+// programs.cuh -- per-thread programs (one unit of work per thread) shared by the CUDA kernels
+// (kernels.cu) and the host simulation used by the CPU-side tests (tests/hostsim/hostsim.cpp).
+// External buffers use the C-ABI layout of include/b381.h.
+#pragma once
+#include "tower.cuh"
+
+namespace b381 {
+
+enum Mode { MODE_ARK = 0, MODE_ZK = 1, MODE_LITERAL = 2 };
+
+// error bits accumulated per call (include/b381.h)
+enum ErrBits { ERR_NOT_CANONICAL = 1, ERR_ZERO_DIVISION = 2 };
+
+// ---- slot plans -------------------------------------------------------------------------------
+// Miller loop: f and the line coefficients and the first scratch slots are the hot set (shared
+// memory when NS = 16); R, Q, P are touched only by the curve steps.
+constexpr int ML_F = 0, ML_L = 6, ML_T = 9, ML_R = 19, ML_Q = 22, ML_P = 24, ML_ACC = 25, ML_NSLOTS = 31;
+// final exponentiation: ACC (the value being squared) and the first scratch slots are hot.
+constexpr int FE_ACC = 0, FE_T = 6, FE_F = 22, FE_Y0 = 28, FE_Y1 = 34, FE_Y2 = 40, FE_R = 46, FE_NSLOTS = 52;
+// literal loop
+constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
+constexpr int MAX_NSLOTS = 52;
+
+#define S_(i) slot(cx, (i))
+
+B381_DEV B381_INL bool f12_load_ext(const Ctx& cx, int f, const uint32_t* src) {
+  bool ok = true;
+  for (int i = 0; i < 6; i++) ok &= f2_load_ext(S_(f + i), src + 24 * i);
+  return ok;
+}
+
+B381_DEV B381_INL void f12_store_ext(const Ctx& cx, uint32_t* dst, int f) {
+  for (int i = 0; i < 6; i++) f2_store_ext(dst + 24 * i, S_(f + i));
+}
+
+// raw (internal-format) dump / load of an Fp12: 6 slots x 28 words, used for partial products
+B381_DEV B381_INL void f12_store_raw(const Ctx& cx, uint32_t* dst, int f) {
+  for (int i = 0; i < 6; i++) {
+    Fp c0, c1;
+    ld_f2(c0, c1, S_(f + i));
+    for (int k = 0; k < NL; k++) { dst[28 * i + k] = (uint32_t)c0.l[k]; dst[28 * i + NL + k] = (uint32_t)c1.l[k]; }
+  }
+}
+
+B381_DEV B381_INL void f12_load_raw(const Ctx& cx, int f, const uint32_t* src) {
+  for (int i = 0; i < 6; i++) {
+    Fp c0, c1;
+    for (int k = 0; k < NL; k++) { c0.l[k] = (int32_t)src[28 * i + k]; c1.l[k] = (int32_t)src[28 * i + NL + k]; }
+    B381_TB(c0.mag = c1.mag = 40.0; c0.lb = c1.lb = 1.0 + 1e-6;)
+    st_f2(S_(f + i), c0, c1);
+  }
+}
+
+// Miller loop of one pair into slots ML_F.. (internal format).  Returns error bits.
+// g1: 24 words (x, y), g2: 48 words (x.c0, x.c1, y.c0, y.c1); inf bit0 = P is identity, bit1 = Q.
+B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const uint32_t* g2, int inf, int mode) {
+  int err = 0;
+  if (inf & 3) {                                   // identity pairs contribute 1 (ark drops them)
+    f12_set_one(cx, ML_F);
+    return 0;
+  }
+  if (!f2_load_ext(S_(ML_P), g1)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(ML_Q), g2)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(ML_Q + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
+  MillerSlots s;
+  s.f = ML_F; s.L = ML_L; s.T = ML_T; s.R = ML_R; s.Q = ML_Q; s.P = ML_P;
+  if (mode == MODE_ZK) zk_miller_loop(cx, s);
+  else ark_miller_loop(cx, s);
+  return err;
+}
+
+// final exponentiation of the value in slots `src`..src+5, result left in FE_F.
+B381_DEV B381_INL int final_exp_slots(const Ctx& cx, int src) {
+  if (src != FE_F) f12_copy(cx, FE_F, src);
+  bool zero = true;
+  for (int i = 0; i < 6; i++) zero = zero && f2_is_zero(S_(FE_F + i));
+  if (zero) return ERR_ZERO_DIVISION;              // ark final_exponentiation(0) is None
+  FexpSlots s;
+  s.f = FE_F; s.y0 = FE_Y0; s.y1 = FE_Y1; s.y2 = FE_Y2; s.r = FE_R; s.acc = FE_ACC; s.T = FE_T;
+  final_exponentiation(cx, s);
+  return 0;
+}
+
+// ---- programs -----------------------------------------------------------------------------------
+B381_DEV B381_INL int prog_miller(const Ctx& cx, const uint32_t* g1, const uint32_t* g2, int inf, uint32_t* out, int mode) {
+  int err = miller_to_slots(cx, g1, g2, inf, mode);
+  f12_store_ext(cx, out, ML_F);
+  return err;
+}
+
+B381_DEV B381_INL int prog_final_exp(const Ctx& cx, const uint32_t* in, uint32_t* out) {
+  int err = 0;
+  if (!f12_load_ext(cx, FE_F, in)) err |= ERR_NOT_CANONICAL;
+  err |= final_exp_slots(cx, FE_F);
+  f12_store_ext(cx, out, FE_F);
+  return err;
+}
+
+B381_DEV B381_INL int prog_pairing(const Ctx& cx, const uint32_t* g1, const uint32_t* g2, int inf, uint32_t* out, int mode) {
+  int err = miller_to_slots(cx, g1, g2, inf, mode);
+  err |= final_exp_slots(cx, ML_F);
+  f12_store_ext(cx, out, FE_F);
+  return err;
+}
+
+// Fp12 product of `cnt` raw values spaced `stride` words apart, result raw
+B381_DEV B381_INL void prog_f12_product_raw(const Ctx& cx, const uint32_t* in, size_t cnt, size_t stride, uint32_t* out) {
+  f12_load_raw(cx, 0, in);
+  for (size_t i = 1; i < cnt; i++) {
+    f12_load_raw(cx, 6, in + i * stride);
+    f12_mul(cx, 0, 0, 6, 12);
+  }
+  f12_store_raw(cx, out, 0);
+}
+
+// tower-order Fp12 multiply on external buffers (config #2 microbench, b381_fp12_mul)
+B381_DEV B381_INL int prog_f12_mul(const Ctx& cx, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  int err = 0;
+  if (!f12_load_ext(cx, 0, a)) err |= ERR_NOT_CANONICAL;
+  if (!f12_load_ext(cx, 6, b)) err |= ERR_NOT_CANONICAL;
+  f12_mul(cx, 0, 0, 6, 12);
+  f12_store_ext(cx, out, 0);
+  return err;
+}
+
+// MyFq12 (w-basis) multiply: /root/reference/src/fields/helpers.rs:90-152.  The reference's
+// schoolbook formula and the tower product are the same field element (its own test
+// helpers.rs:248-267 asserts it), so the product is computed in the tower and permuted with the
+// coefficient map of helpers.rs:39-41: wbasis index -> (tower slot, half).
+B381_DEV B381_INL void wbasis_map(int idx, int& slot_i, int& half) {
+  // coeffs = [c000,c100,c010,c110,c020,c120, c001,c101,c011,c111,c021,c121]; c_ijk: i = Fp6 half, j = Fp2 idx, k = u
+  const int w = idx % 6;          // power of w: i = w & 1, j = w >> 1
+  half = idx / 6;
+  slot_i = 3 * (w & 1) + (w >> 1);
+}
+
+B381_DEV B381_INL int prog_wbasis_mul(const Ctx& cx, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  int err = 0;
+  uint32_t ta[144], tb[144];
+  for (int idx = 0; idx < 12; idx++) {
+    int s, h;
+    wbasis_map(idx, s, h);
+    for (int k = 0; k < 12; k++) {
+      ta[24 * s + 12 * h + k] = a[12 * idx + k];
+      tb[24 * s + 12 * h + k] = b[12 * idx + k];
+    }
+  }
+  if (!f12_load_ext(cx, 0, ta)) err |= ERR_NOT_CANONICAL;
+  if (!f12_load_ext(cx, 6, tb)) err |= ERR_NOT_CANONICAL;
+  f12_mul(cx, 0, 0, 6, 12);
+  f12_store_ext(cx, ta, 0);
+  for (int idx = 0; idx < 12; idx++) {
+    int s, h;
+    wbasis_map(idx, s, h);
+    for (int k = 0; k < 12; k++) out[12 * idx + k] = ta[24 * s + 12 * h + k];
+  }
+  return err;
+}
+
+// LITERAL optimized_miller_loop on (G1Projective x,y,z: 36 words; G2Projective x,y,z: 72 words).
+// Output Fq12 with only c0.c0 populated (/root/reference/src/miller_loop_native_optimized.rs:18-36).
+B381_DEV B381_INL int prog_literal(const Ctx& cx, const uint32_t* g1p, const uint32_t* g2p, uint32_t* out) {
+  int err = 0;
+  uint32_t w[24];
+  for (int c = 0; c < 3; c++) {                    // xp, yp, zp as Fq2::new(v, 0)
+    for (int k = 0; k < 12; k++) { w[k] = g1p[12 * c + k]; w[12 + k] = 0; }
+    if (!f2_load_ext(S_(LT_P + c), w)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(LT_Q + c), g2p + 24 * c)) err |= ERR_NOT_CANONICAL;
+  }
+  LiteralSlots s;
+  s.R = LT_R; s.Q = LT_Q; s.Pp = LT_P; s.fn = LT_FN; s.fd = LT_FD; s.n = LT_N; s.d = LT_D; s.T = LT_T;
+  bool ok = literal_optimized_miller_loop(cx, s, LT_OUT);
+  for (int k = 0; k < 144; k++) out[k] = 0;
+  if (!ok) return err | ERR_ZERO_DIVISION;
+  f2_store_ext(out, S_(LT_OUT));
+  return err;
+}
+
+#undef S_
+
+}  // namespace b381

@@ -1,0 +1,955 @@
+// tower.cuh -- Fp2/Fp6/Fp12 tower, G2 line functions, Miller loops and final exponentiation
+// over memory-resident operands ("slots"), one pairing per thread.
+//
+// Storage model.  Every per-thread value is an Fp2 "slot" of 28 words (2 x 14 limbs) = 7 uint4
+// groups.  Group g of a slot lives at ptr[g * B381_GS]: on the device B381_GS = block size, so a
+// warp touching the same group of its 32 pairings reads 512 contiguous bytes (LDS.128/LDG.128,
+// conflict-free); on the host simulation B381_GS = 1.  Slots [0, NS) are in shared memory, slots
+// >= NS in a per-CTA scratch region of global memory (L2 resident: the kernels are persistent,
+// one CTA per SM).  Fp6 = 3 consecutive slots (c0,c1,c2), Fp12 = 6 consecutive slots
+// (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2) -- the reference's tower order
+// (/root/reference/src/fields/helpers.rs:16-37).
+//
+// Heavy Fp2-level primitives (f2_mul, f2_sqr, ...) are __noinline__: they load their operands
+// into registers, do all arithmetic there (fp28.cuh) and store one result.  Everything above is
+// orchestration.  Formulas follow the reference's tower twins (cited per function) and, for the
+// ARK mode, arkworks 0.4; values are bit-identical to the oracle.
+#pragma once
+#include "fp28.cuh"
+
+#if defined(__CUDACC__)
+typedef uint4 u4;
+#define B381_DEV __device__
+#define B381_NOINL __device__ __noinline__
+#else
+struct alignas(16) u4 { uint32_t x, y, z, w; };
+#define B381_DEV
+#define B381_NOINL __attribute__((noinline))
+#endif
+
+#ifndef B381_BLOCK
+#define B381_BLOCK 128
+#endif
+#if defined(__CUDA_ARCH__)
+#define B381_GS B381_BLOCK
+#else
+#define B381_GS 1
+#endif
+
+namespace b381 {
+
+constexpr int GPS = 7;                 // uint4 groups per slot
+constexpr int SLOT = GPS * B381_GS;    // uint4 stride between slots
+#ifndef B381_NS
+#define B381_NS 16
+#endif
+constexpr int NS = B381_NS;            // slots held in shared memory
+
+struct Ctx {
+  u4* sm;   // this thread's shared-memory slots
+  u4* gm;   // this thread's global-memory slots
+};
+
+B381_DEV B381_INL u4* slot(const Ctx& c, int s) { return s < NS ? c.sm + s * SLOT : c.gm + (s - NS) * SLOT; }
+
+// ---------------------------------------------------------------------------------------------
+// bound-tracking side table (host simulation only)
+// ---------------------------------------------------------------------------------------------
+#ifdef B381_TRACK_BOUNDS
+}  // namespace b381
+#include <unordered_map>
+namespace b381 {
+struct TrackEnt { double mag[2], lb[2]; };
+inline std::unordered_map<const void*, TrackEnt>& track_tab() { static std::unordered_map<const void*, TrackEnt> t; return t; }
+inline void track_ld(const u4* p, int h, Fp& a) {
+  auto it = track_tab().find(p);
+  if (it == track_tab().end()) { a.mag = 1.0; a.lb = 1.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
+}
+inline void track_st(const u4* p, int h, const Fp& a) {
+  B381_CHECK(a.lb < 1.01, "store of non-normalised limbs");
+  B381_CHECK(a.mag < 1000.0, "store of oversized value");
+  auto& e = track_tab()[p];
+  e.mag[h] = a.mag; e.lb[h] = a.lb;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// slot loads / stores
+// ---------------------------------------------------------------------------------------------
+B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
+  u4 g[GPS];
+#pragma unroll
+  for (int i = 0; i < GPS; i++) g[i] = p[i * B381_GS];
+  c0.l[0] = g[0].x; c0.l[1] = g[0].y; c0.l[2] = g[0].z; c0.l[3] = g[0].w;
+  c0.l[4] = g[1].x; c0.l[5] = g[1].y; c0.l[6] = g[1].z; c0.l[7] = g[1].w;
+  c0.l[8] = g[2].x; c0.l[9] = g[2].y; c0.l[10] = g[2].z; c0.l[11] = g[2].w;
+  c0.l[12] = g[3].x; c0.l[13] = g[3].y; c1.l[0] = g[3].z; c1.l[1] = g[3].w;
+  c1.l[2] = g[4].x; c1.l[3] = g[4].y; c1.l[4] = g[4].z; c1.l[5] = g[4].w;
+  c1.l[6] = g[5].x; c1.l[7] = g[5].y; c1.l[8] = g[5].z; c1.l[9] = g[5].w;
+  c1.l[10] = g[6].x; c1.l[11] = g[6].y; c1.l[12] = g[6].z; c1.l[13] = g[6].w;
+  B381_TB(track_ld(p, 0, c0); track_ld(p, 1, c1);)
+}
+
+B381_DEV B381_INL void st_f2(u4* p, const Fp& c0, const Fp& c1) {
+  u4 g[GPS];
+  g[0].x = c0.l[0]; g[0].y = c0.l[1]; g[0].z = c0.l[2]; g[0].w = c0.l[3];
+  g[1].x = c0.l[4]; g[1].y = c0.l[5]; g[1].z = c0.l[6]; g[1].w = c0.l[7];
+  g[2].x = c0.l[8]; g[2].y = c0.l[9]; g[2].z = c0.l[10]; g[2].w = c0.l[11];
+  g[3].x = c0.l[12]; g[3].y = c0.l[13]; g[3].z = c1.l[0]; g[3].w = c1.l[1];
+  g[4].x = c1.l[2]; g[4].y = c1.l[3]; g[4].z = c1.l[4]; g[4].w = c1.l[5];
+  g[5].x = c1.l[6]; g[5].y = c1.l[7]; g[5].z = c1.l[8]; g[5].w = c1.l[9];
+  g[6].x = c1.l[10]; g[6].y = c1.l[11]; g[6].z = c1.l[12]; g[6].w = c1.l[13];
+#pragma unroll
+  for (int i = 0; i < GPS; i++) p[i * B381_GS] = g[i];
+  B381_TB(track_st(p, 0, c0); track_st(p, 1, c1);)
+}
+
+// one half (h = 0: c0, h = 1: c1) of a slot
+B381_DEV B381_INL void ld_fp(Fp& a, const u4* p, int h) {
+  Fp c0, c1;
+  ld_f2(c0, c1, p);
+  if (h) a = c1; else a = c0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// constants in device constant memory / host statics
+// ---------------------------------------------------------------------------------------------
+struct ConstTab {
+  int32_t frob[3][5][2][NL];   // gamma_k[j] = xi^(j (p^k-1)/6), k = 1..3, j = 1..5, (c0, c1)
+  int32_t one[NL];
+  uint8_t pm2_nib[96];         // p - 2 as 4-bit windows, MSB first
+};
+#define B381_CONST_INIT { \
+  { { {B381_FROB1_1_C0, B381_FROB1_1_C1}, {B381_FROB1_2_C0, B381_FROB1_2_C1}, {B381_FROB1_3_C0, B381_FROB1_3_C1}, \
+      {B381_FROB1_4_C0, B381_FROB1_4_C1}, {B381_FROB1_5_C0, B381_FROB1_5_C1} }, \
+    { {B381_FROB2_1_C0, B381_FROB2_1_C1}, {B381_FROB2_2_C0, B381_FROB2_2_C1}, {B381_FROB2_3_C0, B381_FROB2_3_C1}, \
+      {B381_FROB2_4_C0, B381_FROB2_4_C1}, {B381_FROB2_5_C0, B381_FROB2_5_C1} }, \
+    { {B381_FROB3_1_C0, B381_FROB3_1_C1}, {B381_FROB3_2_C0, B381_FROB3_2_C1}, {B381_FROB3_3_C0, B381_FROB3_3_C1}, \
+      {B381_FROB3_4_C0, B381_FROB3_4_C1}, {B381_FROB3_5_C0, B381_FROB3_5_C1} } }, \
+  B381_ONE, B381_PM2_NIBBLES }
+
+#if defined(__CUDACC__)
+__constant__ ConstTab g_ct = B381_CONST_INIT;
+#else
+static const ConstTab g_ct = B381_CONST_INIT;
+#endif
+
+B381_DEV B381_INL void fp_const(Fp& r, const int32_t* v) {
+#pragma unroll
+  for (int k = 0; k < NL; k++) r.l[k] = v[k];
+  B381_TB(r.mag = 1.0; r.lb = 1.0;)
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-level Fp2 helpers
+// ---------------------------------------------------------------------------------------------
+// (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba with one reduction per coefficient:
+// 3 x 196 + 2 x 225 = 1038 IMAD.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
+B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
+  Acc A, B, T;
+  acc_zero(A); acc_mac(A, a0, b0);
+  acc_zero(B); acc_mac(B, a1, b1);
+  acc_sub(T, A, B);
+  acc_redc(r0, T);
+  Fp sa, sb;
+  fp_add(sa, a0, a1);
+  fp_add(sb, b0, b1);
+  acc_add(T, A, B);
+  acc_neg(T, T);
+  acc_mac(T, sa, sb);
+  acc_redc(r1, T);
+}
+
+// ((a0+a1)(a0-a1), 2 a0 a1); fq2_target_tree.rs:80-91.  2 x 196 + 2 x 225 = 842 IMAD.
+B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
+  Fp s, d, t;
+  fp_add(s, a0, a1);
+  fp_sub(d, a0, a1);
+  fp_dbl(t, a0);
+  Acc T;
+  acc_zero(T); acc_mac(T, s, d);
+  acc_redc(r0, T);
+  acc_zero(T); acc_mac(T, t, a1);
+  acc_redc(r1, T);
+}
+
+B381_DEV B381_INL void f2_norm(Fp& a0, Fp& a1) { fp_norm(a0); fp_norm(a1); }
+
+// xi * (a0 + a1 u) = (a0 - a1) + (a0 + a1) u ; fq2_target_tree.rs:137-142
+B381_DEV B381_INL void f2_mulxi_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
+  Fp t0, t1;
+  fp_sub(t0, a0, a1);
+  fp_add(t1, a0, a1);
+  r0 = t0; r1 = t1;
+}
+
+// Fermat inversion a^(p-2), 4-bit fixed windows, table in registers is too large -> binary
+// square-and-multiply driven by the nibble table (uniform control flow across the warp).
+B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
+  Fp x;
+  fp_const(x, g_ct.one);
+  for (int i = 0; i < 96; i++) {
+    int nib = g_ct.pm2_nib[i];
+    for (int b = 3; b >= 0; b--) {
+      Fp t;
+      fp_mul(t, x, x);
+      x = t;
+      if ((nib >> b) & 1) {
+        fp_mul(t, x, a);
+        x = t;
+      }
+    }
+  }
+  r = x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// noinline slot primitives
+// ---------------------------------------------------------------------------------------------
+B381_NOINL void f2_mul(u4* r, const u4* a, const u4* b) {
+  Fp a0, a1, b0, b1, r0, r1;
+  ld_f2(a0, a1, a);
+  ld_f2(b0, b1, b);
+  f2_mul_reg(r0, r1, a0, a1, b0, b1);
+  st_f2(r, r0, r1);
+}
+
+// r = (a + a2) * (b + b2); a2 / b2 may be null
+B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u4* b2) {
+  Fp a0, a1, b0, b1, r0, r1;
+  ld_f2(a0, a1, a);
+  if (a2) {
+    Fp t0, t1;
+    ld_f2(t0, t1, a2);
+    fp_add(a0, a0, t0); fp_add(a1, a1, t1);
+    f2_norm(a0, a1);
+  }
+  ld_f2(b0, b1, b);
+  if (b2) {
+    Fp t0, t1;
+    ld_f2(t0, t1, b2);
+    fp_add(b0, b0, t0); fp_add(b1, b1, t1);
+    f2_norm(b0, b1);
+  }
+  f2_mul_reg(r0, r1, a0, a1, b0, b1);
+  st_f2(r, r0, r1);
+}
+
+// r = (a + a2)^2 ; a2 may be null
+B381_NOINL void f2_sqr(u4* r, const u4* a, const u4* a2) {
+  Fp a0, a1, r0, r1;
+  ld_f2(a0, a1, a);
+  if (a2) {
+    Fp t0, t1;
+    ld_f2(t0, t1, a2);
+    fp_add(a0, a0, t0); fp_add(a1, a1, t1);
+    f2_norm(a0, a1);
+  }
+  f2_sqr_reg(r0, r1, a0, a1);
+  st_f2(r, r0, r1);
+}
+
+// r = a * s where s is half h of slot sp (an Fp scalar): 2 x 196 + 2 x 225 IMAD
+B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h) {
+  Fp a0, a1, s, r0, r1;
+  ld_f2(a0, a1, a);
+  ld_fp(s, sp, h);
+  fp_mul(r0, a0, s);
+  fp_mul(r1, a1, s);
+  st_f2(r, r0, r1);
+}
+
+// r = frob-coefficient multiply: (conj? conj(a) : a) * gamma_k[j]   (k in 1..3, j in 1..5)
+B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
+  Fp a0, a1, g0, g1, r0, r1;
+  ld_f2(a0, a1, a);
+  if (conj) fp_neg(a1, a1);
+  fp_const(g0, g_ct.frob[k - 1][j - 1][0]);
+  fp_const(g1, g_ct.frob[k - 1][j - 1][1]);
+  if (k == 2) {                     // gamma_2[j] lies in Fp
+    fp_mul(r0, a0, g0);
+    fp_mul(r1, a1, g0);
+  } else {
+    f2_mul_reg(r0, r1, a0, a1, g0, g1);
+  }
+  st_f2(r, r0, r1);
+}
+
+// r = 1 / a ; (a0, -a1)/(a0^2 + a1^2) ; fq2_target_tree.rs:66-78.  a = 0 gives 0.
+B381_NOINL void f2_inv(u4* r, const u4* a) {
+  Fp a0, a1, n, ni, r0, r1;
+  ld_f2(a0, a1, a);
+  Acc T;
+  acc_zero(T);
+  acc_mac(T, a0, a0);
+  acc_mac(T, a1, a1);
+  acc_redc(n, T);
+  fp_inv_reg(ni, n);
+  fp_mul(r0, a0, ni);
+  fp_neg(a1, a1);
+  fp_mul(r1, a1, ni);
+  st_f2(r, r0, r1);
+}
+
+// two-operand linear ops
+enum LinOp {
+  L_ADD = 0,      // a + b
+  L_SUB,          // a - b
+  L_NEG,          // -a
+  L_DBL,          // 2a
+  L_TRIPLE,       // 3a
+  L_MULXI,        // xi a
+  L_CONJ,         // conj(a)
+  L_COPY,         // a
+  L_HALF,         // a / 2
+  L_HALFSUM,      // (a + b) / 2
+  L_XIADD,        // a + xi b
+  L_3A_M2B,       // 3a - 2b
+  L_3A_P2B,       // 3a + 2b
+  L_MUL12XI,      // 12 xi a          (ark-ec g2.rs: COEFF_B * 3c with COEFF_B = 4 xi)
+  L_MUL8,         // 8a
+  L_2A_MB,        // 2a - b
+  L_MUL4,         // 4a
+};
+
+B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
+  Fp a0, a1, b0, b1, r0, r1;
+  ld_f2(a0, a1, a);
+  if (b) ld_f2(b0, b1, b); else { fp_zero(b0); fp_zero(b1); }
+  switch (op) {
+    case L_ADD: fp_add(r0, a0, b0); fp_add(r1, a1, b1); break;
+    case L_SUB: fp_sub(r0, a0, b0); fp_sub(r1, a1, b1); break;
+    case L_NEG: fp_neg(r0, a0); fp_neg(r1, a1); break;
+    case L_DBL: fp_dbl(r0, a0); fp_dbl(r1, a1); break;
+    case L_TRIPLE: fp_dbl(r0, a0); fp_add(r0, r0, a0); fp_dbl(r1, a1); fp_add(r1, r1, a1); break;
+    case L_MULXI: f2_mulxi_reg(r0, r1, a0, a1); break;
+    case L_CONJ: r0 = a0; fp_neg(r1, a1); break;
+    case L_COPY: r0 = a0; r1 = a1; break;
+    case L_HALF: fp_half(r0, a0); fp_half(r1, a1); break;
+    case L_HALFSUM:
+      fp_add(r0, a0, b0); fp_add(r1, a1, b1);
+      f2_norm(r0, r1);
+      fp_half(r0, r0); fp_half(r1, r1);
+      break;
+    case L_XIADD: {
+      Fp t0, t1;
+      f2_mulxi_reg(t0, t1, b0, b1);
+      fp_add(r0, a0, t0); fp_add(r1, a1, t1);
+    } break;
+    case L_3A_M2B:
+      fp_sub(r0, a0, b0); fp_dbl(r0, r0); fp_add(r0, r0, a0);
+      fp_sub(r1, a1, b1); fp_dbl(r1, r1); fp_add(r1, r1, a1);
+      break;
+    case L_3A_P2B:
+      fp_add(r0, a0, b0); fp_dbl(r0, r0); fp_add(r0, r0, a0);
+      fp_add(r1, a1, b1); fp_dbl(r1, r1); fp_add(r1, r1, a1);
+      break;
+    case L_MUL12XI: {
+      Fp t0, t1;
+      fp_dbl(t0, a0); fp_add(t0, t0, a0); fp_dbl(t1, a1); fp_add(t1, t1, a1);   // 3a
+      f2_norm(t0, t1);
+      fp_dbl(t0, t0); fp_dbl(t0, t0); fp_dbl(t1, t1); fp_dbl(t1, t1);           // 12a
+      f2_norm(t0, t1);
+      f2_mulxi_reg(r0, r1, t0, t1);
+    } break;
+    case L_MUL8:
+      fp_dbl(r0, a0); fp_dbl(r0, r0); fp_dbl(r1, a1); fp_dbl(r1, r1);
+      f2_norm(r0, r1);
+      fp_dbl(r0, r0); fp_dbl(r1, r1);
+      break;
+    case L_2A_MB:
+      fp_dbl(r0, a0); fp_sub(r0, r0, b0); fp_dbl(r1, a1); fp_sub(r1, r1, b1);
+      break;
+    default:  // L_MUL4
+      fp_dbl(r0, a0); fp_dbl(r0, r0); fp_dbl(r1, a1); fp_dbl(r1, r1);
+      break;
+  }
+  if (op == L_3A_M2B || op == L_3A_P2B) { fp_wreduce(r0); fp_wreduce(r1); }   // linear feedback of b (cyclotomic squaring)
+  else f2_norm(r0, r1);
+  st_f2(r, r0, r1);
+}
+
+// Karatsuba recombination: t = a - b - c (b, c optional); then
+//   K_PLAIN     r = t + d
+//   K_XI_INNER  r = xi t + d
+//   K_XI_D      r = t + xi d
+//   K_XI_C      r = a - b - xi c  (+ d)
+enum KOp { K_PLAIN = 0, K_XI_INNER, K_XI_D, K_XI_C };
+
+B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4* d, int mode) {
+  Fp t0, t1, x0, x1;
+  ld_f2(t0, t1, a);
+  if (b) { ld_f2(x0, x1, b); fp_sub(t0, t0, x0); fp_sub(t1, t1, x1); }
+  if (c) {
+    ld_f2(x0, x1, c);
+    if (mode == K_XI_C) f2_mulxi_reg(x0, x1, x0, x1);
+    fp_sub(t0, t0, x0); fp_sub(t1, t1, x1);
+  }
+  if (mode == K_XI_INNER) { f2_norm(t0, t1); f2_mulxi_reg(t0, t1, t0, t1); }
+  if (d) {
+    ld_f2(x0, x1, d);
+    if (mode == K_XI_D) f2_mulxi_reg(x0, x1, x0, x1);
+    fp_add(t0, t0, x0); fp_add(t1, t1, x1);
+  }
+  f2_norm(t0, t1);
+  st_f2(r, t0, t1);
+}
+
+// set slot to the Fp2 constant (one, 0) or (0, 0)
+B381_NOINL void f2_set_small(u4* r, int one) {
+  Fp c0, c1;
+  fp_zero(c0); fp_zero(c1);
+  if (one) fp_const(c0, g_ct.one);
+  B381_TB(c0.lb = 1; c1.lb = 1; c0.mag = 1; c1.mag = 1;)
+  st_f2(r, c0, c1);
+}
+
+// canonical test a == 0 (full reduction; rare path)
+B381_NOINL bool f2_is_zero(const u4* a) {
+  Fp a0, a1;
+  ld_f2(a0, a1, a);
+  fp_canon(a0); fp_canon(a1);
+  return fp_is_zero_canon(a0) && fp_is_zero_canon(a1);
+}
+
+B381_NOINL bool f2_equal(const u4* a, const u4* b) {
+  Fp a0, a1, b0, b1;
+  ld_f2(a0, a1, a);
+  ld_f2(b0, b1, b);
+  fp_sub(a0, a0, b0); fp_sub(a1, a1, b1);
+  f2_norm(a0, a1);
+  fp_canon(a0); fp_canon(a1);
+  return fp_is_zero_canon(a0) && fp_is_zero_canon(a1);
+}
+
+// external (12 x u32 Montgomery R=2^384) <-> slot.  src = 24 words (c0, c1).  Returns validity.
+B381_NOINL bool f2_load_ext(u4* r, const uint32_t* src) {
+  uint32_t w0[12], w1[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { w0[i] = src[i]; w1[i] = src[12 + i]; }
+  Fp c0, c1;
+  bool ok0 = fp_from_ext(c0, w0);
+  bool ok1 = fp_from_ext(c1, w1);
+  st_f2(r, c0, c1);
+  return ok0 && ok1;
+}
+
+B381_NOINL void f2_store_ext(uint32_t* dst, const u4* a) {
+  Fp c0, c1;
+  ld_f2(c0, c1, a);
+  uint32_t w0[12], w1[12];
+  fp_to_ext(w0, c0);
+  fp_to_ext(w1, c1);
+#pragma unroll
+  for (int i = 0; i < 12; i++) { dst[i] = w0[i]; dst[12 + i] = w1[i]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// orchestration helpers (slot indices)
+// ---------------------------------------------------------------------------------------------
+#define S_(i) slot(cx, (i))
+
+B381_DEV B381_INL void lin(const Ctx& cx, int r, int a, int b, int op) { f2_lin(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, op); }
+B381_DEV B381_INL void mul(const Ctx& cx, int r, int a, int b) { f2_mul(S_(r), S_(a), S_(b)); }
+B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2) {
+  f2_mul_ss(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, S_(b), b2 >= 0 ? S_(b2) : nullptr);
+}
+B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { f2_sqr(S_(r), S_(a), nullptr); }
+B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { f2_sqr(S_(r), S_(a), S_(a2)); }
+B381_DEV B381_INL void kcomb(const Ctx& cx, int r, int a, int b, int c, int d, int mode) {
+  f2_kcomb(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, c >= 0 ? S_(c) : nullptr, d >= 0 ? S_(d) : nullptr, mode);
+}
+
+// Fp6 multiplication r = a * b (Karatsuba, 6 Fp2 muls); fq6_target_tree.rs:172-214.
+// r must not alias a or b; t = 4 scratch slots.
+B381_DEV B381_INL void f6_mul(const Ctx& cx, int r, int a, int b, int t) {
+  const int v0 = t, v1 = t + 1, v2 = t + 2, m = t + 3;
+  mul(cx, v0, a, b);
+  mul(cx, v1, a + 1, b + 1);
+  mul(cx, v2, a + 2, b + 2);
+  mul_ss(cx, m, a + 1, a + 2, b + 1, b + 2);
+  kcomb(cx, r, m, v1, v2, v0, K_XI_INNER);        // c0 = xi((a1+a2)(b1+b2) - v1 - v2) + v0
+  mul_ss(cx, m, a, a + 1, b, b + 1);
+  kcomb(cx, r + 1, m, v0, v1, v2, K_XI_D);        // c1 = (a0+a1)(b0+b1) - v0 - v1 + xi v2
+  mul_ss(cx, m, a, a + 2, b, b + 2);
+  kcomb(cx, r + 2, m, v0, v2, v1, K_PLAIN);       // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+}
+
+// Fp6 squaring via f6_mul-style Karatsuba with squarings (3 sqr + 3 mul)
+B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
+  const int v0 = t, v1 = t + 1, v2 = t + 2, m = t + 3;
+  sqr(cx, v0, a);
+  sqr(cx, v1, a + 1);
+  sqr(cx, v2, a + 2);
+  sqr_s(cx, m, a + 1, a + 2);
+  kcomb(cx, r, m, v1, v2, v0, K_XI_INNER);
+  sqr_s(cx, m, a, a + 1);
+  kcomb(cx, r + 1, m, v0, v1, v2, K_XI_D);
+  sqr_s(cx, m, a, a + 2);
+  kcomb(cx, r + 2, m, v0, v2, v1, K_PLAIN);
+}
+
+// Fp12 multiplication r = a * b (3 Fp6 muls); fq12_target_tree.rs:130-141.
+// r may alias a or b.  t = 16 scratch slots.
+B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t) {
+  const int aa = t, bb = t + 3, sa = t + 6, sb = t + 9, w = t + 12;   // w: 4 slots
+  f6_mul(cx, aa, a, b, w);
+  f6_mul(cx, bb, a + 3, b + 3, w);
+  for (int i = 0; i < 3; i++) {
+    lin(cx, sa + i, a + i, a + 3 + i, L_ADD);
+    lin(cx, sb + i, b + i, b + 3 + i, L_ADD);
+  }
+  f6_mul(cx, r + 3, sa, sb, w);                   // (a0+a1)(b0+b1)   (a, b dead from here on)
+  for (int i = 0; i < 3; i++) kcomb(cx, r + 3 + i, r + 3 + i, aa + i, bb + i, -1, K_PLAIN);
+  lin(cx, r, aa, bb + 2, L_XIADD);                // c0 = aa + v bb ; v bb = (xi bb2, bb0, bb1)
+  lin(cx, r + 1, aa + 1, bb, L_ADD);
+  lin(cx, r + 2, aa + 2, bb + 1, L_ADD);
+}
+
+// Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  t = 10 scratch slots.
+B381_DEV void f12_sqr(const Ctx& cx, int f, int t) {
+  const int ab = t, s = t + 3, w = t + 6;         // w: 4 slots
+  f6_mul(cx, ab, f, f + 3, w);                    // ab = a0 a1
+  for (int i = 0; i < 3; i++) lin(cx, s + i, f + i, f + 3 + i, L_ADD);      // s = a0 + a1
+  // u = a0 + v a1 = (a00 + xi a12, a01 + a10, a02 + a11), built in place over a1
+  lin(cx, w, f + 5, -1, L_COPY);                  // keep a12
+  lin(cx, f + 5, f + 2, f + 4, L_ADD);            // u2
+  lin(cx, f + 4, f + 1, f + 3, L_ADD);            // u1
+  lin(cx, f + 3, f, w, L_XIADD);                  // u0
+  f6_mul(cx, f, s, f + 3, w);                     // c0 = s * u  (a0 dead)
+  kcomb(cx, f, f, ab, ab + 2, -1, K_XI_C);        // c0 -= ab + v ab ; v ab = (xi ab2, ab0, ab1)
+  kcomb(cx, f + 1, f + 1, ab + 1, ab, -1, K_PLAIN);
+  kcomb(cx, f + 2, f + 2, ab + 2, ab + 1, -1, K_PLAIN);
+  for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, ab + i, -1, L_DBL);        // c1 = 2 ab
+}
+
+// sparse multiplication f *= (c0 + c1 v + c4 v w), in place; fq12_target_tree.rs:157-176 and
+// the native twin /root/reference/src/miller_loop_native.rs:118-137.  13 Fp2 muls.
+// t = 9 scratch slots.
+B381_DEV void f12_mul_by_014(const Ctx& cx, int f, int c0, int c1, int c4, int t) {
+  const int b0 = t, b1 = t + 1, b2 = t + 2, o = t + 3, p0 = t + 4, p1 = t + 5, m0 = t + 6, m1 = t + 7, m2 = t + 8;
+  // bb = f1.mul_by_1(c4) = (xi f12 c4, f10 c4, f11 c4)     (fq6_target_tree.rs:261-268)
+  mul(cx, b0, f + 5, c4);
+  lin(cx, b0, b0, -1, L_MULXI);
+  mul(cx, b1, f + 3, c4);
+  mul(cx, b2, f + 4, c4);
+  // s = f1 + f0 (in place over f1), o = c1 + c4
+  for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, f + 3 + i, f + i, L_ADD);
+  lin(cx, o, c1, c4, L_ADD);
+  // n = s.mul_by_01(c0, o)                                   (fq6_target_tree.rs:232-259)
+  mul(cx, p0, f + 3, c0);
+  mul(cx, p1, f + 4, o);
+  mul_ss(cx, m0, f + 4, f + 5, o, -1);
+  mul_ss(cx, m1, f + 3, f + 4, c0, o);
+  mul_ss(cx, m2, f + 3, f + 5, c0, -1);
+  kcomb(cx, f + 3, m0, p1, -1, p0, K_XI_INNER);   // n0 = xi(o (s1+s2) - p1) + p0
+  kcomb(cx, f + 4, m1, p0, p1, -1, K_PLAIN);      // n1 = (c0+o)(s0+s1) - p0 - p1
+  kcomb(cx, f + 5, m2, p0, -1, p1, K_PLAIN);      // n2 = c0 (s0+s2) - p0 + p1
+  // aa = f0.mul_by_01(c0, c1), written over f0
+  mul(cx, p0, f, c0);
+  mul(cx, p1, f + 1, c1);
+  mul_ss(cx, m0, f + 1, f + 2, c1, -1);
+  mul_ss(cx, m1, f, f + 1, c0, c1);
+  mul_ss(cx, m2, f, f + 2, c0, -1);
+  kcomb(cx, f, m0, p1, -1, p0, K_XI_INNER);
+  kcomb(cx, f + 1, m1, p0, p1, -1, K_PLAIN);
+  kcomb(cx, f + 2, m2, p0, -1, p1, K_PLAIN);
+  // new c1 = n - aa - bb ; new c0 = aa + v bb = aa + (xi bb2, bb0, bb1)
+  kcomb(cx, f + 3, f + 3, f, b0, -1, K_PLAIN);
+  kcomb(cx, f + 4, f + 4, f + 1, b1, -1, K_PLAIN);
+  kcomb(cx, f + 5, f + 5, f + 2, b2, -1, K_PLAIN);
+  lin(cx, f, f, b2, L_XIADD);
+  lin(cx, f + 1, f + 1, b0, L_ADD);
+  lin(cx, f + 2, f + 2, b1, L_ADD);
+}
+
+B381_DEV B381_INL void f12_set_one(const Ctx& cx, int f) {
+  f2_set_small(S_(f), 1);
+  for (int i = 1; i < 6; i++) f2_set_small(S_(f + i), 0);
+}
+
+B381_DEV B381_INL void f12_copy(const Ctx& cx, int r, int a) {
+  for (int i = 0; i < 6; i++) lin(cx, r + i, a + i, -1, L_COPY);
+}
+
+// conjugation (c0, -c1) in place; fq12_target_tree.rs:53-58; /root/reference/src/miller_loop_native.rs:194-200
+B381_DEV B381_INL void f12_conj(const Ctx& cx, int f) {
+  for (int i = 3; i < 6; i++) lin(cx, f + i, f + i, -1, L_NEG);
+}
+
+// Frobenius map f -> f^(p^k) in place, k in 1..3; fq12_target_tree.rs:92-128, fq6_target_tree.rs:129-169.
+// Slot f + 3 i + j holds the coefficient of w^(2j+i).
+B381_DEV void f12_frobenius(const Ctx& cx, int f, int k) {
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++) {
+      const int tw = 2 * j + i;
+      u4* p = S_(f + 3 * i + j);
+      if (tw == 0) { if (k & 1) f2_lin(p, p, nullptr, L_CONJ); }
+      else f2_mul_gamma(p, p, k, tw, k & 1);
+    }
+}
+
+// Fp6 inverse; fq6_target_tree.rs:59-89.  r may alias a.  t = 5 scratch slots.
+B381_DEV void f6_inv(const Ctx& cx, int r, int a, int t) {
+  const int c0 = t, c1 = t + 1, c2 = t + 2, x = t + 3, y = t + 4;
+  sqr(cx, c0, a); mul(cx, x, a + 1, a + 2); kcomb(cx, c0, c0, -1, x, -1, K_XI_C);        // c0 = a0^2 - xi a1 a2
+  sqr(cx, c1, a + 2); lin(cx, c1, c1, -1, L_MULXI); mul(cx, x, a, a + 1); lin(cx, c1, c1, x, L_SUB);   // c1 = xi a2^2 - a0 a1
+  sqr(cx, c2, a + 1); mul(cx, x, a, a + 2); lin(cx, c2, c2, x, L_SUB);                   // c2 = a1^2 - a0 a2
+  mul(cx, x, a + 2, c1); mul(cx, y, a + 1, c2); lin(cx, x, x, y, L_ADD); lin(cx, x, x, -1, L_MULXI);
+  mul(cx, y, a, c0); lin(cx, x, x, y, L_ADD);                                            // t = xi(a2 c1 + a1 c2) + a0 c0
+  f2_inv(S_(x), S_(x));
+  mul(cx, r, x, c0); mul(cx, r + 1, x, c1); mul(cx, r + 2, x, c2);
+}
+
+// Fp12 inverse in place; fq12_target_tree.rs:77-90.  t = 15 scratch slots.
+B381_DEV void f12_inv(const Ctx& cx, int f, int t) {
+  const int u = t, v = t + 3, w = t + 6;          // w: up to 5 + 4
+  f6_sqr(cx, u, f, w);
+  f6_sqr(cx, v, f + 3, w);
+  kcomb(cx, u, u, -1, v + 2, -1, K_XI_C);         // u = c0^2 - v c1^2 ; v x = (xi x2, x0, x1)
+  lin(cx, u + 1, u + 1, v, L_SUB);
+  lin(cx, u + 2, u + 2, v + 1, L_SUB);
+  f6_inv(cx, u, u, w);
+  f6_mul(cx, v, f, u, w);
+  for (int i = 0; i < 3; i++) lin(cx, f + i, v + i, -1, L_COPY);
+  f6_mul(cx, v, f + 3, u, w);
+  for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, v + i, -1, L_NEG);
+}
+
+// fp4_square(a, b) -> (ra, rb) = (a^2 + xi b^2, (a+b)^2 - a^2 - b^2);
+// /root/reference/src/fields_as_trees/miller_loop.rs:29-44.  t = 1 scratch slot beyond outputs.
+B381_DEV B381_INL void fp4_square(const Ctx& cx, int ra, int rb, int a, int b, int t) {
+  sqr(cx, ra, a);
+  sqr(cx, t, b);
+  sqr_s(cx, rb, a, b);
+  kcomb(cx, rb, rb, ra, t, -1, K_PLAIN);
+  lin(cx, ra, ra, t, L_XIADD);
+}
+
+// Granger-Scott cyclotomic squaring in place; miller_loop.rs:46-104.  t = 5 scratch slots.
+B381_DEV void f12_cyclotomic_square(const Ctx& cx, int f, int t) {
+  const int z0 = f, z4 = f + 1, z3 = f + 2, z2 = f + 3, z1 = f + 4, z5 = f + 5;
+  const int t0 = t, t1 = t + 1, t2 = t + 2, t3 = t + 3, w = t + 4;
+  fp4_square(cx, t0, t1, z0, z1, w);
+  lin(cx, z0, t0, z0, L_3A_M2B);
+  lin(cx, z1, t1, z1, L_3A_P2B);
+  fp4_square(cx, t0, t1, z2, z3, w);
+  fp4_square(cx, t2, t3, z4, z5, w);
+  lin(cx, z4, t0, z4, L_3A_M2B);
+  lin(cx, z5, t1, z5, L_3A_P2B);
+  lin(cx, t3, t3, -1, L_MULXI);
+  lin(cx, z2, t3, z2, L_3A_P2B);
+  lin(cx, z3, t2, z3, L_3A_M2B);
+}
+
+// r = conj(a^|x|): ark Bls12::exp_by_x (x < 0).  The running value lives in the fixed slots
+// `acc` (shared memory) so the 63 cyclotomic squarings never touch global memory; r may alias a.
+// t = 16 scratch slots.
+B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int t) {
+  f12_copy(cx, acc, a);
+  const uint64_t xabs = B381_X_ABS;
+  for (int b = 62; b >= 0; b--) {
+    f12_cyclotomic_square(cx, acc, t);
+    if ((xabs >> b) & 1) f12_mul(cx, acc, acc, a, t);
+  }
+  for (int i = 0; i < 3; i++) lin(cx, r + i, acc + i, -1, L_COPY);
+  for (int i = 3; i < 6; i++) lin(cx, r + i, acc + i, -1, L_NEG);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ARK mode: G2 homogeneous-projective steps (ark-ec 0.4 models/bls12/g2.rs)
+// R = slots (X, Y, Z) = (R, R+1, R+2); line coefficients -> (L, L+1, L+2); t = 5 scratch slots.
+// ---------------------------------------------------------------------------------------------
+B381_DEV void ark_double_step(const Ctx& cx, int R, int L, int t) {
+  const int X = R, Y = R + 1, Z = R + 2, T0 = t, T1 = t + 1, T2 = t + 2, T3 = t + 3, T4 = t + 4;
+  mul(cx, T0, X, Y); lin(cx, T0, T0, -1, L_HALF);                  // a = X Y / 2
+  sqr(cx, T1, Y);                                                  // b = Y^2
+  sqr(cx, T2, Z);                                                  // c = Z^2
+  sqr(cx, L + 1, X); lin(cx, L + 1, L + 1, -1, L_TRIPLE);          // 3 j = 3 X^2
+  sqr_s(cx, T3, Y, Z); kcomb(cx, T3, T3, T1, T2, -1, K_PLAIN);     // h = (Y+Z)^2 - (b + c)
+  lin(cx, T2, T2, -1, L_MUL12XI);                                  // e = B' 3c = 12 xi c
+  lin(cx, L, T2, T1, L_SUB);                                       // i = e - b
+  lin(cx, T4, T2, -1, L_TRIPLE);                                   // f = 3e
+  lin(cx, X, T1, T4, L_SUB); mul(cx, X, T0, X);                    // X' = a (b - f)
+  lin(cx, T0, T1, T4, L_HALFSUM);                                  // g = (b + f) / 2
+  mul(cx, Z, T1, T3);                                              // Z' = b h
+  lin(cx, L + 2, T3, -1, L_NEG);                                   // -h
+  sqr(cx, T2, T2); lin(cx, T2, T2, -1, L_TRIPLE);                  // 3 e^2
+  sqr(cx, Y, T0); lin(cx, Y, Y, T2, L_SUB);                        // Y' = g^2 - 3 e^2
+}
+
+// mixed addition R += Q, Q = slots (Qs, Qs+1) affine; coefficients (j, -theta, lambda)
+B381_DEV void ark_add_step(const Ctx& cx, int R, int Qs, int L, int t) {
+  const int X = R, Y = R + 1, Z = R + 2, qx = Qs, qy = Qs + 1;
+  const int th = t, la = t + 1, c = t + 2, d = t + 3, e = t + 4;
+  mul(cx, th, qy, Z); lin(cx, th, Y, th, L_SUB);                   // theta = Y - qy Z
+  mul(cx, la, qx, Z); lin(cx, la, X, la, L_SUB);                   // lambda = X - qx Z
+  sqr(cx, c, th);                                                  // c = theta^2
+  sqr(cx, d, la);                                                  // d = lambda^2
+  mul(cx, e, la, d);                                               // e = lambda d
+  mul(cx, c, Z, c);                                                // f = Z c
+  mul(cx, d, X, d);                                                // g = X d
+  lin(cx, c, e, c, L_ADD); lin(cx, X, d, -1, L_DBL); lin(cx, c, c, X, L_SUB);   // h = e + f - 2g
+  mul(cx, X, la, c);                                               // X' = lambda h
+  lin(cx, d, d, c, L_SUB); mul(cx, d, th, d);                      // theta (g - h)
+  mul(cx, Y, e, Y); lin(cx, Y, d, Y, L_SUB);                       // Y' = theta (g-h) - e Y
+  mul(cx, Z, Z, e);                                                // Z' = Z e
+  mul(cx, c, th, qx); mul(cx, d, la, qy); lin(cx, L, c, d, L_SUB); // j = theta qx - lambda qy
+  lin(cx, L + 1, th, -1, L_NEG);
+  lin(cx, L + 2, la, -1, L_COPY);
+}
+
+// ell for the M-twist: c2 *= py ; c1 *= px ; f.mul_by_014(c0, c1, c2).  Pt = slot (px, py).
+B381_DEV B381_INL void ark_ell(const Ctx& cx, int f, int L, int Pt, int t) {
+  f2_mulfp(S_(L + 2), S_(L + 2), S_(Pt), 1);
+  f2_mulfp(S_(L + 1), S_(L + 1), S_(Pt), 0);
+  f12_mul_by_014(cx, f, L, L + 1, L + 2, t);
+}
+
+// slot plan shared by the Miller-loop kernels
+struct MillerSlots { int f, L, T, R, Q, P; };
+
+// Bls12::multi_miller_loop for one pair: f = 1; per bit: f = f^2; ell(double);
+// if bit: ell(add); finally conjugate (x < 0).  Q (affine) at slots (Q, Q+1), P at slot P,
+// R scratch at (R..R+2).  T = 10 scratch slots.
+B381_DEV void ark_miller_loop(const Ctx& cx, const MillerSlots& s) {
+  f12_set_one(cx, s.f);
+  lin(cx, s.R, s.Q, -1, L_COPY);
+  lin(cx, s.R + 1, s.Q + 1, -1, L_COPY);
+  f2_set_small(S_(s.R + 2), 1);
+  const uint64_t xabs = B381_X_ABS;
+  for (int b = 62; b >= 0; b--) {
+    if (b != 62) f12_sqr(cx, s.f, s.T);           // first squaring is 1^2
+    ark_double_step(cx, s.R, s.L, s.T);
+    ark_ell(cx, s.f, s.L, s.P, s.T);
+    if ((xabs >> b) & 1) {
+      ark_add_step(cx, s.R, s.Q, s.L, s.T);
+      ark_ell(cx, s.f, s.L, s.P, s.T);
+    }
+  }
+  f12_conj(cx, s.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ZK mode: /root/reference/src/miller_loop_native.rs:27-116 with ell (:139-152) wired in.
+// ---------------------------------------------------------------------------------------------
+// Alg. 26 doubling, miller_loop_native.rs:27-55.  t = 7 scratch slots.  coeffs -> (L, L+1, L+2)
+B381_DEV void zk_double_step(const Ctx& cx, int R, int L, int t) {
+  const int x = R, y = R + 1, z = R + 2;
+  const int t0 = t, t1 = t + 1, t2 = t + 2, t3 = t + 3, t4 = t + 4, t5 = t + 5, zs = t + 6;
+  sqr(cx, t0, x);                                                  // tmp0 = x^2
+  sqr(cx, t1, y);                                                  // tmp1 = y^2
+  sqr(cx, t2, t1);                                                 // tmp2 = tmp1^2
+  sqr_s(cx, t3, t1, x); kcomb(cx, t3, t3, t0, t2, -1, K_PLAIN); lin(cx, t3, t3, -1, L_DBL);   // tmp3
+  lin(cx, t4, t0, -1, L_TRIPLE);                                   // tmp4 = 3 tmp0
+  lin(cx, L + 2, x, t4, L_ADD);                                    // tmp6 = x + tmp4
+  sqr(cx, t5, t4);                                                 // tmp5 = tmp4^2
+  sqr(cx, zs, z);                                                  // zsquared
+  kcomb(cx, x, t5, t3, t3, -1, K_PLAIN);                           // x' = tmp5 - 2 tmp3
+  sqr_s(cx, z, z, y); kcomb(cx, z, z, t1, zs, -1, K_PLAIN);        // z' = (z+y)^2 - tmp1 - zsq
+  lin(cx, y, t3, x, L_SUB); mul(cx, y, y, t4);                     // y' = (tmp3 - x') tmp4
+  lin(cx, t2, t2, -1, L_MUL8); lin(cx, y, y, t2, L_SUB);           // y' -= 8 tmp2
+  mul(cx, L + 1, t4, zs); lin(cx, L + 1, L + 1, -1, L_DBL); lin(cx, L + 1, L + 1, -1, L_NEG);   // -2 tmp4 zsq
+  sqr(cx, L + 2, L + 2); kcomb(cx, L + 2, L + 2, t0, t5, -1, K_PLAIN);                          // tmp6^2 - tmp0 - tmp5
+  lin(cx, t1, t1, -1, L_MUL4); lin(cx, L + 2, L + 2, t1, L_SUB);   // - 4 tmp1
+  mul(cx, L, z, zs); lin(cx, L, L, -1, L_DBL);                     // 2 z' zsq
+}
+
+// Alg. 27 mixed addition, miller_loop_native.rs:58-87.  t = 10 scratch slots.
+B381_DEV void zk_add_step(const Ctx& cx, int R, int Qs, int L, int t) {
+  const int x = R, y = R + 1, z = R + 2, qx = Qs, qy = Qs + 1;
+  const int zs = t, ys = t + 1, t0 = t + 2, t1 = t + 3, t2 = t + 4, t3 = t + 5, t4 = t + 6, t5 = t + 7, t6 = t + 8, t7 = t + 9;
+  sqr(cx, zs, z);
+  sqr(cx, ys, qy);
+  mul(cx, t0, zs, qx);
+  sqr_s(cx, t1, qy, z); kcomb(cx, t1, t1, ys, zs, -1, K_PLAIN); mul(cx, t1, t1, zs);
+  lin(cx, t2, t0, x, L_SUB);
+  sqr(cx, t3, t2);
+  lin(cx, t4, t3, -1, L_MUL4);
+  mul(cx, t5, t4, t2);
+  kcomb(cx, t6, t1, y, y, -1, K_PLAIN);                            // t6 = t1 - 2y
+  mul(cx, L + 2, t6, qx);                                          // t9
+  mul(cx, t7, t4, x);
+  sqr(cx, x, t6); kcomb(cx, x, x, t5, t7, -1, K_PLAIN); lin(cx, x, x, t7, L_SUB);   // x' = t6^2 - t5 - 2 t7
+  sqr_s(cx, z, z, t2); kcomb(cx, z, z, zs, t3, -1, K_PLAIN);       // z' = (z + t2)^2 - zs - t3
+  lin(cx, t7, t7, x, L_SUB); mul(cx, t7, t7, t6);                  // t8 = (t7 - x') t6
+  mul(cx, t0, y, t5); lin(cx, t0, t0, -1, L_DBL);                  // t0 = 2 y t5
+  lin(cx, y, t7, t0, L_SUB);                                       // y' = t8 - t0
+  sqr_s(cx, t0, qy, z); lin(cx, t0, t0, ys, L_SUB);                // t10 = (qy + z')^2 - ysq
+  sqr(cx, t1, z); lin(cx, t0, t0, t1, L_SUB);                      // t10 -= z'^2
+  lin(cx, L + 2, L + 2, t0, L_2A_MB);                              // t9 = 2 t9 - t10
+  lin(cx, L, z, -1, L_DBL);                                        // t10 = 2 z'
+  lin(cx, L + 1, t6, -1, L_DBL); lin(cx, L + 1, L + 1, -1, L_NEG); // t1 = -2 t6
+}
+
+// miller_loop_native.rs:139-152: c0 *= py; c1 *= px; f.mul_by_014(coeffs.2, c1, c0)
+B381_DEV B381_INL void zk_ell(const Ctx& cx, int f, int L, int Pt, int t) {
+  f2_mulfp(S_(L), S_(L), S_(Pt), 1);
+  f2_mulfp(S_(L + 1), S_(L + 1), S_(Pt), 0);
+  f12_mul_by_014(cx, f, L + 2, L + 1, L, t);
+}
+
+// driver miller_loop_native.rs:89-116
+B381_DEV void zk_miller_loop(const Ctx& cx, const MillerSlots& s) {
+  f12_set_one(cx, s.f);
+  lin(cx, s.R, s.Q, -1, L_COPY);
+  lin(cx, s.R + 1, s.Q + 1, -1, L_COPY);
+  f2_set_small(S_(s.R + 2), 1);
+  const uint64_t xh = B381_X_ABS >> 1;
+  bool found_one = false;
+  for (int b = 63; b >= 0; b--) {
+    bool bit = (xh >> b) & 1;
+    if (!found_one) { found_one = bit; continue; }
+    zk_double_step(cx, s.R, s.L, s.T);
+    zk_ell(cx, s.f, s.L, s.P, s.T);
+    if (bit) {
+      zk_add_step(cx, s.R, s.Q, s.L, s.T);
+      zk_ell(cx, s.f, s.L, s.P, s.T);
+    }
+    f12_sqr(cx, s.f, s.T);
+  }
+  zk_double_step(cx, s.R, s.L, s.T);
+  zk_ell(cx, s.f, s.L, s.P, s.T);
+  f12_conj(cx, s.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// final exponentiation f -> f^(3 (p^12 - 1)/r): ark Bls12::final_exponentiation chain
+// (same exponent as the zkcrypto chain at
+// /root/reference/src/fields_as_trees/miller_loop.rs:128-178).  In place on f.
+// y0, y1, y2, r2 = four Fp12 scratch values (6 slots each); t = 16 scratch slots.
+// ---------------------------------------------------------------------------------------------
+struct FexpSlots { int f, y0, y1, y2, r, acc, T; };
+
+B381_DEV void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
+  const int f = s.f, y0 = s.y0, y1 = s.y1, y2 = s.y2, r = s.r, acc = s.acc, T = s.T;
+  // easy part: r = f^((p^6-1)(p^2+1))
+  f12_copy(cx, r, f);
+  f12_conj(cx, r);                                // f1 = conj(f)
+  f12_inv(cx, f, T);                              // f2 = f^-1
+  f12_mul(cx, r, r, f, T);                        // r = f1 f2
+  f12_copy(cx, f, r);                             // f2 = r
+  f12_frobenius(cx, r, 2);
+  f12_mul(cx, r, r, f, T);
+  // hard part
+  f12_copy(cx, y0, r); f12_cyclotomic_square(cx, y0, T);            // y0 = r^2
+  f12_exp_by_x(cx, y1, r, acc, T);                                       // y1 = r^x
+  f12_copy(cx, y2, r); f12_conj(cx, y2);                            // y2 = r^-1
+  f12_mul(cx, y1, y1, y2, T);
+  f12_exp_by_x(cx, y2, y1, acc, T);
+  f12_conj(cx, y1);
+  f12_mul(cx, y1, y1, y2, T);
+  f12_exp_by_x(cx, y2, y1, acc, T);
+  f12_frobenius(cx, y1, 1);
+  f12_mul(cx, y1, y1, y2, T);
+  f12_mul(cx, r, r, y0, T);
+  f12_exp_by_x(cx, y0, y1, acc, T);
+  f12_exp_by_x(cx, y2, y0, acc, T);
+  f12_copy(cx, y0, y1); f12_frobenius(cx, y0, 2);
+  f12_conj(cx, y1);
+  f12_mul(cx, y1, y1, y2, T);
+  f12_mul(cx, y1, y1, y0, T);
+  f12_mul(cx, f, r, y1, T);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LITERAL mode: /root/reference/src/miller_loop_native_optimized.rs:8-127 exactly as written
+// (everything in Fq2; Jacobian coordinates fed to a homogeneous line formula; one squaring as
+// "final exponentiation").  Slots: R (3), Q (3), P (x,y | z,-) in 2 slots as Fq2-embedded Fp,
+// fn, fd, n, d, and t = 8 scratch slots.  Returns false where the reference panics (f_den = 0).
+// ---------------------------------------------------------------------------------------------
+struct LiteralSlots { int R, Q, Pp, fn, fd, n, d, T; };   // Pp: 3 slots xp, yp, zp as Fq2 (c1 = 0)
+
+// ark-ec 0.4 Projective::double_in_place (a = 0, dbl-2009-l); t = 5 scratch
+B381_DEV void jac_double(const Ctx& cx, int R, int t) {
+  const int X = R, Y = R + 1, Z = R + 2, A = t, B = t + 1, C = t + 2, D = t + 3, E = t + 4;
+  if (f2_is_zero(S_(Z))) return;
+  sqr(cx, A, X);
+  sqr(cx, B, Y);
+  sqr(cx, C, B);
+  sqr_s(cx, D, X, B); kcomb(cx, D, D, A, C, -1, K_PLAIN); lin(cx, D, D, -1, L_DBL);
+  lin(cx, E, A, -1, L_TRIPLE);
+  mul(cx, Z, Y, Z); lin(cx, Z, Z, -1, L_DBL);                      // Z3 = 2 Y Z
+  sqr(cx, X, E); kcomb(cx, X, X, D, D, -1, K_PLAIN);               // X3 = E^2 - 2D
+  lin(cx, D, D, X, L_SUB); mul(cx, Y, E, D);                       // E (D - X3)
+  lin(cx, C, C, -1, L_MUL8); lin(cx, Y, Y, C, L_SUB);              // - 8C
+}
+
+// ark-ec 0.4 Projective += Projective (add-2007-bl); result in R1.  t = 9 scratch
+B381_DEV void jac_add(const Ctx& cx, int R1, int R2, int t) {
+  const int X1 = R1, Y1 = R1 + 1, Z1 = R1 + 2, X2 = R2, Y2 = R2 + 1, Z2 = R2 + 2;
+  const int z1z1 = t, z2z2 = t + 1, u1 = t + 2, u2 = t + 3, s1 = t + 4, s2 = t + 5, h = t + 6, i = t + 7, j = t + 8;
+  if (f2_is_zero(S_(Z1))) { for (int k = 0; k < 3; k++) lin(cx, R1 + k, R2 + k, -1, L_COPY); return; }
+  if (f2_is_zero(S_(Z2))) return;
+  sqr(cx, z1z1, Z1);
+  sqr(cx, z2z2, Z2);
+  mul(cx, u1, X1, z2z2);
+  mul(cx, u2, X2, z1z1);
+  mul(cx, s1, Y1, Z2); mul(cx, s1, s1, z2z2);
+  mul(cx, s2, Y2, Z1); mul(cx, s2, s2, z1z1);
+  if (f2_equal(S_(u1), S_(u2)) && f2_equal(S_(s1), S_(s2))) { jac_double(cx, R1, t); return; }
+  lin(cx, h, u2, u1, L_SUB);
+  lin(cx, i, h, -1, L_DBL); sqr(cx, i, i);
+  mul(cx, j, h, i);
+  lin(cx, s2, s2, s1, L_SUB); lin(cx, s2, s2, -1, L_DBL);          // r = 2 (S2 - S1)
+  mul(cx, u1, u1, i);                                              // V = U1 I
+  sqr_s(cx, Z1, Z1, Z2); kcomb(cx, Z1, Z1, z1z1, z2z2, -1, K_PLAIN); mul(cx, Z1, Z1, h);   // Z3
+  sqr(cx, X1, s2); kcomb(cx, X1, X1, j, u1, -1, K_PLAIN); lin(cx, X1, X1, u1, L_SUB);      // X3 = r^2 - J - 2V
+  lin(cx, u1, u1, X1, L_SUB); mul(cx, u1, s2, u1);                 // r (V - X3)
+  mul(cx, s1, s1, j); lin(cx, s1, s1, -1, L_DBL);                  // 2 S1 J
+  lin(cx, Y1, u1, s1, L_SUB);
+}
+
+// optimized_line_function (:8-78): (n, d) for the line through Q1, Q2 at P.  t = 6 scratch
+B381_DEV void literal_line(const Ctx& cx, int Q1, int Q2, int Pp, int n, int d, int t) {
+  const int x1 = Q1, y1 = Q1 + 1, z1 = Q1 + 2, x2 = Q2, y2 = Q2 + 1, z2 = Q2 + 2, xp = Pp, yp = Pp + 1, zp = Pp + 2;
+  const int num = t, den = t + 1, A = t + 2, B = t + 3, w = t + 4, w2 = t + 5;
+  mul(cx, A, xp, z1); mul(cx, w, x1, zp); lin(cx, A, A, w, L_SUB);
+  mul(cx, B, yp, z1); mul(cx, w, y1, zp); lin(cx, B, B, w, L_SUB);
+  bool den_zero = true, num_zero = true;           // Q1 == Q2 (same object): both differences are 0
+  if (Q1 != Q2) {
+    mul(cx, num, y2, z1); mul(cx, w, y1, z2); lin(cx, num, num, w, L_SUB);
+    mul(cx, den, x2, z1); mul(cx, w, x1, z2); lin(cx, den, den, w, L_SUB);
+    den_zero = f2_is_zero(S_(den));
+    num_zero = den_zero && f2_is_zero(S_(num));
+  }
+  if (den_zero && !num_zero) {                     // vertical line
+    lin(cx, n, A, -1, L_COPY);
+    mul(cx, d, z1, zp);
+    return;
+  }
+  if (den_zero) {                                  // tangent
+    sqr(cx, num, x1); lin(cx, num, num, -1, L_TRIPLE);             // 3 x1^2  (= Fq2::from(3) * x1 * x1)
+    mul(cx, den, y1, z1); lin(cx, den, den, -1, L_DBL);            // 2 y1 z1
+  }
+  mul(cx, w, num, A); mul(cx, w2, den, B); lin(cx, n, w, w2, L_SUB);
+  mul(cx, d, den, zp); mul(cx, d, d, z1);
+}
+
+B381_DEV bool literal_optimized_miller_loop(const Ctx& cx, const LiteralSlots& s, int out /* slot for c0.c0 */) {
+  for (int k = 0; k < 3; k++) lin(cx, s.R + k, s.Q + k, -1, L_COPY);
+  f2_set_small(S_(s.fn), 1);
+  f2_set_small(S_(s.fd), 1);
+  const uint64_t xabs = B381_X_ABS;
+  for (int v = 0; v < 64; v++) {                   // PSEUDO_BINARY_ENCODING, forward (LSB first)
+    literal_line(cx, s.R, s.R, s.Pp, s.n, s.d, s.T);
+    sqr(cx, s.fn, s.fn); mul(cx, s.fn, s.fn, s.n);
+    sqr(cx, s.fd, s.fd); mul(cx, s.fd, s.fd, s.d);
+    jac_double(cx, s.R, s.T);                      // R + R: ark's add detects U1==U2 && S1==S2 -> double
+    if ((xabs >> v) & 1) {
+      literal_line(cx, s.R, s.Q, s.Pp, s.n, s.d, s.T);
+      mul(cx, s.fn, s.fn, s.n);
+      mul(cx, s.fd, s.fd, s.d);
+      jac_add(cx, s.R, s.Q, s.T);
+    }
+  }
+  if (f2_is_zero(S_(s.fd))) return false;
+  f2_inv(S_(s.fd), S_(s.fd));
+  mul(cx, out, s.fn, s.fd);
+  sqr(cx, out, out);
+  return true;
+}
+
+#undef S_
+
+}  // namespace b381

@@ -1,0 +1,146 @@
+// hostsim.cpp -- TEST-ONLY host build of the device arithmetic (fp28.cuh / tower.cuh / programs.cuh).
+// The CUDA sources are plain C++ (no inline PTX), so compiling them with g++ gives a bit-exact
+// simulation of what every GPU thread computes.  tests/ use it on the CPU box to check the device
+// algorithms against the oracle without a GPU, and (built with -DB381_TRACK_BOUNDS) to verify the
+// worst-case limb / column / magnitude bounds of the lazy arithmetic along the executed path.
+// It is NOT part of the product: libb381.so never links or loads it.
+#include <cstring>
+#include "../../plonky2-bls12-381-pairing_b200/csrc/programs.cuh"
+
+using namespace b381;
+
+static thread_local u4 g_arena[(MAX_NSLOTS + 8) * GPS];
+
+static Ctx make_ctx() {
+  Ctx cx;
+  cx.sm = g_arena;
+  cx.gm = g_arena + NS * SLOT;
+#ifdef B381_TRACK_BOUNDS
+  track_tab().clear();
+#endif
+  return cx;
+}
+
+extern "C" {
+
+int hs_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  // Montgomery product in the external domain: out = a * b / 2^384, via internal conversion
+  uint32_t wa[12], wb[12], wo[12];
+  memcpy(wa, a, 48); memcpy(wb, b, 48);
+  Fp x, y, z;
+  bool ok = fp_from_ext(x, wa);
+  ok &= fp_from_ext(y, wb);
+  fp_mul(z, x, y);
+  fp_to_ext(wo, z);
+  memcpy(out, wo, 48);
+  return ok ? 0 : 1;
+}
+
+int hs_fp_roundtrip(const uint32_t* a, uint32_t* out) {
+  uint32_t wa[12], wo[12];
+  memcpy(wa, a, 48);
+  Fp x;
+  bool ok = fp_from_ext(x, wa);
+  fp_to_ext(wo, x);
+  memcpy(out, wo, 48);
+  return ok ? 0 : 1;
+}
+
+int hs_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f2_load_ext(slot(cx, 0), a);
+  ok &= f2_load_ext(slot(cx, 1), b);
+  f2_mul(slot(cx, 2), slot(cx, 0), slot(cx, 1));
+  f2_store_ext(out, slot(cx, 2));
+  return ok ? 0 : 1;
+}
+
+int hs_fp2_inv(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f2_load_ext(slot(cx, 0), a);
+  f2_inv(slot(cx, 1), slot(cx, 0));
+  f2_store_ext(out, slot(cx, 1));
+  return ok ? 0 : 1;
+}
+
+int hs_fp12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_mul(cx, a, b, out); }
+int hs_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out) { Ctx cx = make_ctx(); return prog_wbasis_mul(cx, a, b, out); }
+
+int hs_fp12_sqr(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, 0, a);
+  f12_sqr(cx, 0, 6);
+  f12_store_ext(cx, out, 0);
+  return ok ? 0 : 1;
+}
+
+int hs_fp12_inv(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, 0, a);
+  f12_inv(cx, 0, 6);
+  f12_store_ext(cx, out, 0);
+  return ok ? 0 : 1;
+}
+
+int hs_fp12_frobenius(const uint32_t* a, int k, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, 0, a);
+  f12_frobenius(cx, 0, k);
+  f12_store_ext(cx, out, 0);
+  return ok ? 0 : 1;
+}
+
+int hs_fp12_cyclotomic_square(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, 0, a);
+  f12_cyclotomic_square(cx, 0, 6);
+  f12_store_ext(cx, out, 0);
+  return ok ? 0 : 1;
+}
+
+int hs_fp12_mul_by_014(const uint32_t* f, const uint32_t* c0, const uint32_t* c1, const uint32_t* c4, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, 0, f);
+  ok &= f2_load_ext(slot(cx, 6), c0);
+  ok &= f2_load_ext(slot(cx, 7), c1);
+  ok &= f2_load_ext(slot(cx, 8), c4);
+  f12_mul_by_014(cx, 0, 6, 7, 8, 9);
+  f12_store_ext(cx, out, 0);
+  return ok ? 0 : 1;
+}
+
+int hs_miller_loop(const uint32_t* g1, const uint32_t* g2, int inf, uint32_t* out, int mode) { Ctx cx = make_ctx(); return prog_miller(cx, g1, g2, inf, out, mode); }
+int hs_final_exp(const uint32_t* in, uint32_t* out) { Ctx cx = make_ctx(); return prog_final_exp(cx, in, out); }
+int hs_pairing(const uint32_t* g1, const uint32_t* g2, int inf, uint32_t* out, int mode) { Ctx cx = make_ctx(); return prog_pairing(cx, g1, g2, inf, out, mode); }
+int hs_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out) { Ctx cx = make_ctx(); return prog_literal(cx, g1p, g2p, out); }
+
+// product of n Miller values (raw path used by multi_pairing): returns external format
+int hs_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, uint32_t* out, int mode) {
+  Ctx cx = make_ctx();
+  int err = 0;
+  f12_set_one(cx, ML_ACC);
+  for (size_t i = 0; i < n; i++) {
+    err |= miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, mode);
+    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);
+  }
+  f12_store_ext(cx, out, ML_ACC);
+  return err;
+}
+
+int hs_tracking(void) {
+#ifdef B381_TRACK_BOUNDS
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+}  // extern "C"
+
+extern "C" int hs_fp12_exp_by_x(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, FE_F, a);
+  f12_exp_by_x(cx, FE_Y0, FE_F, FE_ACC, FE_T);
+  f12_store_ext(cx, out, FE_Y0);
+  return ok ? 0 : 1;
+}
