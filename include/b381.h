@@ -1,0 +1,108 @@
+/* b381.h -- C ABI of libb381.so: B200-native batched BLS12-381 pairing engine.
+ *
+ * Drop-in boundary for the native pairing path of NikolayKostadinov21/plonky2-bls12-381-pairing
+ * (citations relative to /root/reference).  The reference has no FFI; the boundary is its Rust
+ * `pub` surface, and each entry point below names the item it replaces.  A Rust (or ctypes)
+ * binding only marshals flat buffers -- see INTEGRATION.md.
+ *
+ * Data layout (identical to ark-ff 0.4 `Fp384` in memory, which is what the reference's types hold):
+ *   Fp    : 12 x uint32 little-endian limbs, Montgomery form with R = 2^384, fully reduced (< p)
+ *   Fp2   : c0, c1                                  (24 words)
+ *   Fp12  : c0.c0.c0, c0.c0.c1, c0.c1.c0, ... , c1.c2.c1   (144 words; tower order of
+ *           src/fields/helpers.rs:16-37)
+ *   MyFq12: coeffs[0..12] in the w-basis order of src/fields/helpers.rs:39-41 (144 words)
+ *   G1 affine: x, y (24 words);  G2 affine: x.c0, x.c1, y.c0, y.c1 (48 words)
+ *   G1/G2 projective (Jacobian, as ark-ec 0.4): x, y, z (36 / 72 words)
+ *   inf   : one byte per pair, bit0 = P is the identity, bit1 = Q is the identity (may be NULL)
+ *
+ * All functions return 0 on success, a negative B381_E_* code otherwise; they never throw or
+ * unwind.  Host-pointer functions are synchronous (H2D copy, kernels, D2H copy inside the call);
+ * `_dev` functions take device pointers, enqueue on `stream` (a cudaStream_t, may be NULL) and do
+ * not synchronise.  One process drives one GPU (the device given to b381_init); independent
+ * pairings shard across GPUs by giving each process a slice of the batch.
+ * There is NO CPU fallback: without a CUDA device every compute call fails with B381_E_CUDA.
+ */
+#ifndef B381_H
+#define B381_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* parity modes */
+#define B381_MODE_ARK 0      /* ark_bls12_381::Bls12_381::multi_miller_loop semantics (the truth the reference
+                                defers to: src/miller_loop_native_optimized.rs:131-132,151,163) */
+#define B381_MODE_ZK 1       /* the loop spelled out at src/miller_loop_native.rs:27-116 with ell (:139-152) wired in */
+#define B381_MODE_LITERAL 2  /* the code exactly as written: multi_miller_loop -> 1 (src/miller_loop_native.rs:163-188) */
+
+/* error codes */
+#define B381_OK 0
+#define B381_E_CUDA (-1)            /* CUDA runtime failure / no device; see b381_last_error() */
+#define B381_E_ARG (-2)             /* null pointer, n == 0, bad mode */
+#define B381_E_NOT_CANONICAL (-3)   /* an input limb vector is >= p (reference: Fq::from_bigint(..).unwrap() panics) */
+#define B381_E_ZERO_DIVISION (-4)   /* final_exponentiation(0) / LITERAL f_den == 0 (reference panics) */
+#define B381_E_NOT_INIT (-5)
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int b381_init(int device);                  /* bind this process to one GPU, allocate scratch */
+int b381_shutdown(void);
+const char* b381_last_error(void);
+int b381_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* scratch_bytes);
+/* number of kernels this library has launched since b381_init (bench.py reports it as gpu_launches) */
+unsigned long long b381_kernel_launches(void);
+
+/* field-op microbenchmarks (BASELINE config #2) -------------------------------------------------- */
+/* out[i] = a[i] * b[i] in Fq  -- replaces ark `Fq * Fq` as used at src/fields/helpers.rs:102-105 */
+int b381_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+/* out[i] = a[i] * b[i]^k (k dependent multiplications held in registers; pure integer-pipe number) */
+int b381_fp_mul_chain(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k);
+/* Fq2 product -- ark `Fq2 * Fq2` at src/miller_loop_native.rs:42,50,53 */
+int b381_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+/* Fq12 product in tower order -- ark `Fq12 * Fq12` at src/miller_loop_native_optimized.rs:91-99 */
+int b381_fp12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+/* MyFq12 product in w-basis order -- `impl Mul for MyFq12`, src/fields/helpers.rs:90-152 */
+int b381_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+
+/* Miller loop / final exponentiation / pairing ---------------------------------------------------- */
+/* batched variant: out[i] = miller_loop(P_i, Q_i), one Fq12 per pair.  Identity pairs give 1. */
+int b381_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode);
+/* multi_miller_loop(&[(&G1Affine,&G2Affine)]) -> MillerLoopResult, src/miller_loop_native.rs:154-212:
+   ONE Fq12 = product over the n terms (ARK/ZK), or 1 (LITERAL, the code as written). */
+int b381_multi_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode);
+/* final exponentiation f^(3 (p^12-1)/r) -- ark Bls12::final_exponentiation; algorithm spec
+   src/fields_as_trees/miller_loop.rs:128-178; the native stub it completes is
+   src/miller_loop_native_optimized.rs:104-121 */
+int b381_final_exp(const uint32_t* f, uint32_t* out, size_t n);
+/* out[i] = final_exp(miller_loop(P_i, Q_i)) fused in one kernel (no HBM round trip of the Miller value) */
+int b381_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode);
+/* final_exp(multi_miller_loop(...)): the BLS batch-verify shape, one Fq12 out */
+int b381_multi_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode);
+/* product of n Fq12 values (used to combine per-GPU partial products after an all-gather) */
+int b381_fp12_product(const uint32_t* in, uint32_t* out144, size_t n);
+/* optimized_miller_loop(G1Projective, G2Projective) -> Fq12, src/miller_loop_native_optimized.rs:81-127,
+   exactly as written (LITERAL): only c0.c0 of the output is non-zero. */
+int b381_literal_optimized(const uint32_t* g1proj, const uint32_t* g2proj, uint32_t* out, size_t n);
+
+/* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
+int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);
+int b381_final_exp_dev(const uint32_t* f, uint32_t* out, size_t n, void* stream);
+int b381_pairing_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);
+int b381_multi_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, void* stream);
+int b381_fp_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
+int b381_fp_mul_chain_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k, void* stream);
+int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
+int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
+/* fetch-and-clear the device error word after synchronising `stream`; returns 0 or a B381_E_* code */
+int b381_check_dev(void* stream);
+
+/* integer-multiply roofline probe: sustained IMAD.WIDE issue rate of this GPU, in 1e9 thread-instructions/s,
+   and the SM clock (MHz) seen while it ran (the denominator of roofline.frac) */
+int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B381_H */

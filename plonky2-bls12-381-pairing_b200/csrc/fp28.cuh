@@ -235,6 +235,37 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
   B381_TB(r.mag = 1.0 + t.mag / 1.0e11 + 1e-9; r.lb = 1.0;)   // p / 2^420 * p^2 / p ~ 2^-39
 }
 
+// r = t / 2^384 mod p: Montgomery reduction in the EXTERNAL domain (R = 2^384), 13 full rows plus
+// one 20-bit row.  Used by the element-wise Fp / Fp2 multiply entry points, which then need no
+// domain conversion.  For canonical operands the result lies in (-p, 2p).
+B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
+  B381_CHECK(t.cb + 14.0 + 1.0 < 127.0, "acc_redc384: column overflow");
+  B381_CHECK(t.mag < 4.0, "acc_redc384: operands must be canonical");
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) {
+    uint32_t m = ((uint32_t)t.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
+#pragma unroll
+    for (int j = 0; j < NL; j++) t.c[i + j] += (int64_t)(int32_t)m * (int64_t)plimb(j);
+    t.c[i + 1] += t.c[i] >> W;
+  }
+  {
+    uint32_t m = ((uint32_t)t.c[NL - 1] * (uint32_t)B381_N0P) & 0xfffffu;
+#pragma unroll
+    for (int j = 0; j < NL; j++) t.c[NL - 1 + j] += (int64_t)(int32_t)m * (int64_t)plimb(j);
+  }
+  int32_t d[NL + 1];
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    d[k] = (int32_t)t.c[NL - 1 + k] & MASK;
+    t.c[NL + k] += t.c[NL - 1 + k] >> W;
+  }
+  d[NL] = (int32_t)t.c[2 * NL - 1];
+#pragma unroll
+  for (int k = 0; k < NL - 1; k++) r.l[k] = (d[k] >> 20) | ((d[k + 1] & 0xfffff) << 8);
+  r.l[NL - 1] = (d[NL - 1] >> 20) + (d[NL] << 8);
+  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = 1.0;)
+}
+
 B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
   Acc t;
   acc_zero(t);

@@ -1,0 +1,786 @@
+// kernels.cu -- CUDA kernels (sm_100a) and the C ABI of libb381.so (include/b381.h).
+//
+// Execution model.  One pairing per thread.  The tower kernels are PERSISTENT: one CTA of
+// B381_BLOCK threads per SM (grid = min(batches, #SM)), each CTA loops over batches of
+// B381_BLOCK pairings.  Per-thread state is an arena of Fp2 slots: the hot 16 slots in shared
+// memory (224 KB per CTA, word-interleaved so every LDS.128/STS.128 is conflict-free), the cold
+// slots in a per-CTA global scratch region that stays L2-resident because only #SM CTAs exist.
+// The arithmetic (fp28.cuh) is carry-free IMAD.WIDE column accumulation; see DESIGN.md.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b381.h"
+#include "programs.cuh"
+
+using namespace b381;
+
+namespace {
+
+constexpr int BLOCK = B381_BLOCK;
+constexpr int NG_SLOTS = MAX_NSLOTS - NS;                               // cold slots per thread
+constexpr size_t SMEM_BYTES = (size_t)NS * GPS * sizeof(u4) * BLOCK;    // 16*7*16*128 = 224 KB
+constexpr size_t GARENA_U4_PER_CTA = (size_t)NG_SLOTS * GPS * BLOCK;
+constexpr int RAW_WORDS = 6 * 28;                                       // internal-format Fp12
+
+__device__ __forceinline__ Ctx make_ctx(u4* garena) {
+  extern __shared__ u4 smem[];
+  Ctx cx;
+  cx.sm = smem + threadIdx.x;
+  cx.gm = garena + (size_t)blockIdx.x * GARENA_U4_PER_CTA + threadIdx.x;
+  return cx;
+}
+
+__device__ __forceinline__ void report(int e, int* err) {
+  if (e) atomicOr(err, e);
+}
+
+// ---- tower kernels (persistent, one CTA per SM) ---------------------------------------------------
+__global__ void __launch_bounds__(BLOCK, 1)
+k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) report(prog_miller(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, out + 144 * i, mode), err);
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 1)
+k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) report(prog_final_exp(cx, in + 144 * i, out + 144 * i), err);
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 1)
+k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) report(prog_pairing(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, out + 144 * i, mode), err);
+  }
+}
+
+// every thread multiplies the Miller values of its pairs into a private accumulator and dumps it
+// (internal format) to partial[global thread id]
+__global__ void __launch_bounds__(BLOCK, 1)
+k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  f12_set_one(cx, ML_ACC);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) {
+      report(miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, mode), err);
+      f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);      // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
+    }
+  }
+  f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), ML_ACC);
+}
+
+// out[j] = product of in[j*K .. min((j+1)K, n_in))   (internal format)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_f12_reduce_raw(const uint32_t* in, size_t n_in, uint32_t* out, size_t n_out, int K, u4* garena) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n_out; base += (size_t)gridDim.x * BLOCK) {
+    size_t j = base + threadIdx.x;
+    if (j < n_out) {
+      size_t lo = j * (size_t)K, hi = lo + K < n_in ? lo + K : n_in;
+      prog_f12_product_raw(cx, in + lo * RAW_WORDS, hi - lo, RAW_WORDS, out + j * RAW_WORDS);
+    }
+  }
+}
+
+// external -> internal dump (for b381_fp12_product) and internal -> external (optionally via final exp)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_ext_to_raw(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) {
+      if (!f12_load_ext(cx, 0, in + 144 * i)) report(ERR_NOT_CANONICAL, err);
+      f12_store_raw(cx, out + i * RAW_WORDS, 0);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 1)
+k_raw_finish(const uint32_t* in_raw, uint32_t* out_ext, int do_final_exp, u4* garena, int* err) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Ctx cx = make_ctx(garena);
+  f12_load_raw(cx, FE_F, in_raw);
+  if (do_final_exp) report(final_exp_slots(cx, FE_F), err);
+  f12_store_ext(cx, out_ext, FE_F);
+}
+
+__global__ void __launch_bounds__(BLOCK, 1)
+k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) {
+      if (wbasis) report(prog_wbasis_mul(cx, a + 144 * i, b + 144 * i, out + 144 * i), err);
+      else report(prog_f12_mul(cx, a + 144 * i, b + 144 * i, out + 144 * i), err);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, 1)
+k_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out, size_t n, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) report(prog_literal(cx, g1p + 36 * i, g2p + 72 * i, out + 144 * i), err);
+  }
+}
+
+__global__ void k_fill_one_ext(uint32_t* out144) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t one[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                              0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};  // 2^384 mod p
+    for (int k = 0; k < 144; k++) out144[k] = k < 12 ? one[k] : 0;
+  }
+}
+
+// ---- register-only element-wise kernels (no arena) -------------------------------------------------
+__device__ __forceinline__ bool load_canon(Fp& x, const uint32_t* src) {
+  uint32_t w[12];
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
+  w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+  w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+  fp_unpack32(x, w);
+  Fp t;
+#pragma unroll
+  for (int k = 0; k < NL; k++) t.l[k] = x.l[k] - plimb(k);
+  fp_carry_exact(t);
+  return (t.l[NL - 1] >> 31) != 0;
+}
+
+__device__ __forceinline__ void store_canon(uint32_t* dst, Fp& x) {   // x in (-p, 2p)
+  fp_canon_small(x);
+  uint32_t w[12];
+  fp_pack32(w, x);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  d4[2] = make_uint4(w[8], w[9], w[10], w[11]);
+}
+
+__global__ void __launch_bounds__(256)
+k_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* err) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fp x, y, r;
+    bool ok = load_canon(x, a + 12 * i);
+    ok &= load_canon(y, b + 12 * i);
+    if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
+    Acc t;
+    acc_zero(t);
+    acc_mac(t, x, y);
+    acc_redc384(r, t);
+    store_canon(out + 12 * i, r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_fp_mul_chain(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k, int* err) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t wa[12], wb[12], wo[12];
+    for (int j = 0; j < 12; j++) { wa[j] = a[12 * i + j]; wb[j] = b[12 * i + j]; }
+    Fp x, y;
+    bool ok = fp_from_ext(x, wa);
+    ok &= fp_from_ext(y, wb);
+    if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
+    for (int s = 0; s < k; s++) {
+      Fp t;
+      fp_mul(t, x, y);
+      x = t;
+    }
+    fp_to_ext(wo, x);
+    for (int j = 0; j < 12; j++) out[12 * i + j] = wo[j];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* err) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fp a0, a1, b0, b1, r0, r1;
+    bool ok = load_canon(a0, a + 24 * i);
+    ok &= load_canon(a1, a + 24 * i + 12);
+    ok &= load_canon(b0, b + 24 * i);
+    ok &= load_canon(b1, b + 24 * i + 12);
+    if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
+    Acc A, B, T;
+    acc_zero(A); acc_mac(A, a0, b0);
+    acc_zero(B); acc_mac(B, a1, b1);
+    acc_sub(T, A, B);
+    acc_redc384(r0, T);
+    Fp sa, sb;
+    fp_add(sa, a0, a1);
+    fp_add(sb, b0, b1);
+    acc_add(T, A, B);
+    acc_neg(T, T);
+    acc_mac(T, sa, sb);
+    acc_redc384(r1, T);
+    store_canon(out + 24 * i, r0);
+    store_canon(out + 24 * i + 12, r1);
+  }
+}
+
+// integer-pipe roofline probe: independent IMAD.WIDE chains, all SMs, register only
+__global__ void __launch_bounds__(1024)
+k_imad_peak(uint32_t* out, const uint32_t* in, unsigned long long* cyc, int iters) {
+  uint32_t a = in[threadIdx.x & 31], b = in[32 + (threadIdx.x & 31)];
+  unsigned long long d[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) d[j] = in[64 + j] + threadIdx.x;
+  __syncthreads();
+  unsigned long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(d[j]) : "r"(a), "r"(b));
+    }
+  }
+  unsigned long long t1 = clock64();
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= d[j];
+  if (s == 0x12345678ull) out[threadIdx.x] = (uint32_t)s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+struct State {
+  bool init = false;
+  int device = -1;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  u4* garena[2] = {nullptr, nullptr};
+  int* d_err = nullptr;
+  uint32_t* d_in1[2] = {nullptr, nullptr};      // staging (device) per lane
+  uint32_t* d_in2[2] = {nullptr, nullptr};
+  uint8_t* d_inf[2] = {nullptr, nullptr};
+  uint32_t* d_out[2] = {nullptr, nullptr};
+  size_t cap_in1 = 0, cap_in2 = 0, cap_inf = 0, cap_out = 0;   // bytes per lane
+  uint32_t* d_partial[2] = {nullptr, nullptr};  // raw partial products for multi_miller
+  unsigned long long launches = 0;
+  std::string last_error;
+  std::mutex mu;
+};
+State g;
+
+int fail_cuda(cudaError_t e, const char* what) {
+  g.last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return B381_E_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, #x); } while (0)
+
+int fail_arg(const char* what) {
+  g.last_error = what;
+  return B381_E_ARG;
+}
+
+int map_err(int bits) {
+  if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
+  if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0) or f_den == 0)"; return B381_E_ZERO_DIVISION; }
+  return B381_OK;
+}
+
+int grid_for(size_t n) {
+  size_t batches = (n + BLOCK - 1) / BLOCK;
+  return (int)(batches < (size_t)g.sm_count ? batches : (size_t)g.sm_count);
+}
+
+template <typename K>
+int set_smem(K kernel) {
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  return 0;
+}
+
+
+int grow(uint32_t** p0, uint32_t** p1, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p0) cudaFree(*p0);
+  if (*p1) cudaFree(*p1);
+  *p0 = *p1 = nullptr; *cap = 0;
+  CU(cudaMalloc((void**)p0, need));
+  CU(cudaMalloc((void**)p1, need));
+  *cap = need;
+  return 0;
+}
+
+int read_err(cudaStream_t s) {
+  int h = 0;
+  CU(cudaMemcpyAsync(&h, g.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (h) CU(cudaMemsetAsync(g.d_err, 0, sizeof(int), s));
+  return map_err(h);
+}
+
+constexpr size_t CHUNK = 1u << 17;    // pairs per pipelined chunk of the host-pointer API
+
+// launch helpers (device pointers) ----------------------------------------------------------------------
+int launch_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
+  k_miller<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+int launch_final_exp(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t s, int lane) {
+  k_final_exp<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(in, out, n, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+int launch_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
+  k_pairing<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// raw tree reduction of `cnt` partials living in buf (ping) using pong; returns pointer to the single result
+int reduce_raw(uint32_t* ping, uint32_t* pong, size_t cnt, cudaStream_t s, int lane, uint32_t** result) {
+  const int K = 16;
+  while (cnt > 1) {
+    size_t n_out = (cnt + K - 1) / K;
+    k_f12_reduce_raw<<<grid_for(n_out), BLOCK, SMEM_BYTES, s>>>(ping, cnt, pong, n_out, K, g.garena[lane]);
+    g.launches++;
+    CU(cudaGetLastError());
+    uint32_t* t = ping; ping = pong; pong = t;
+    cnt = n_out;
+  }
+  *result = ping;
+  return 0;
+}
+
+// product of all Miller values of device-resident pairs -> out144 (device, external format), optional final exp
+int launch_multi(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe, cudaStream_t s, int lane) {
+  if (mode == B381_MODE_LITERAL) {                 // the reference's multi_miller_loop as written returns 1
+    k_fill_one_ext<<<1, 32, 0, s>>>(out144);
+    g.launches++;
+    CU(cudaGetLastError());
+    if (do_fe) { int rc = launch_final_exp(out144, out144, 1, s, lane); if (rc) return rc; }
+    return 0;
+  }
+  int grid = grid_for(n);
+  size_t nthreads = (size_t)grid * BLOCK;
+  uint32_t* ping = g.d_partial[lane];
+  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
+  k_multi_miller<<<grid, BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, n, mode, ping, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  uint32_t* res = nullptr;
+  int rc = reduce_raw(ping, pong, nthreads, s, lane, &res);
+  if (rc) return rc;
+  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, out144, do_fe, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+bool bad_mode(int mode) { return mode != B381_MODE_ARK && mode != B381_MODE_ZK && mode != B381_MODE_LITERAL; }
+
+#define REQUIRE_INIT() do { if (!g.init) { g.last_error = "b381_init not called"; return B381_E_NOT_INIT; } } while (0)
+
+// host-pointer pipelines --------------------------------------------------------------------------------
+enum PairKind { PK_MILLER, PK_PAIRING };
+
+int host_pairs(PairKind kind, const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  size_t c = n < CHUNK ? n : CHUNK;
+  int rc;
+  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * 24 * 4))) return rc;
+  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * 48 * 4))) return rc;
+  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * 144 * 4))) return rc;
+  if (inf) {
+    if (c > g.cap_inf) {
+      for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
+      g.cap_inf = 0;
+      for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
+      g.cap_inf = c;
+    }
+  }
+  int lane = 0;
+  for (size_t off = 0; off < n; off += CHUNK, lane ^= 1) {
+    size_t m = n - off < CHUNK ? n - off : CHUNK;
+    cudaStream_t s = g.stream[lane];
+    CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, s));
+    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, s));
+    const uint8_t* dinf = inf ? g.d_inf[lane] : nullptr;
+    if (kind == PK_MILLER) rc = launch_miller(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, s, lane);
+    else rc = launch_pairing(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, s, lane);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out + off * 144, g.d_out[lane], m * 144 * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(g.stream[1]));
+  return read_err(g.stream[0]);
+}
+
+// generic element-wise host pipeline: two inputs of wi words, one output of wo words per element
+template <typename L>
+int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, size_t wa, size_t wb, size_t wo, size_t chunk, L launch) {
+  size_t c = n < chunk ? n : chunk;
+  int rc;
+  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * wa * 4))) return rc;
+  if (b && (rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * wb * 4))) return rc;
+  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * wo * 4))) return rc;
+  int lane = 0;
+  for (size_t off = 0; off < n; off += chunk, lane ^= 1) {
+    size_t m = n - off < chunk ? n - off : chunk;
+    cudaStream_t s = g.stream[lane];
+    CU(cudaMemcpyAsync(g.d_in1[lane], a + off * wa, m * wa * 4, cudaMemcpyHostToDevice, s));
+    if (b) CU(cudaMemcpyAsync(g.d_in2[lane], b + off * wb, m * wb * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = launch(g.d_in1[lane], g.d_in2[lane], g.d_out[lane], m, s, lane))) return rc;
+    CU(cudaMemcpyAsync(out + off * wo, g.d_out[lane], m * wo * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(g.stream[1]));
+  return read_err(g.stream[0]);
+}
+
+int elem_grid(size_t n, int threads, int per_sm) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)g.sm_count * per_sm;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+int b381_init(int device) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.init) {
+    if (g.device == device) return B381_OK;
+    g.last_error = "already initialised on another device";
+    return B381_E_ARG;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g.last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb381 has no CPU fallback)";
+    return B381_E_CUDA;
+  }
+  if (device < 0 || device >= count) return fail_arg("device index out of range");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  g.device = device;
+  g.sm_count = prop.multiProcessorCount;
+  g.cc_major = prop.major;
+  g.cc_minor = prop.minor;
+  if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) {
+    g.last_error = "device lacks 224 KB opt-in shared memory per block (built for sm_100a)";
+    return B381_E_CUDA;
+  }
+  for (int l = 0; l < 2; l++) {
+    CU(cudaStreamCreateWithFlags(&g.stream[l], cudaStreamNonBlocking));
+    CU(cudaMalloc((void**)&g.garena[l], GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count));
+    CU(cudaMalloc((void**)&g.d_partial[l], 2 * (size_t)g.sm_count * BLOCK * RAW_WORDS * sizeof(uint32_t)));
+  }
+  CU(cudaMalloc((void**)&g.d_err, sizeof(int)));
+  CU(cudaMemset(g.d_err, 0, sizeof(int)));
+  int rc;
+  if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
+      (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
+      (rc = set_smem(k_literal)))
+    return rc;
+  CU(cudaDeviceSynchronize());
+  g.launches = 0;
+  g.init = true;
+  return B381_OK;
+}
+
+int b381_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.init) return B381_OK;
+  cudaDeviceSynchronize();
+  for (int l = 0; l < 2; l++) {
+    if (g.stream[l]) cudaStreamDestroy(g.stream[l]);
+    cudaFree(g.garena[l]); cudaFree(g.d_partial[l]);
+    cudaFree(g.d_in1[l]); cudaFree(g.d_in2[l]); cudaFree(g.d_inf[l]); cudaFree(g.d_out[l]);
+    g.stream[l] = nullptr; g.garena[l] = nullptr; g.d_partial[l] = nullptr;
+    g.d_in1[l] = g.d_in2[l] = g.d_out[l] = nullptr; g.d_inf[l] = nullptr;
+  }
+  cudaFree(g.d_err);
+  g.d_err = nullptr;
+  g.cap_in1 = g.cap_in2 = g.cap_inf = g.cap_out = 0;
+  g.init = false;
+  return B381_OK;
+}
+
+const char* b381_last_error(void) { return g.last_error.c_str(); }
+
+int b381_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* scratch_bytes) {
+  REQUIRE_INIT();
+  if (sm_count) *sm_count = g.sm_count;
+  if (cc_major) *cc_major = g.cc_major;
+  if (cc_minor) *cc_minor = g.cc_minor;
+  if (scratch_bytes) *scratch_bytes = 2 * GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count;
+  return B381_OK;
+}
+
+unsigned long long b381_kernel_launches(void) { return g.launches; }
+
+// ---- device-pointer API ---------------------------------------------------------------------------
+int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode)) return fail_arg("b381_miller_loop_dev: bad argument");
+  if (mode == B381_MODE_LITERAL) return fail_arg("LITERAL per-pair values: use b381_literal_optimized / b381_multi_miller_loop");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_miller(g1, g2, inf, out, n, mode, (cudaStream_t)stream, 0);
+}
+
+int b381_final_exp_dev(const uint32_t* f, uint32_t* out, size_t n, void* stream) {
+  REQUIRE_INIT();
+  if (!f || !out || n == 0) return fail_arg("b381_final_exp_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_final_exp(f, out, n, (cudaStream_t)stream, 0);
+}
+
+int b381_pairing_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_pairing(g1, g2, inf, out, n, mode, (cudaStream_t)stream, 0);
+}
+
+int b381_multi_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, void* stream) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_miller_loop_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_multi(g1, g2, inf, out144, n, mode, 0, (cudaStream_t)stream, 0);
+}
+
+int b381_fp_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp_mul_dev: bad argument");
+  k_fp_mul<<<elem_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b381_fp_mul_chain_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k, void* stream) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0 || k < 0) return fail_arg("b381_fp_mul_chain_dev: bad argument");
+  k_fp_mul_chain<<<elem_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, k, g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp2_mul_dev: bad argument");
+  k_fp2_mul<<<elem_grid(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(a, b, out, n, g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  k_f12_mul<<<grid_for(n), BLOCK, SMEM_BYTES, (cudaStream_t)stream>>>(a, b, out, n, 0, g.garena[0], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int b381_check_dev(void* stream) {
+  REQUIRE_INIT();
+  return read_err((cudaStream_t)stream);
+}
+
+// ---- host-pointer API -----------------------------------------------------------------------------
+int b381_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode)) return fail_arg("b381_miller_loop: bad argument");
+  if (mode == B381_MODE_LITERAL) return fail_arg("LITERAL per-pair values: use b381_literal_optimized / b381_multi_miller_loop");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_pairs(PK_MILLER, g1, g2, inf, out, n, mode);
+}
+
+int b381_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_pairs(PK_PAIRING, g1, g2, inf, out, n, mode);
+}
+
+int b381_final_exp(const uint32_t* f, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!f || !out || n == 0) return fail_arg("b381_final_exp: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(f, nullptr, out, n, 144, 0, 144, CHUNK,
+                     [](uint32_t* a, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) { return launch_final_exp(a, o, m, s, lane); });
+}
+
+static int multi_host(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe) {
+  // stage the whole batch (288 B per pair), run on lane 0
+  int rc;
+  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * 24 * 4))) return rc;
+  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, n * 48 * 4))) return rc;
+  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, 144 * 4))) return rc;
+  if (inf && n > g.cap_inf) {
+    for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
+    g.cap_inf = 0;
+    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], n));
+    g.cap_inf = n;
+  }
+  cudaStream_t s = g.stream[0];
+  CU(cudaMemcpyAsync(g.d_in1[0], g1, n * 24 * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(g.d_in2[0], g2, n * 48 * 4, cudaMemcpyHostToDevice, s));
+  if (inf) CU(cudaMemcpyAsync(g.d_inf[0], inf, n, cudaMemcpyHostToDevice, s));
+  if ((rc = launch_multi(g.d_in1[0], g.d_in2[0], inf ? g.d_inf[0] : nullptr, g.d_out[0], n, mode, do_fe, s, 0))) return rc;
+  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, s));
+  return read_err(s);
+}
+
+int b381_multi_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_miller_loop: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return multi_host(g1, g2, inf, out144, n, mode, 0);
+}
+
+int b381_multi_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_pairing: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return multi_host(g1, g2, inf, out144, n, mode, 1);
+}
+
+int b381_fp12_product(const uint32_t* in, uint32_t* out144, size_t n) {
+  REQUIRE_INIT();
+  if (!in || !out144 || n == 0) return fail_arg("b381_fp12_product: bad argument");
+  if (n > (size_t)g.sm_count * BLOCK) return fail_arg("b381_fp12_product: n too large (max sm_count * 128)");
+  std::lock_guard<std::mutex> lk(g.mu);
+  int rc;
+  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * 144 * 4))) return rc;
+  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, 144 * 4))) return rc;
+  cudaStream_t s = g.stream[0];
+  CU(cudaMemcpyAsync(g.d_in1[0], in, n * 144 * 4, cudaMemcpyHostToDevice, s));
+  uint32_t* ping = g.d_partial[0];
+  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
+  k_ext_to_raw<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g.d_in1[0], ping, n, g.garena[0], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  uint32_t* res = nullptr;
+  if ((rc = reduce_raw(ping, pong, n, s, 0, &res))) return rc;
+  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, g.d_out[0], 0, g.garena[0], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, s));
+  return read_err(s);
+}
+
+int b381_literal_optimized(const uint32_t* g1proj, const uint32_t* g2proj, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!g1proj || !g2proj || !out || n == 0) return fail_arg("b381_literal_optimized: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(g1proj, g2proj, out, n, 36, 72, 144, CHUNK,
+                     [](uint32_t* a, uint32_t* b, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                       k_literal<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(a, b, o, m, g.garena[lane], g.d_err);
+                       g.launches++;
+                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_literal");
+                     });
+}
+
+int b381_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp_mul: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(a, b, out, n, 12, 12, 12, (size_t)1 << 22,
+                     [](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp_mul_dev(x, y, o, m, s); });
+}
+
+int b381_fp_mul_chain(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0 || k < 0) return fail_arg("b381_fp_mul_chain: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(a, b, out, n, 12, 12, 12, (size_t)1 << 22,
+                     [k](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp_mul_chain_dev(x, y, o, m, k, s); });
+}
+
+int b381_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp2_mul: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(a, b, out, n, 24, 24, 24, (size_t)1 << 21,
+                     [](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp2_mul_dev(x, y, o, m, s); });
+}
+
+static int f12_mul_host(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis) {
+  return host_binary(a, b, out, n, 144, 144, 144, CHUNK,
+                     [wbasis](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                       k_f12_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, o, m, wbasis, g.garena[lane], g.d_err);
+                       g.launches++;
+                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_f12_mul");
+                     });
+}
+
+int b381_fp12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return f12_mul_host(a, b, out, n, 0);
+}
+
+int b381_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_wbasis: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return f12_mul_host(a, b, out, n, 1);
+}
+
+int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {
+  REQUIRE_INIT();
+  std::lock_guard<std::mutex> lk(g.mu);
+  const int threads = 1024, iters = 4096;
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  unsigned long long* d_cyc = nullptr;
+  CU(cudaMalloc((void**)&d_in, 4096 * 4));
+  CU(cudaMalloc((void**)&d_out, 4096 * 4));
+  CU(cudaMalloc((void**)&d_cyc, 1024 * 8));
+  std::vector<uint32_t> h(4096);
+  for (int i = 0; i < 4096; i++) h[i] = (0x9e3779b9u * (uint32_t)(i + 1)) | 1u;
+  CU(cudaMemcpy(d_in, h.data(), 4096 * 4, cudaMemcpyHostToDevice));
+  cudaStream_t s = g.stream[0];
+  k_imad_peak<<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, 256);
+  g.launches++;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, s));
+  k_imad_peak<<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, iters);
+  g.launches++;
+  CU(cudaEventRecord(e1, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<unsigned long long> hc(g.sm_count);
+  CU(cudaMemcpy(hc.data(), d_cyc, g.sm_count * 8, cudaMemcpyDeviceToHost));
+  double cavg = 0;
+  for (int i = 0; i < g.sm_count; i++) cavg += (double)hc[i];
+  cavg /= g.sm_count;
+  double inst = 16.0 * 8.0 * iters * threads * (double)g.sm_count;
+  if (imad_wide_ginst_per_s) *imad_wide_ginst_per_s = inst / (ms * 1e-3) / 1e9;
+  if (sm_mhz) *sm_mhz = cavg / (ms * 1e-3) / 1e6;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_cyc);
+  return B381_OK;
+}
+
+}  // extern "C"
