@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: full BLS12-381 pairings (Miller loop + final exponentiation) per
+second, BASELINE.json config #4 (2^20 pairs per GPU per step; independent pairings shard across GPUs
+with no collective => weak scaling), on N GPUs of one node, one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      CPU reference arm (oracle port on host cores)
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events on the launch
+stream, max over ranks); `e2e` = the same metric through the host-pointer C-ABI call
+(b381_pairing) with pinned host buffers, H2D and D2H inside the timed region.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP_MULS_MILLER = 6952          # oracle Fp-mul counter (tests/golden/pairing_vectors.json)
+FP_MULS_FINAL_EXP = 7675
+FP_MULS_PAIRING = FP_MULS_MILLER + FP_MULS_FINAL_EXP
+MACS_PER_FP_MUL = 300          # 2 n^2 + n 32x32->64 multiply-accumulates, n = 12; one IMAD.WIDE each
+PAIRS_PER_GPU = 1 << 20
+WORKLOAD = "config#4: full pairing (Miller loop + final exp, ARK mode), 2^20 pairs per GPU per step"
+
+
+def load_fixture():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pairs_256.npz"))
+    return z["g1"], z["g2"], z["pairing"]
+
+
+def tiled_inputs(n, seed):
+    g1, g2, pr = load_fixture()
+    perm = np.random.default_rng(seed).integers(0, 256, size=n)
+    return np.ascontiguousarray(g1[perm]).reshape(-1), np.ascontiguousarray(g2[perm]).reshape(-1), perm, pr
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_ref():
+    """the oracle's C port (the one place bench.py may execute oracle/): CPU baseline arm only."""
+    import __graft_entry__ as g
+    path = os.path.join(ROOT, "oracle", "_build", "libb381_ref.so")
+    if not os.path.exists(path):
+        g.build_oracle()
+    lib = ctypes.CDLL(path)
+    u32p, u8p = ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint8)
+    lib.ref_pairing.argtypes = [u32p, u32p, u8p, u32p, ctypes.c_size_t, ctypes.c_int]
+    return lib
+
+
+def cpu_pairing_rate(n_sample, threads, reps=1):
+    lib = load_ref()
+    g1, g2, perm, pr = tiled_inputs(n_sample, 7)
+    out = np.zeros(n_sample * 144, dtype=np.uint32)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        rc = lib.ref_pairing(g1.ctypes.data_as(u32p), g2.ctypes.data_as(u32p), None, out.ctypes.data_as(u32p), n_sample, threads)
+        dt = time.perf_counter() - t
+        assert rc == 0
+        best = dt if best is None else min(best, dt)
+    assert np.array_equal(out.reshape(n_sample, 144), pr[perm]), "CPU baseline output differs from the golden fixture"
+    return n_sample / best, best
+
+
+def run_reference(args):
+    """reference arm: the reference's own Rust path cannot be built here (no cargo, un-vendored
+    arkworks), so this times the oracle's C port of it on all host cores, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 4096
+    for _ in range(args.warmup):
+        cpu_pairing_rate(256, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pairing_rate(n_sample, threads)
+    dt = time.perf_counter() - t0
+    v = n_sample * args.steps / dt
+    line = {"impl": "reference", "metric": "pairings/sec (Miller loop + final exp)", "value": v, "unit": "pairings/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (6x64-bit Montgomery)",
+            "data": "synthetic: 256 seeded pairs (a_i G1, b_i G2) tiled",
+            "config": {"workload": WORKLOAD, "sample": "%d pairs per step" % n_sample},
+            "cpu_baseline": {"value": v, "unit": "pairings/s", "cores": threads, "kind": "port",
+                             "sample": "%d pairs per step x %d steps, oracle/b381_ref.c (C port of the ark-0.4 path; the Rust reference cannot be built here)" % (n_sample, args.steps)},
+            "e2e": {"value": v, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b381")
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step (default 2^20 = the named config)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import b381
+    L = b381._lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    lib = L.init(local)
+    dev = torch.device("cuda", local)
+    n = args.pairs
+    W = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # integer-multiply roofline denominator, measured live on this GPU
+    pk, mhz = ctypes.c_double(), ctypes.c_double()
+    L.check(lib.b381_imad_peak(ctypes.byref(pk), ctypes.byref(mhz)))
+
+    g1, g2, perm, golden = tiled_inputs(n, 1000 + rank)
+    # ---- device-resident throughput --------------------------------------------------------------
+    d1 = torch.from_numpy(g1.view(np.int32)).to(dev)
+    d2 = torch.from_numpy(g2.view(np.int32)).to(dev)
+    dout = torch.empty(n * 144, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+
+    def step_dev():
+        L.check(lib.b381_pairing_dev(d1.data_ptr(), d2.data_ptr(), None, dout.data_ptr(), n, L.MODE_ARK, st))
+
+    for _ in range(W):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.b381_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.b381_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    L.check(lib.b381_check_dev(st))
+    # parity gate: the timed kernel's output against the golden fixture
+    sample = np.arange(0, n, max(1, n // 4096))
+    got = dout.view(n, 144)[torch.from_numpy(sample).to(dev)].cpu().numpy().view(np.uint32)
+    parity_ok = bool(np.array_equal(got, golden[perm[sample]]))
+    value = n * world * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    del dout
+
+    # ---- end to end through the host-pointer C ABI (pinned host memory) --------------------------
+    h1 = torch.from_numpy(g1.view(np.int32)).pin_memory()
+    h2 = torch.from_numpy(g2.view(np.int32)).pin_memory()
+    hout = torch.empty(n * 144, dtype=torch.int32).pin_memory()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+
+    def step_host():
+        L.check(lib.b381_pairing(ctypes.cast(h1.data_ptr(), u32p), ctypes.cast(h2.data_ptr(), u32p), None,
+                                 ctypes.cast(hout.data_ptr(), u32p), n, L.MODE_ARK))
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n * world * e2e_steps / e2e_s
+    hsample = hout.view(n, 144)[torch.from_numpy(sample)].numpy().view(np.uint32)
+    parity_ok = parity_ok and bool(np.array_equal(hsample, golden[perm[sample]]))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel of the step: k_pairing -----------------------------
+    kernel_s = ms_per_step * 1e-3                       # one k_pairing launch per step per GPU
+    alg_ginst = n * FP_MULS_PAIRING * MACS_PER_FP_MUL / kernel_s / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            tj = json.load(open(tfile))
+            traffic = tj.get("k_pairing_dram_bytes_per_launch_2p20")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "imad", "achieved": alg_ginst, "peak": pk.value, "unit": "G IMAD.WIDE/s", "frac": alg_ginst / pk.value,
+                "traffic": traffic,
+                "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
+                        "peak = IMAD.WIDE issue rate measured live by b381_imad_peak (%.0f MHz); the kernel executes 421 IMAD per Fp mul "
+                        "(14 x 28-bit limbs + 15-row reduction), i.e. executed-instruction fraction = frac x 1.40; HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_pairing_rate(4096, threads)
+        cpu = {"value": rate, "unit": "pairings/s", "cores": threads, "kind": "port",
+               "sample": "4096 pairs of the same workload in %.2f s, oracle/b381_ref.c on all host cores" % dt}
+
+    extras = {}
+    if not args.no_extras:
+        def time_dev(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = None
+            for _ in range(reps):
+                a.record(stream); fn(); b.record(stream); torch.cuda.synchronize()
+                t = a.elapsed_time(b)
+                best = t if best is None else min(best, t)
+            return best
+        m = 1 << 16
+        mout = torch.empty(m * 144, dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), m, 0, st)))
+        extras["config3_miller_loops_per_s_2p16"] = m / t * 1e3
+        t = time_dev(lambda: L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), n, 0, st)), reps=2)
+        extras["config5_multi_miller_pairs_per_s_2p20"] = n / t * 1e3
+        k = 1 << 22
+        fa = torch.from_numpy(np.tile(g1[:12], k).view(np.int32)).to(dev); fb = torch.from_numpy(np.tile(g1[12:24], k).view(np.int32)).to(dev)
+        fo = torch.empty(k * 12, dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_fp_mul_chain_dev(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k, 256, st)))
+        extras["config2_fp_mul_chain_G_per_s"] = k * 259 / t / 1e6
+        t = time_dev(lambda: L.check(lib.b381_fp_mul_dev(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k, st)))
+        extras["config2_fp_mul_stream_G_per_s"] = k / t / 1e6
+        extras["config2_fp_mul_stream_GBps"] = k * 144 / t / 1e6
+        L.check(lib.b381_check_dev(st))
+
+    line = {"metric": "pairings/sec (Miller loop + final exp)", "value": value, "unit": "pairings/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64 column accumulators over 14x28-bit limbs (IMAD.WIDE)",
+            "data": "synthetic: 256 seeded pairs (a_i G1, b_i G2) tiled to 2^20 per GPU by a seeded permutation",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "mode": "ARK", "sharding": "contiguous per rank, no collective",
+                       "l2": "inputs+outputs are 906 MB per step > 126 MB L2 (no flush needed)"},
+            "parity": "ok" if parity_ok else "MISMATCH",
+            "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 576,
+                    "api": "b381_pairing (host pointers, pinned)", "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extras": extras}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not parity_ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""The device arithmetic (fp28.cuh / tower.cuh / programs.cuh are plain C++), compiled for the host
+by tests/hostsim/hostsim.cpp, checked bit-for-bit against the oracle -- and, in the
+-DB381_TRACK_BOUNDS build, with every limb / column / magnitude bound of the lazy carry-free
+arithmetic asserted along the executed path (control flow is input-independent in ARK/ZK mode, so
+one run covers the worst case of every operation site)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import b381_oracle as o
+import util
+
+
+def u(n):
+    return (ctypes.c_uint32 * n)()
+
+
+def A(l):
+    return (ctypes.c_uint32 * len(l))(*[int(x) for x in l])
+
+
+@pytest.fixture(scope="module", params=[False, True], ids=["plain", "track_bounds"])
+def hs(request):
+    lib = util.load_hostsim(track=request.param)
+    assert lib.hs_tracking() == (1 if request.param else 0)
+    return lib
+
+
+def test_fp_roundtrip_and_mul_edges(hs):
+    r = util.rng(21)
+    edge = [0, 1, 2, o.P - 1, o.P - 2, o.MONT_R_MOD_P, o.MONT_R2_MOD_P, (1 << 380), o.P >> 1]
+    for v in edge + [util.rfp(r) for _ in range(40)]:
+        out = u(12)
+        assert hs.hs_fp_roundtrip(A(o.fp_to_limbs32(v)), out) == 0
+        assert o.fp_from_limbs32(list(out)) == v
+    vals = edge + [util.rfp(r) for _ in range(30)]
+    for a in vals:
+        for b in (vals[0], vals[3], vals[-1], util.rfp(r)):
+            out = u(12)
+            hs.hs_fp_mul(A(o.fp_to_limbs32(a)), A(o.fp_to_limbs32(b)), out)
+            assert o.fp_from_limbs32(list(out)) == a * b % o.P
+    # limbs >= p are rejected (the reference panics in Fq::from_bigint(..).unwrap())
+    for bad in (o.P, o.P + 1, (1 << 384) - 1):
+        out = u(12)
+        assert hs.hs_fp_roundtrip(A([(bad >> (32 * i)) & 0xFFFFFFFF for i in range(12)]), out) == 1
+
+
+def test_fp2_ops(hs):
+    r = util.rng(22)
+    cases = [((0, 0), (0, 0)), ((1, 0), (0, 1)), ((o.P - 1, o.P - 1), (o.P - 1, o.P - 1))] + [(util.rf2(r), util.rf2(r)) for _ in range(20)]
+    for a, b in cases:
+        out = u(24)
+        hs.hs_fp2_mul(A(util.f2_words(a)), A(util.f2_words(b)), out)
+        assert util.f2_from_words(list(out)) == o.f2_mul(a, b)
+        if a != (0, 0):
+            hs.hs_fp2_inv(A(util.f2_words(a)), out)
+            assert util.f2_from_words(list(out)) == o.f2_inv(a)
+
+
+def test_fp12_ops(hs):
+    r = util.rng(23)
+    for _ in range(4):
+        a, b = util.rf12(r), util.rf12(r)
+        wa, wb = A(o.f12_to_limbs32(a)), A(o.f12_to_limbs32(b))
+        out = u(144)
+        hs.hs_fp12_mul(wa, wb, out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_mul(a, b))
+        hs.hs_fp12_sqr(wa, out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_sqr(a))
+        hs.hs_fp12_inv(wa, out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_inv(a))
+        for k in (1, 2, 3):
+            hs.hs_fp12_frobenius(wa, k, out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_frobenius(a, k))
+        c0, c1, c4 = util.rf2(r), util.rf2(r), util.rf2(r)
+        hs.hs_fp12_mul_by_014(wa, A(util.f2_words(c0)), A(util.f2_words(c1)), A(util.f2_words(c4)), out)
+        assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_mul_by_014(a, c0, c1, c4))
+        am, bm = o.myfq12_from_fq12(a), o.myfq12_from_fq12(b)
+        hs.hs_fp12_mul_wbasis(A(sum((o.fp_to_limbs32(x) for x in am), [])), A(sum((o.fp_to_limbs32(x) for x in bm), [])), out)
+        assert [o.fp_from_limbs32(list(out)[12 * i:12 * i + 12]) for i in range(12)] == o.myfq12_mul(am, bm)
+
+
+def test_reference_fixed_fq12_inputs(hs):
+    """the reference's fixed Fq12 inputs (fq12_target_tree.rs:447-942) through the device arithmetic:
+    a^2 = a a and (a+b) c^2 = c^2 a + c^2 b."""
+    v = util.ref_vectors()["fq12_arith_abc"]["fp"]
+    words = [sum((util.limbs64_to_words(l) for l in v[12 * k:12 * k + 12]), []) for k in range(3)]
+    vals = [o.f12_from_limbs32(w) for w in words]
+    out = u(144)
+    for w, t in zip(words, vals):
+        hs.hs_fp12_sqr(A(w), out)
+        sq = list(out)
+        hs.hs_fp12_mul(A(w), A(w), out)
+        assert sq == list(out) and o.f12_eq(o.f12_from_limbs32(sq), o.f12_sqr(t))
+    a, b, c = vals
+    hs.hs_fp12_sqr(A(words[2]), out); c2 = list(out)
+    hs.hs_fp12_mul(A(o.f12_to_limbs32(o.f12_add(a, b))), A(c2), out); lhs = list(out)
+    hs.hs_fp12_mul(A(c2), A(words[0]), out); t1 = o.f12_from_limbs32(list(out))
+    hs.hs_fp12_mul(A(c2), A(words[1]), out); t2 = o.f12_from_limbs32(list(out))
+    assert o.f12_eq(o.f12_from_limbs32(lhs), o.f12_add(t1, t2))
+
+
+def test_miller_final_exp_pairing_all_modes(hs):
+    kv = util.pairing_vectors()
+    z = util.pairs_256()
+    out = u(144)
+    g1, g2 = A(z["g1"][0]), A(z["g2"][0])
+    assert hs.hs_miller_loop(g1, g2, 0, out, 0) == 0
+    assert o.f12_sha256(o.f12_from_limbs32(list(out))) == kv["ark_miller_g1_g2_sha256"]
+    assert hs.hs_miller_loop(g1, g2, 0, out, 1) == 0
+    assert o.f12_sha256(o.f12_from_limbs32(list(out))) == kv["zk_miller_g1_g2_sha256"]
+    for i in (0, 1, 2, 100, 255):
+        g1, g2 = A(z["g1"][i]), A(z["g2"][i])
+        assert hs.hs_miller_loop(g1, g2, 0, out, 0) == 0 and list(out) == list(z["miller_ark"][i])
+        assert hs.hs_final_exp(A(z["miller_ark"][i]), out) == 0 and list(out) == list(z["pairing"][i])
+        assert hs.hs_pairing(g1, g2, 0, out, 0) == 0 and list(out) == list(z["pairing"][i])
+        assert hs.hs_pairing(g1, g2, 0, out, 1) == 0 and list(out) == list(z["pairing"][i])     # ZK == ARK after final exp
+    one = o.f12_to_limbs32(o.F12_ONE)
+    for inf in (1, 2, 3):
+        assert hs.hs_pairing(g1, g2, inf, out, 0) == 0 and list(out) == one
+        assert hs.hs_miller_loop(g1, g2, inf, out, 1) == 0 and list(out) == one
+    assert hs.hs_final_exp(A([0] * 144), out) == 2               # final_exponentiation(0) is None in ark
+    # cyclotomic squaring and exp_by_x on a cyclotomic element
+    e = o.f12_from_limbs32(z["pairing"][5])
+    hs.hs_fp12_cyclotomic_square(A(z["pairing"][5]), out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.f12_sqr(e))
+    hs.hs_fp12_exp_by_x(A(z["pairing"][5]), out); assert o.f12_eq(o.f12_from_limbs32(list(out)), o.ark_exp_by_x(e))
+
+
+def test_multi_miller_and_literal(hs):
+    z = util.pairs_256()
+    n = 5
+    g1 = A(np.ascontiguousarray(z["g1"][:n]).reshape(-1)); g2 = A(np.ascontiguousarray(z["g2"][:n]).reshape(-1))
+    out = u(144)
+    assert hs.hs_multi_miller(g1, g2, None, ctypes.c_size_t(n), out, 0) == 0
+    pr = o.F12_ONE
+    for i in range(n):
+        pr = o.f12_mul(pr, o.f12_from_limbs32(z["miller_ark"][i]))
+    assert o.f12_eq(o.f12_from_limbs32(list(out)), pr)
+    kv = util.pairing_vectors()
+    g1p = o.fp_to_limbs32(o.G1_X) + o.fp_to_limbs32(o.G1_Y) + o.fp_to_limbs32(1)
+    g2p = util.f2_words(o.G2_X) + util.f2_words(o.G2_Y) + util.f2_words((1, 0))
+    assert hs.hs_literal(A(g1p), A(g2p), out) == 0
+    lit = o.f12_from_limbs32(list(out))
+    assert [lit[0][0][0], lit[0][0][1]] == [int(h, 16) for h in kv["literal_g1_g2_c00"]]
+    r = util.rng(24)
+    P, Q = util.random_pairs(25, 1)[0]
+    z1, z2 = util.rfp(r) or 1, util.rf2(r)
+    pj = (P[0] * z1 * z1 % o.P, P[1] * z1 * z1 * z1 % o.P, z1)
+    z22 = o.f2_sqr(z2)
+    qj = (o.f2_mul(Q[0], z22), o.f2_mul(Q[1], o.f2_mul(z22, z2)), z2)
+    assert hs.hs_literal(A(sum((o.fp_to_limbs32(x) for x in pj), [])), A(sum((util.f2_words(x) for x in qj), [])), out) == 0
+    assert o.f12_eq(o.f12_from_limbs32(list(out)), o.literal_optimized_miller_loop(pj, qj))
+    # Q at infinity (z = 0): f_den becomes 0 and the reference panics -> error bit 2
+    qinf = ((0, 0), (1, 0), (0, 0))
+    assert hs.hs_literal(A(g1p), A(sum((util.f2_words(x) for x in qinf), [])), out) == 2
