@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb381.so")
+LIB_PATH = os.environ.get("B381_LIB", os.path.join(_HERE, "libb381.so"))   # B381_LIB: experiment builds only
 
 MODE_ARK, MODE_ZK, MODE_LITERAL = 0, 1, 2
 

@@ -26,11 +26,12 @@ constexpr size_t SMEM_BYTES = (size_t)NS * GPS * sizeof(u4) * BLOCK;    // 16*7*
 constexpr size_t GARENA_U4_PER_CTA = (size_t)NG_SLOTS * GPS * BLOCK;
 constexpr int RAW_WORDS = 6 * 28;                                       // internal-format Fp12
 
-__device__ __forceinline__ Ctx make_ctx(u4* garena) {
+__device__ __forceinline__ Ctx make_ctx(u4* garena, int lockstep) {
   extern __shared__ u4 smem[];
   Ctx cx;
   cx.sm = smem + threadIdx.x;
   cx.gm = garena + (size_t)blockIdx.x * GARENA_U4_PER_CTA + threadIdx.x;
+  cx.sync = lockstep;
   return cx;
 }
 
@@ -39,30 +40,48 @@ __device__ __forceinline__ void report(int e, int* err) {
 }
 
 // ---- tower kernels (persistent, one CTA per SM) ---------------------------------------------------
+// Lock-step kernels: every thread of the CTA executes the same program (threads past the end of the
+// batch recompute the last element and drop the result), so sync_point() barriers are legal.
+#ifndef B381_LOCKSTEP
+#define B381_LOCKSTEP 1
+#endif
+
 __global__ void __launch_bounds__(BLOCK, 1)
-k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
     size_t i = base + threadIdx.x;
-    if (i < n) report(prog_miller(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, out + 144 * i, mode), err);
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_miller(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode);
+    if (active) report(e, err);
   }
 }
 
 __global__ void __launch_bounds__(BLOCK, 1)
-k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err, uint32_t* dump) {
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
     size_t i = base + threadIdx.x;
-    if (i < n) report(prog_final_exp(cx, in + 144 * i, out + 144 * i), err);
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_final_exp(cx, in + 144 * i, active ? out + 144 * i : dump + 144 * threadIdx.x);
+    if (active) report(e, err);
   }
 }
 
 __global__ void __launch_bounds__(BLOCK, 1)
-k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
     size_t i = base + threadIdx.x;
-    if (i < n) report(prog_pairing(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, out + 144 * i, mode), err);
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_pairing(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode);
+    if (active) report(e, err);
   }
 }
 
@@ -70,22 +89,24 @@ k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* 
 // (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
 k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   f12_set_one(cx, ML_ACC);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
     size_t i = base + threadIdx.x;
-    if (i < n) {
-      report(miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, mode), err);
-      f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);      // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
-    }
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, active ? (inf ? inf[i] : 0) : 3, mode);   // inactive: contributes 1
+    if (active) report(e, err);
+    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);        // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
   }
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), ML_ACC);
 }
 
-// out[j] = product of in[j*K .. min((j+1)K, n_in))   (internal format)
+// out[j] = product of in[j*K .. min((j+1)K, n_in))   (internal format; trip counts differ -> no lock step)
 __global__ void __launch_bounds__(BLOCK, 1)
 k_f12_reduce_raw(const uint32_t* in, size_t n_in, uint32_t* out, size_t n_out, int K, u4* garena) {
-  Ctx cx = make_ctx(garena);
+  Ctx cx = make_ctx(garena, 0);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n_out; base += (size_t)gridDim.x * BLOCK) {
     size_t j = base + threadIdx.x;
     if (j < n_out) {
@@ -98,7 +119,7 @@ k_f12_reduce_raw(const uint32_t* in, size_t n_in, uint32_t* out, size_t n_out, i
 // external -> internal dump (for b381_fp12_product) and internal -> external (optionally via final exp)
 __global__ void __launch_bounds__(BLOCK, 1)
 k_ext_to_raw(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+  Ctx cx = make_ctx(garena, 0);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     size_t i = base + threadIdx.x;
     if (i < n) {
@@ -111,27 +132,30 @@ k_ext_to_raw(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err) 
 __global__ void __launch_bounds__(BLOCK, 1)
 k_raw_finish(const uint32_t* in_raw, uint32_t* out_ext, int do_final_exp, u4* garena, int* err) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Ctx cx = make_ctx(garena);
+  Ctx cx = make_ctx(garena, 0);
   f12_load_raw(cx, FE_F, in_raw);
   if (do_final_exp) report(final_exp_slots(cx, FE_F), err);
   f12_store_ext(cx, out_ext, FE_F);
 }
 
 __global__ void __launch_bounds__(BLOCK, 1)
-k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis, u4* garena, int* err, uint32_t* dump) {
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
     size_t i = base + threadIdx.x;
-    if (i < n) {
-      if (wbasis) report(prog_wbasis_mul(cx, a + 144 * i, b + 144 * i, out + 144 * i), err);
-      else report(prog_f12_mul(cx, a + 144 * i, b + 144 * i, out + 144 * i), err);
-    }
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    uint32_t* o = active ? out + 144 * i : dump + 144 * threadIdx.x;
+    int e = wbasis ? prog_wbasis_mul(cx, a + 144 * i, b + 144 * i, o) : prog_f12_mul(cx, a + 144 * i, b + 144 * i, o);
+    if (active) report(e, err);
   }
 }
 
+// LITERAL loop: data-dependent branches (the reference's three line-function cases) -> no lock step
 __global__ void __launch_bounds__(BLOCK, 1)
 k_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out, size_t n, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena);
+  Ctx cx = make_ctx(garena, 0);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     size_t i = base + threadIdx.x;
     if (i < n) report(prog_literal(cx, g1p + 36 * i, g2p + 72 * i, out + 144 * i), err);
@@ -269,6 +293,7 @@ struct State {
   uint32_t* d_out[2] = {nullptr, nullptr};
   size_t cap_in1 = 0, cap_in2 = 0, cap_inf = 0, cap_out = 0;   // bytes per lane
   uint32_t* d_partial[2] = {nullptr, nullptr};  // raw partial products for multi_miller
+  uint32_t* d_dump[2] = {nullptr, nullptr};     // sink for the outputs of padding threads (BLOCK x 144 words)
   unsigned long long launches = 0;
   std::string last_error;
   std::mutex mu;
@@ -327,19 +352,19 @@ constexpr size_t CHUNK = 1u << 17;    // pairs per pipelined chunk of the host-p
 
 // launch helpers (device pointers) ----------------------------------------------------------------------
 int launch_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  k_miller<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err);
+  k_miller<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
   g.launches++;
   CU(cudaGetLastError());
   return 0;
 }
 int launch_final_exp(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t s, int lane) {
-  k_final_exp<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(in, out, n, g.garena[lane], g.d_err);
+  k_final_exp<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(in, out, n, g.garena[lane], g.d_err, g.d_dump[lane]);
   g.launches++;
   CU(cudaGetLastError());
   return 0;
 }
 int launch_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  k_pairing<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err);
+  k_pairing<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
   g.launches++;
   CU(cudaGetLastError());
   return 0;
@@ -486,6 +511,7 @@ int b381_init(int device) {
     CU(cudaStreamCreateWithFlags(&g.stream[l], cudaStreamNonBlocking));
     CU(cudaMalloc((void**)&g.garena[l], GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count));
     CU(cudaMalloc((void**)&g.d_partial[l], 2 * (size_t)g.sm_count * BLOCK * RAW_WORDS * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&g.d_dump[l], (size_t)BLOCK * 144 * sizeof(uint32_t)));
   }
   CU(cudaMalloc((void**)&g.d_err, sizeof(int)));
   CU(cudaMemset(g.d_err, 0, sizeof(int)));
@@ -506,7 +532,7 @@ int b381_shutdown(void) {
   cudaDeviceSynchronize();
   for (int l = 0; l < 2; l++) {
     if (g.stream[l]) cudaStreamDestroy(g.stream[l]);
-    cudaFree(g.garena[l]); cudaFree(g.d_partial[l]);
+    cudaFree(g.garena[l]); cudaFree(g.d_partial[l]); cudaFree(g.d_dump[l]); g.d_dump[l] = nullptr;
     cudaFree(g.d_in1[l]); cudaFree(g.d_in2[l]); cudaFree(g.d_inf[l]); cudaFree(g.d_out[l]);
     g.stream[l] = nullptr; g.garena[l] = nullptr; g.d_partial[l] = nullptr;
     g.d_in1[l] = g.d_in2[l] = g.d_out[l] = nullptr; g.d_inf[l] = nullptr;
@@ -592,7 +618,7 @@ int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_
   REQUIRE_INIT();
   if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_dev: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
-  k_f12_mul<<<grid_for(n), BLOCK, SMEM_BYTES, (cudaStream_t)stream>>>(a, b, out, n, 0, g.garena[0], g.d_err);
+  k_f12_mul<<<grid_for(n), BLOCK, SMEM_BYTES, (cudaStream_t)stream>>>(a, b, out, n, 0, g.garena[0], g.d_err, g.d_dump[0]);
   g.launches++;
   CU(cudaGetLastError());
   return 0;
@@ -725,7 +751,7 @@ int b381_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) 
 static int f12_mul_host(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis) {
   return host_binary(a, b, out, n, 144, 144, 144, CHUNK,
                      [wbasis](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                       k_f12_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, o, m, wbasis, g.garena[lane], g.d_err);
+                       k_f12_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, o, m, wbasis, g.garena[lane], g.d_err, g.d_dump[lane]);
                        g.launches++;
                        return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_f12_mul");
                      });

@@ -55,17 +55,19 @@ B381_DEV B381_INL void f12_load_raw(const Ctx& cx, int f, const uint32_t* src) {
 // g1: 24 words (x, y), g2: 48 words (x.c0, x.c1, y.c0, y.c1); inf bit0 = P is identity, bit1 = Q.
 B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const uint32_t* g2, int inf, int mode) {
   int err = 0;
-  if (inf & 3) {                                   // identity pairs contribute 1 (ark drops them)
-    f12_set_one(cx, ML_F);
-    return 0;
+  const bool ident = (inf & 3) != 0;               // identity pairs contribute 1 (ark drops them)
+  if (ident) {                                     // run the (uniform) loop on zeros, discard the result
+    f2_set_small(S_(ML_P), 0); f2_set_small(S_(ML_Q), 0); f2_set_small(S_(ML_Q + 1), 0);
+  } else {
+    if (!f2_load_ext(S_(ML_P), g1)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(ML_Q), g2)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(ML_Q + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
   }
-  if (!f2_load_ext(S_(ML_P), g1)) err |= ERR_NOT_CANONICAL;
-  if (!f2_load_ext(S_(ML_Q), g2)) err |= ERR_NOT_CANONICAL;
-  if (!f2_load_ext(S_(ML_Q + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
   MillerSlots s;
   s.f = ML_F; s.L = ML_L; s.T = ML_T; s.R = ML_R; s.Q = ML_Q; s.P = ML_P;
   if (mode == MODE_ZK) zk_miller_loop(cx, s);
   else ark_miller_loop(cx, s);
+  if (ident) f12_set_one(cx, ML_F);
   return err;
 }
 
@@ -73,12 +75,11 @@ B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const u
 B381_DEV B381_INL int final_exp_slots(const Ctx& cx, int src) {
   if (src != FE_F) f12_copy(cx, FE_F, src);
   bool zero = true;
-  for (int i = 0; i < 6; i++) zero = zero && f2_is_zero(S_(FE_F + i));
-  if (zero) return ERR_ZERO_DIVISION;              // ark final_exponentiation(0) is None
+  for (int i = 0; i < 6; i++) zero = f2_is_zero(S_(FE_F + i)) && zero;
   FexpSlots s;
   s.f = FE_F; s.y0 = FE_Y0; s.y1 = FE_Y1; s.y2 = FE_Y2; s.r = FE_R; s.acc = FE_ACC; s.T = FE_T;
-  final_exponentiation(cx, s);
-  return 0;
+  final_exponentiation(cx, s);                     // uniform control flow: f = 0 just flows through as 0
+  return zero ? ERR_ZERO_DIVISION : 0;             // ark final_exponentiation(0) is None
 }
 
 // ---- programs -----------------------------------------------------------------------------------

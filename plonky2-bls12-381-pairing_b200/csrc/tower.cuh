@@ -28,7 +28,7 @@ struct alignas(16) u4 { uint32_t x, y, z, w; };
 #endif
 
 #ifndef B381_BLOCK
-#define B381_BLOCK 128
+#define B381_BLOCK 256
 #endif
 #if defined(__CUDA_ARCH__)
 #define B381_GS B381_BLOCK
@@ -41,14 +41,27 @@ namespace b381 {
 constexpr int GPS = 7;                 // uint4 groups per slot
 constexpr int SLOT = GPS * B381_GS;    // uint4 stride between slots
 #ifndef B381_NS
-#define B381_NS 16
+#define B381_NS 8
 #endif
 constexpr int NS = B381_NS;            // slots held in shared memory
 
 struct Ctx {
   u4* sm;   // this thread's shared-memory slots
   u4* gm;   // this thread's global-memory slots
+  int sync; // 1: the whole CTA runs the same program in lock step -> barrier before every primitive
 };
+
+// Warps of a CTA execute the identical instruction stream (control flow does not depend on the
+// data).  Left alone they drift apart and each SM sub-partition streams the ~0.5 MB kernel through
+// the instruction caches on its own; a barrier before every primitive keeps the four warps within
+// one primitive of each other, so one fetch serves all of them (measured: see DESIGN.md).
+B381_DEV B381_INL void sync_point(const Ctx& c) {
+#if defined(__CUDA_ARCH__)
+  if (c.sync) __syncthreads();
+#else
+  (void)c;
+#endif
+}
 
 B381_DEV B381_INL u4* slot(const Ctx& c, int s) { return s < NS ? c.sm + s * SLOT : c.gm + (s - NS) * SLOT; }
 
@@ -449,14 +462,16 @@ B381_NOINL void f2_store_ext(uint32_t* dst, const u4* a) {
 // ---------------------------------------------------------------------------------------------
 #define S_(i) slot(cx, (i))
 
-B381_DEV B381_INL void lin(const Ctx& cx, int r, int a, int b, int op) { f2_lin(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, op); }
-B381_DEV B381_INL void mul(const Ctx& cx, int r, int a, int b) { f2_mul(S_(r), S_(a), S_(b)); }
+B381_DEV B381_INL void lin(const Ctx& cx, int r, int a, int b, int op) { sync_point(cx); f2_lin(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, op); }
+B381_DEV B381_INL void mul(const Ctx& cx, int r, int a, int b) { sync_point(cx); f2_mul(S_(r), S_(a), S_(b)); }
 B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2) {
+  sync_point(cx);
   f2_mul_ss(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, S_(b), b2 >= 0 ? S_(b2) : nullptr);
 }
-B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { f2_sqr(S_(r), S_(a), nullptr); }
-B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { f2_sqr(S_(r), S_(a), S_(a2)); }
+B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { sync_point(cx); f2_sqr(S_(r), S_(a), nullptr); }
+B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { sync_point(cx); f2_sqr(S_(r), S_(a), S_(a2)); }
 B381_DEV B381_INL void kcomb(const Ctx& cx, int r, int a, int b, int c, int d, int mode) {
+  sync_point(cx);
   f2_kcomb(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, c >= 0 ? S_(c) : nullptr, d >= 0 ? S_(d) : nullptr, mode);
 }
 
@@ -584,6 +599,7 @@ B381_DEV void f12_frobenius(const Ctx& cx, int f, int k) {
     for (int j = 0; j < 3; j++) {
       const int tw = 2 * j + i;
       u4* p = S_(f + 3 * i + j);
+      sync_point(cx);
       if (tw == 0) { if (k & 1) f2_lin(p, p, nullptr, L_CONJ); }
       else f2_mul_gamma(p, p, k, tw, k & 1);
     }
@@ -597,6 +613,7 @@ B381_DEV void f6_inv(const Ctx& cx, int r, int a, int t) {
   sqr(cx, c2, a + 1); mul(cx, x, a, a + 2); lin(cx, c2, c2, x, L_SUB);                   // c2 = a1^2 - a0 a2
   mul(cx, x, a + 2, c1); mul(cx, y, a + 1, c2); lin(cx, x, x, y, L_ADD); lin(cx, x, x, -1, L_MULXI);
   mul(cx, y, a, c0); lin(cx, x, x, y, L_ADD);                                            // t = xi(a2 c1 + a1 c2) + a0 c0
+  sync_point(cx);
   f2_inv(S_(x), S_(x));
   mul(cx, r, x, c0); mul(cx, r + 1, x, c1); mul(cx, r + 2, x, c2);
 }
@@ -701,6 +718,7 @@ B381_DEV void ark_add_step(const Ctx& cx, int R, int Qs, int L, int t) {
 
 // ell for the M-twist: c2 *= py ; c1 *= px ; f.mul_by_014(c0, c1, c2).  Pt = slot (px, py).
 B381_DEV B381_INL void ark_ell(const Ctx& cx, int f, int L, int Pt, int t) {
+  sync_point(cx);
   f2_mulfp(S_(L + 2), S_(L + 2), S_(Pt), 1);
   f2_mulfp(S_(L + 1), S_(L + 1), S_(Pt), 0);
   f12_mul_by_014(cx, f, L, L + 1, L + 2, t);
@@ -784,6 +802,7 @@ B381_DEV void zk_add_step(const Ctx& cx, int R, int Qs, int L, int t) {
 
 // miller_loop_native.rs:139-152: c0 *= py; c1 *= px; f.mul_by_014(coeffs.2, c1, c0)
 B381_DEV B381_INL void zk_ell(const Ctx& cx, int f, int L, int Pt, int t) {
+  sync_point(cx);
   f2_mulfp(S_(L), S_(L), S_(Pt), 1);
   f2_mulfp(S_(L + 1), S_(L + 1), S_(Pt), 0);
   f12_mul_by_014(cx, f, L + 2, L + 1, L, t);

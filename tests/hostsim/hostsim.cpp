@@ -15,6 +15,7 @@ static Ctx make_ctx() {
   Ctx cx;
   cx.sm = g_arena;
   cx.gm = g_arena + NS * SLOT;
+  cx.sync = 0;
 #ifdef B381_TRACK_BOUNDS
   track_tab().clear();
 #endif
