@@ -30,6 +30,9 @@ struct alignas(16) u4 { uint32_t x, y, z, w; };
 #ifndef B381_BLOCK
 #define B381_BLOCK 256
 #endif
+#ifndef B381_SYNC_GROUPS
+#define B381_SYNC_GROUPS 1
+#endif
 #if defined(__CUDA_ARCH__)
 #define B381_GS B381_BLOCK
 #else
@@ -57,7 +60,14 @@ struct Ctx {
 // one primitive of each other, so one fetch serves all of them (measured: see DESIGN.md).
 B381_DEV B381_INL void sync_point(const Ctx& c) {
 #if defined(__CUDA_ARCH__)
+#if B381_SYNC_GROUPS
+  // one named barrier per group of 4 warps (one warp per SM sub-partition): the groups share the
+  // code stream loosely but are free to drift against each other, so while one group is in a
+  // multiply-heavy stretch the other can be in its carry / load-store stretch.
+  if (c.sync) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
+#else
   if (c.sync) __syncthreads();
+#endif
 #else
   (void)c;
 #endif
