@@ -55,6 +55,7 @@ struct Fp {
 #ifdef B381_TRACK_BOUNDS
   double mag;   // bound on |value| / p
   double lb;    // bound on max |limb| / 2^28
+  bool nonneg;  // limbs 0..12 are known to be >= 0 (the sign lives in limb 13 only)
 #endif
 };
 
@@ -82,45 +83,45 @@ B381_HD B381_INL constexpr int32_t plimb(int j) {
 B381_HD B381_INL void fp_zero(Fp& r) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = 0;
-  B381_TB(r.mag = 0; r.lb = 0;)
+  B381_TB(r.mag = 0; r.lb = 0; r.nonneg = true;)
 }
 
 B381_HD B381_INL void fp_add(Fp& r, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = a.l[k] + b.l[k];
-  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb;)
+  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb; r.nonneg = a.nonneg && b.nonneg;)
 }
 
 B381_HD B381_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = a.l[k] - b.l[k];
-  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb;)
+  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb; r.nonneg = false;)
 }
 
 B381_HD B381_INL void fp_neg(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = -a.l[k];
-  B381_TB(r.mag = a.mag; r.lb = a.lb;)
+  B381_TB(r.mag = a.mag; r.lb = a.lb; r.nonneg = false;)
 }
 
 B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = a.l[k] << 1;
-  B381_TB(r.mag = 2 * a.mag; r.lb = 2 * a.lb;)
+  B381_TB(r.mag = 2 * a.mag; r.lb = 2 * a.lb; r.nonneg = a.nonneg;)
 }
 
-// loose carry pass (all carries move one limb in parallel): limbs end in [-2^k, 2^28 + 2^k]
+// carry pass used before every store: sequential and exact, limbs 0..12 end in [0, 2^28) and the
+// sign of the value lives in limb 13 (so multiplications can treat limbs 0..12 as unsigned)
 B381_HD B381_INL void fp_norm(Fp& a) {
   B381_CHECK(a.lb < 7.9, "fp_norm: limb overflow (int32)");
   B381_CHECK(a.mag < 1200.0, "fp_norm: value does not fit 14 limbs");
-  int32_t c[NL - 1];
 #pragma unroll
-  for (int k = 0; k < NL - 1; k++) c[k] = a.l[k] >> W;
-#pragma unroll
-  for (int k = 0; k < NL - 1; k++) a.l[k] &= MASK;
-#pragma unroll
-  for (int k = 1; k < NL; k++) a.l[k] += c[k - 1];
-  B381_TB(a.lb = 1.0 + 1e-6;)     // |carry| <= 8 << 2^28
+  for (int k = 0; k < NL - 1; k++) {
+    int32_t c = a.l[k] >> W;
+    a.l[k] &= MASK;
+    a.l[k + 1] += c;
+  }
+  B381_TB(a.lb = 1.0; a.nonneg = true;)
 }
 
 // exact sequential carry pass: limbs 0..12 in [0, 2^28), l[13] carries the sign
@@ -131,7 +132,7 @@ B381_HD B381_INL void fp_carry_exact(Fp& a) {
     a.l[k] &= MASK;
     a.l[k + 1] += c;
   }
-  B381_TB(a.lb = 1.0;)
+  B381_TB(a.lb = 1.0; a.nonneg = true;)
 }
 
 // weak reduction: subtract q*p with q ~ floor(v/p) estimated from the top limbs, carrying in 64 bits.
@@ -153,7 +154,7 @@ B381_HD B381_INL void fp_wreduce(Fp& a) {
   }
   c += (int64_t)a.l[NL - 1] - (int64_t)q * (int64_t)plimb(NL - 1);
   a.l[NL - 1] = (int32_t)c;
-  B381_TB(a.mag = 1.01; a.lb = 1.0;)
+  B381_TB(a.mag = 1.01; a.lb = 1.0; a.nonneg = true;)
 }
 
 // exact halving mod p: (v + (v odd ? p : 0)) / 2.  Equals multiplication by 2^-1 (ark-ec g2.rs
@@ -166,7 +167,8 @@ B381_HD B381_INL void fp_half(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 0; k < NL - 1; k++) r.l[k] = (t.l[k] >> 1) + ((t.l[k + 1] & 1) << (W - 1));
   r.l[NL - 1] = t.l[NL - 1] >> 1;
-  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = (a.lb + 1) / 2 + 0.5;)
+  B381_CHECK(a.nonneg, "fp_half: limbs must be non-negative");
+  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = (a.lb + 1) / 2 + 0.5; r.nonneg = true;)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -178,13 +180,43 @@ B381_HD B381_INL void acc_zero(Acc& t) {
   B381_TB(t.cb = 0; t.mag = 0;)
 }
 
+// Multiply-accumulate into a 64-bit column.  Stored values keep limbs 0..12 in [0, 2^28] and carry
+// the sign in limb 13 only, so 169 of the 196 products of a 14 x 14 block are UNSIGNED: they compile
+// to one IMAD.WIDE.U32 each (ptxas emulates signed 32x32->64 with an unsigned multiply plus a
+// correction add, which doubled the ALU traffic of an all-signed formulation); only the 27 products
+// touching a top limb are signed.  B381_MAC_STYLE 1 emits volatile PTX in row-major order (the 14
+// IMADs of a row share their first operand -> operand-reuse cache), 0 leaves the order to ptxas.
+#ifndef B381_MAC_STYLE
+#define B381_MAC_STYLE 0
+#endif
+#if defined(__CUDA_ARCH__) && B381_MAC_STYLE == 1
+#define B381_MACU(c, a, b) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b))
+#define B381_MACS(c, a, b) asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b))
+#define B381_MACI(c, a, imm) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "n"(imm))
+#else
+#define B381_MACU(c, a, b) (c) = (int64_t)((uint64_t)(c) + (uint64_t)(uint32_t)(a) * (uint64_t)(uint32_t)(b))
+#define B381_MACS(c, a, b) (c) += (int64_t)(int32_t)(a) * (int64_t)(int32_t)(b)
+#define B381_MACI(c, a, imm) (c) = (int64_t)((uint64_t)(c) + (uint64_t)(uint32_t)(a) * (uint64_t)(uint32_t)(imm))
+#endif
+// one Montgomery row: t.c[i .. i+13] += m * p
+#define B381_ROW_P(t, i, m)                                                                          \
+  B381_MACI(t.c[(i) + 0], m, B381_P0);  B381_MACI(t.c[(i) + 1], m, B381_P1);  B381_MACI(t.c[(i) + 2], m, B381_P2);   \
+  B381_MACI(t.c[(i) + 3], m, B381_P3);  B381_MACI(t.c[(i) + 4], m, B381_P4);  B381_MACI(t.c[(i) + 5], m, B381_P5);   \
+  B381_MACI(t.c[(i) + 6], m, B381_P6);  B381_MACI(t.c[(i) + 7], m, B381_P7);  B381_MACI(t.c[(i) + 8], m, B381_P8);   \
+  B381_MACI(t.c[(i) + 9], m, B381_P9);  B381_MACI(t.c[(i) + 10], m, B381_P10); B381_MACI(t.c[(i) + 11], m, B381_P11); \
+  B381_MACI(t.c[(i) + 12], m, B381_P12); B381_MACI(t.c[(i) + 13], m, B381_P13)
+
 // t += a * b   (196 IMAD.WIDE, no carries)
 B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int i = 0; i < NL; i++)
 #pragma unroll
-    for (int j = 0; j < NL; j++) t.c[i + j] += (int64_t)a.l[i] * (int64_t)b.l[j];
+    for (int j = 0; j < NL; j++) {
+      if (i == NL - 1 || j == NL - 1) B381_MACS(t.c[i + j], a.l[i], b.l[j]);   // a top limb is signed
+      else B381_MACU(t.c[i + j], a.l[i], b.l[j]);
+    }
   B381_TB(t.cb += 14.0 * a.lb * b.lb; t.mag += a.mag * b.mag;)
+  B381_CHECK(a.nonneg && b.nonneg, "acc_mac: operand limbs 0..12 must be non-negative");
   B381_CHECK(t.cb < 120.0, "acc_mac: column overflow");
 }
 
@@ -222,8 +254,7 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
 #pragma unroll
   for (int i = 0; i < NROWS; i++) {
     uint32_t m = ((uint32_t)t.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
-#pragma unroll
-    for (int j = 0; j < NL; j++) t.c[i + j] += (int64_t)(int32_t)m * (int64_t)plimb(j);
+    B381_ROW_P(t, i, m);
     t.c[i + 1] += t.c[i] >> W;
   }
 #pragma unroll
@@ -232,7 +263,33 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
     t.c[NROWS + k + 1] += t.c[NROWS + k] >> W;
   }
   r.l[NL - 1] = (int32_t)t.c[NROWS + NL - 1];
-  B381_TB(r.mag = 1.0 + t.mag / 1.0e11 + 1e-9; r.lb = 1.0;)   // p / 2^420 * p^2 / p ~ 2^-39
+  B381_TB(r.mag = 1.0 + t.mag / 1.0e11 + 1e-9; r.lb = 1.0; r.nonneg = true;)   // p / 2^420 * p^2 / p ~ 2^-39
+}
+
+// two independent reductions with their rows interleaved in source order: the latency of one row's
+// m = c * n0' chain hides behind the other reduction's 14 multiply-accumulates.
+B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
+  B381_CHECK(t0.cb + 14.0 + 1.0 < 127.0 && t1.cb + 14.0 + 1.0 < 127.0, "acc_redc2: column overflow");
+  B381_CHECK(t0.mag < 1.5e6 && t1.mag < 1.5e6, "acc_redc2: input too large");
+#pragma unroll
+  for (int i = 0; i < NROWS; i++) {
+    uint32_t m0 = ((uint32_t)t0.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
+    uint32_t m1 = ((uint32_t)t1.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
+    B381_ROW_P(t0, i, m0);
+    B381_ROW_P(t1, i, m1);
+    t0.c[i + 1] += t0.c[i] >> W;
+    t1.c[i + 1] += t1.c[i] >> W;
+  }
+#pragma unroll
+  for (int k = 0; k < NL - 1; k++) {
+    r0.l[k] = (int32_t)t0.c[NROWS + k] & MASK;
+    r1.l[k] = (int32_t)t1.c[NROWS + k] & MASK;
+    t0.c[NROWS + k + 1] += t0.c[NROWS + k] >> W;
+    t1.c[NROWS + k + 1] += t1.c[NROWS + k] >> W;
+  }
+  r0.l[NL - 1] = (int32_t)t0.c[NROWS + NL - 1];
+  r1.l[NL - 1] = (int32_t)t1.c[NROWS + NL - 1];
+  B381_TB(r0.mag = 1.0 + t0.mag / 1.0e11 + 1e-9; r0.lb = 1.0; r1.mag = 1.0 + t1.mag / 1.0e11 + 1e-9; r1.lb = 1.0; r0.nonneg = r1.nonneg = true;)
 }
 
 // r = t / 2^384 mod p: Montgomery reduction in the EXTERNAL domain (R = 2^384), 13 full rows plus
@@ -244,14 +301,12 @@ B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
 #pragma unroll
   for (int i = 0; i < NL - 1; i++) {
     uint32_t m = ((uint32_t)t.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
-#pragma unroll
-    for (int j = 0; j < NL; j++) t.c[i + j] += (int64_t)(int32_t)m * (int64_t)plimb(j);
+    B381_ROW_P(t, i, m);
     t.c[i + 1] += t.c[i] >> W;
   }
   {
     uint32_t m = ((uint32_t)t.c[NL - 1] * (uint32_t)B381_N0P) & 0xfffffu;
-#pragma unroll
-    for (int j = 0; j < NL; j++) t.c[NL - 1 + j] += (int64_t)(int32_t)m * (int64_t)plimb(j);
+    B381_ROW_P(t, NL - 1, m);
   }
   int32_t d[NL + 1];
 #pragma unroll
@@ -263,7 +318,7 @@ B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
 #pragma unroll
   for (int k = 0; k < NL - 1; k++) r.l[k] = (d[k] >> 20) | ((d[k + 1] & 0xfffff) << 8);
   r.l[NL - 1] = (d[NL - 1] >> 20) + (d[NL] << 8);
-  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = 1.0;)
+  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = 1.0; r.nonneg = true;)
 }
 
 B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
@@ -276,7 +331,7 @@ B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
 B381_HD B381_INL void fp_set(Fp& r, const int32_t (&v)[NL]) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
-  B381_TB(r.mag = 1.0; r.lb = 1.0;)
+  B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -297,7 +352,7 @@ B381_HD B381_INL void fp_canon_small(Fp& a) {
   int32_t ge = ~(t.l[NL - 1] >> 31);                 // -1 if a >= p
 #pragma unroll
   for (int k = 0; k < NL; k++) a.l[k] = (t.l[k] & ge) | (a.l[k] & ~ge);
-  B381_TB(a.mag = 1.0; a.lb = 1.0;)
+  B381_TB(a.mag = 1.0; a.lb = 1.0; a.nonneg = true;)
 }
 
 // full reduction of any stored value to canonical [0,p): one Montgomery multiplication by R' mod p
@@ -334,7 +389,7 @@ B381_HD B381_INL void fp_unpack32(Fp& r, const uint32_t (&w)[12]) {
     if (s > 32 - W && j + 1 < 12) v |= w[j + 1] << (32 - s);
     r.l[k] = (int32_t)(v & (uint32_t)MASK);
   }
-  B381_TB(r.mag = 9.9; r.lb = 1.0;)     // any 384-bit integer
+  B381_TB(r.mag = 9.9; r.lb = 1.0; r.nonneg = true;)     // any 384-bit integer
 }
 
 // canonical limbs -> 12 x u32
@@ -357,7 +412,7 @@ B381_HD B381_INL bool fp_from_ext(Fp& r, const uint32_t (&w)[12]) {
   Fp t;
 #pragma unroll
   for (int k = 0; k < NL; k++) t.l[k] = x.l[k] - plimb(k);
-  B381_TB(t.mag = 11; t.lb = 2;)
+  B381_TB(t.mag = 11; t.lb = 2; t.nonneg = false;)
   fp_carry_exact(t);
   bool ok = (t.l[NL - 1] >> 31) != 0;
   const int32_t cin[NL] = B381_CIN;

@@ -87,9 +87,10 @@ inline std::unordered_map<const void*, TrackEnt>& track_tab() { static std::unor
 inline void track_ld(const u4* p, int h, Fp& a) {
   auto it = track_tab().find(p);
   if (it == track_tab().end()) { a.mag = 1.0; a.lb = 1.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
+  a.nonneg = true;
 }
 inline void track_st(const u4* p, int h, const Fp& a) {
-  B381_CHECK(a.lb < 1.01, "store of non-normalised limbs");
+  B381_CHECK(a.lb < 1.01 && a.nonneg, "store of non-normalised limbs");
   B381_CHECK(a.mag < 1000.0, "store of oversized value");
   auto& e = track_tab()[p];
   e.mag[h] = a.mag; e.lb[h] = a.lb;
@@ -160,7 +161,7 @@ static const ConstTab g_ct = B381_CONST_INIT;
 B381_DEV B381_INL void fp_const(Fp& r, const int32_t* v) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
-  B381_TB(r.mag = 1.0; r.lb = 1.0;)
+  B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,18 +170,24 @@ B381_DEV B381_INL void fp_const(Fp& r, const int32_t* v) {
 // (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba with one reduction per coefficient:
 // 3 x 196 + 2 x 225 = 1038 IMAD.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
 B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
-  Acc A, B, T;
+  // re = a0 b0 - a1 b1 ; im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1.
+  // Register diet: after the two products only the sums stay live, the butterfly runs in place on
+  // the column accumulators, and both reductions are interleaved.
+  Acc A, B;
   acc_zero(A); acc_mac(A, a0, b0);
   acc_zero(B); acc_mac(B, a1, b1);
-  acc_sub(T, A, B);
-  acc_redc(r0, T);
   Fp sa, sb;
   fp_add(sa, a0, a1);
   fp_add(sb, b0, b1);
-  acc_add(T, A, B);
-  acc_neg(T, T);
-  acc_mac(T, sa, sb);
-  acc_redc(r1, T);
+#pragma unroll
+  for (int k = 0; k < 2 * NL - 1; k++) {
+    const int64_t x = A.c[k], y = B.c[k];
+    A.c[k] = x - y;                                 // re
+    B.c[k] = -x - y;                                // -(a0 b0 + a1 b1)
+  }
+  B381_TB(A.cb = A.cb + B.cb; B.cb = A.cb; A.mag = A.mag + B.mag; B.mag = A.mag;)
+  acc_mac(B, sa, sb);
+  acc_redc2(r0, A, r1, B);
 }
 
 // ((a0+a1)(a0-a1), 2 a0 a1); fq2_target_tree.rs:80-91.  2 x 196 + 2 x 225 = 842 IMAD.
@@ -188,12 +195,20 @@ B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
   Fp s, d, t;
   fp_add(s, a0, a1);
   fp_sub(d, a0, a1);
+  fp_norm(d);                                       // multiplicand limbs 0..12 must be non-negative
   fp_dbl(t, a0);
-  Acc T;
+  Acc T, U;
   acc_zero(T); acc_mac(T, s, d);
-  acc_redc(r0, T);
-  acc_zero(T); acc_mac(T, t, a1);
-  acc_redc(r1, T);
+  acc_zero(U); acc_mac(U, t, a1);
+  acc_redc2(r0, T, r1, U);
+}
+
+// (a0 s, a1 s) for an Fp scalar s
+B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& s) {
+  Acc T, U;
+  acc_zero(T); acc_mac(T, a0, s);
+  acc_zero(U); acc_mac(U, a1, s);
+  acc_redc2(r0, T, r1, U);
 }
 
 B381_DEV B381_INL void f2_norm(Fp& a0, Fp& a1) { fp_norm(a0); fp_norm(a1); }
@@ -277,8 +292,7 @@ B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h) {
   Fp a0, a1, s, r0, r1;
   ld_f2(a0, a1, a);
   ld_fp(s, sp, h);
-  fp_mul(r0, a0, s);
-  fp_mul(r1, a1, s);
+  f2_mulfp_reg(r0, r1, a0, a1, s);
   st_f2(r, r0, r1);
 }
 
@@ -286,12 +300,11 @@ B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h) {
 B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
   Fp a0, a1, g0, g1, r0, r1;
   ld_f2(a0, a1, a);
-  if (conj) fp_neg(a1, a1);
+  if (conj) { fp_neg(a1, a1); fp_norm(a1); }
   fp_const(g0, g_ct.frob[k - 1][j - 1][0]);
   fp_const(g1, g_ct.frob[k - 1][j - 1][1]);
   if (k == 2) {                     // gamma_2[j] lies in Fp
-    fp_mul(r0, a0, g0);
-    fp_mul(r1, a1, g0);
+    f2_mulfp_reg(r0, r1, a0, a1, g0);
   } else {
     f2_mul_reg(r0, r1, a0, a1, g0, g1);
   }
@@ -310,6 +323,7 @@ B381_NOINL void f2_inv(u4* r, const u4* a) {
   fp_inv_reg(ni, n);
   fp_mul(r0, a0, ni);
   fp_neg(a1, a1);
+  fp_norm(a1);
   fp_mul(r1, a1, ni);
   st_f2(r, r0, r1);
 }
@@ -423,7 +437,7 @@ B381_NOINL void f2_set_small(u4* r, int one) {
   Fp c0, c1;
   fp_zero(c0); fp_zero(c1);
   if (one) fp_const(c0, g_ct.one);
-  B381_TB(c0.lb = 1; c1.lb = 1; c0.mag = 1; c1.mag = 1;)
+  B381_TB(c0.lb = 1; c1.lb = 1; c0.mag = 1; c1.mag = 1; c0.nonneg = c1.nonneg = true;)
   st_f2(r, c0, c1);
 }
 
