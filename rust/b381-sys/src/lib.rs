@@ -1,0 +1,47 @@
+//! Raw bindings to `include/b381.h`.  Layouts: Fp = 12 x u32 LE, Montgomery R = 2^384.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const B381_MODE_ARK: c_int = 0;
+pub const B381_MODE_ZK: c_int = 1;
+pub const B381_MODE_LITERAL: c_int = 2;
+
+pub const B381_OK: c_int = 0;
+pub const B381_E_CUDA: c_int = -1;
+pub const B381_E_ARG: c_int = -2;
+pub const B381_E_NOT_CANONICAL: c_int = -3;
+pub const B381_E_ZERO_DIVISION: c_int = -4;
+pub const B381_E_NOT_INIT: c_int = -5;
+
+extern "C" {
+    pub fn b381_init(device: c_int) -> c_int;
+    pub fn b381_shutdown() -> c_int;
+    pub fn b381_last_error() -> *const c_char;
+    pub fn b381_device_info(sm_count: *mut c_int, cc_major: *mut c_int, cc_minor: *mut c_int, scratch_bytes: *mut usize) -> c_int;
+    pub fn b381_kernel_launches() -> u64;
+
+    pub fn b381_fp_mul(a: *const u32, b: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp_mul_chain(a: *const u32, b: *const u32, out: *mut u32, n: usize, k: c_int) -> c_int;
+    pub fn b381_fp2_mul(a: *const u32, b: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp12_mul(a: *const u32, b: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp12_mul_wbasis(a: *const u32, b: *const u32, out: *mut u32, n: usize) -> c_int;
+
+    pub fn b381_miller_loop(g1: *const u32, g2: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_multi_miller_loop(g1: *const u32, g2: *const u32, inf: *const u8, out144: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_final_exp(f: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_pairing(g1: *const u32, g2: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_multi_pairing(g1: *const u32, g2: *const u32, inf: *const u8, out144: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_fp12_product(input: *const u32, out144: *mut u32, n: usize) -> c_int;
+    pub fn b381_literal_optimized(g1proj: *const u32, g2proj: *const u32, out: *mut u32, n: usize) -> c_int;
+
+    pub fn b381_miller_loop_dev(g1: *const u32, g2: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_final_exp_dev(f: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_pairing_dev(g1: *const u32, g2: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_multi_miller_loop_dev(g1: *const u32, g2: *const u32, inf: *const u8, out144: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_fp_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_fp_mul_chain_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, k: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_fp2_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_fp12_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_check_dev(stream: *mut c_void) -> c_int;
+    pub fn b381_imad_peak(imad_wide_ginst_per_s: *mut f64, sm_mhz: *mut f64) -> c_int;
+}
