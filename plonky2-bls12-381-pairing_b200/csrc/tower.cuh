@@ -432,6 +432,65 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
   st_f2(r, t0, t1);
 }
 
+// Fused step of the Granger-Scott cyclotomic squaring (/root/reference/src/fields_as_trees/miller_loop.rs:29-104):
+//   (t0, t1) = fp4_square(a, b) = (a^2 + xi b^2, 2 a b)
+//   mode 0:  ra = 3 t0 - 2 za ;      rb = 3 t1 + 2 zb
+//   mode 1:  ra = 3 xi t1 + 2 za ;   rb = 3 t0 - 2 zb
+// a^2 + xi b^2 is accumulated in the column domain (4 MAC blocks, one reduction per coefficient)
+// and 2ab is one Karatsuba product: 7 x 196 + 4 x 225 + 4 x 15 IMAD instead of three separate
+// squarings (6 x 196 + 6 x 225) plus seven memory-to-memory linear operations.  The linear feedback
+// of z is absorbed by the weak reduction, so every output has magnitude <= 2.02 p.
+B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode) {
+  Fp a0, a1, b0, b1, t00, t01, t10, t11;
+  ld_f2(a0, a1, a);
+  ld_f2(b0, b1, b);
+  {
+    // t0 = a^2 + xi b^2:  re = PA + (PB - QB) ; im = QA + (PB + QB)   with
+    // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
+    Fp s, d, e;
+    Acc X, Y;
+    fp_add(s, b0, b1); fp_sub(d, b0, b1); fp_norm(d);
+    acc_zero(X); acc_mac(X, s, d);                  // PB
+    fp_dbl(e, b0);
+    acc_zero(Y); acc_mac(Y, e, b1);                 // QB
+#pragma unroll
+    for (int k = 0; k < 2 * NL - 1; k++) {
+      const int64_t x = X.c[k], y = Y.c[k];
+      X.c[k] = x - y;
+      Y.c[k] = x + y;
+    }
+    B381_TB(X.cb = X.cb + Y.cb; Y.cb = X.cb; X.mag = X.mag + Y.mag; Y.mag = X.mag;)
+    fp_add(s, a0, a1); fp_sub(d, a0, a1); fp_norm(d);
+    acc_mac(X, s, d);                               // + PA
+    fp_dbl(e, a0);
+    acc_mac(Y, e, a1);                              // + QA
+    acc_redc2(t00, X, t01, Y);
+  }
+  Fp z0, z1;
+  {
+    // outputs built from t0: 3 t0 - 2 z, stored at once so t0 is dead before the a*b product starts
+    const u4* zt0 = mode == 0 ? za : zb;
+    if (zt0 == a) { z0 = a0; z1 = a1; } else ld_f2(z0, z1, zt0);
+    Fp w0, w1;
+    fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
+    fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
+    fp_wreduce(w0); fp_wreduce(w1);
+    st_f2(mode == 0 ? ra : rb, w0, w1);
+  }
+  f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
+  // outputs built from t1 = 2ab:  3 t1 + 2 z = 2 (3 ab + z)   or   3 xi t1 + 2 z = 2 (3 xi ab + z)
+  const u4* zt1 = mode == 0 ? zb : za;
+  if (zt1 == b) { z0 = b0; z1 = b1; } else ld_f2(z0, z1, zt1);
+  if (mode == 1) f2_mulxi_reg(t10, t11, t10, t11);
+  Fp x0, x1;
+  fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
+  fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
+  fp_wreduce(x0); fp_wreduce(x1);
+  fp_dbl(x0, x0); fp_dbl(x1, x1);
+  f2_norm(x0, x1);
+  st_f2(mode == 0 ? rb : ra, x0, x1);
+}
+
 // set slot to the Fp2 constant (one, 0) or (0, 0)
 B381_NOINL void f2_set_small(u4* r, int one) {
   Fp c0, c1;
@@ -657,44 +716,32 @@ B381_DEV void f12_inv(const Ctx& cx, int f, int t) {
   for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, v + i, -1, L_NEG);
 }
 
-// fp4_square(a, b) -> (ra, rb) = (a^2 + xi b^2, (a+b)^2 - a^2 - b^2);
-// /root/reference/src/fields_as_trees/miller_loop.rs:29-44.  t = 1 scratch slot beyond outputs.
-B381_DEV B381_INL void fp4_square(const Ctx& cx, int ra, int rb, int a, int b, int t) {
-  sqr(cx, ra, a);
-  sqr(cx, t, b);
-  sqr_s(cx, rb, a, b);
-  kcomb(cx, rb, rb, ra, t, -1, K_PLAIN);
-  lin(cx, ra, ra, t, L_XIADD);
+// Granger-Scott cyclotomic squaring d = s^2, OUT OF PLACE (d and s distinct Fp12 slot ranges);
+// /root/reference/src/fields_as_trees/miller_loop.rs:46-104.  With z0=c0.c0, z4=c0.c1, z3=c0.c2,
+// z2=c1.c0, z1=c1.c1, z5=c1.c2:  (z0',z1') from fp4(z0,z1); (z4',z5') from fp4(z2,z3);
+// (z2',z3') from fp4(z4,z5) with the xi twist.  Three fused primitive calls, no scratch.
+B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s) {
+  const int z0 = 0, z4 = 1, z3 = 2, z2 = 3, z1 = 4, z5 = 5;
+  sync_point(cx);
+  f2_cyc_fp4(S_(d + z0), S_(d + z1), S_(s + z0), S_(s + z1), S_(s + z0), S_(s + z1), 0);
+  sync_point(cx);
+  f2_cyc_fp4(S_(d + z4), S_(d + z5), S_(s + z2), S_(s + z3), S_(s + z4), S_(s + z5), 0);
+  sync_point(cx);
+  f2_cyc_fp4(S_(d + z2), S_(d + z3), S_(s + z4), S_(s + z5), S_(s + z2), S_(s + z3), 1);
 }
 
-// Granger-Scott cyclotomic squaring in place; miller_loop.rs:46-104.  t = 5 scratch slots.
-B381_DEV void f12_cyclotomic_square(const Ctx& cx, int f, int t) {
-  const int z0 = f, z4 = f + 1, z3 = f + 2, z2 = f + 3, z1 = f + 4, z5 = f + 5;
-  const int t0 = t, t1 = t + 1, t2 = t + 2, t3 = t + 3, w = t + 4;
-  fp4_square(cx, t0, t1, z0, z1, w);
-  lin(cx, z0, t0, z0, L_3A_M2B);
-  lin(cx, z1, t1, z1, L_3A_P2B);
-  fp4_square(cx, t0, t1, z2, z3, w);
-  fp4_square(cx, t2, t3, z4, z5, w);
-  lin(cx, z4, t0, z4, L_3A_M2B);
-  lin(cx, z5, t1, z5, L_3A_P2B);
-  lin(cx, t3, t3, -1, L_MULXI);
-  lin(cx, z2, t3, z2, L_3A_P2B);
-  lin(cx, z3, t2, z3, L_3A_M2B);
-}
-
-// r = conj(a^|x|): ark Bls12::exp_by_x (x < 0).  The running value lives in the fixed slots
-// `acc` (shared memory) so the 63 cyclotomic squarings never touch global memory; r may alias a.
-// t = 16 scratch slots.
-B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int t) {
-  f12_copy(cx, acc, a);
+// r = conj(a^|x|): ark Bls12::exp_by_x (x < 0).  The running value ping-pongs between the two
+// fixed slot ranges acc / acc2 (the hot end of the arena); r may alias a.  t = 16 scratch slots.
+B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int acc2, int t) {
+  int cur = acc, nxt = acc2;
   const uint64_t xabs = B381_X_ABS;
   for (int b = 62; b >= 0; b--) {
-    f12_cyclotomic_square(cx, acc, t);
-    if ((xabs >> b) & 1) f12_mul(cx, acc, acc, a, t);
+    f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur);
+    const int sw = cur; cur = nxt; nxt = sw;
+    if ((xabs >> b) & 1) f12_mul(cx, cur, cur, a, t);
   }
-  for (int i = 0; i < 3; i++) lin(cx, r + i, acc + i, -1, L_COPY);
-  for (int i = 3; i < 6; i++) lin(cx, r + i, acc + i, -1, L_NEG);
+  for (int i = 0; i < 3; i++) lin(cx, r + i, cur + i, -1, L_COPY);
+  for (int i = 3; i < 6; i++) lin(cx, r + i, cur + i, -1, L_NEG);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,10 +909,10 @@ B381_DEV void zk_miller_loop(const Ctx& cx, const MillerSlots& s) {
 // /root/reference/src/fields_as_trees/miller_loop.rs:128-178).  In place on f.
 // y0, y1, y2, r2 = four Fp12 scratch values (6 slots each); t = 16 scratch slots.
 // ---------------------------------------------------------------------------------------------
-struct FexpSlots { int f, y0, y1, y2, r, acc, T; };
+struct FexpSlots { int f, y0, y1, y2, r, acc, acc2, T; };
 
 B381_DEV void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
-  const int f = s.f, y0 = s.y0, y1 = s.y1, y2 = s.y2, r = s.r, acc = s.acc, T = s.T;
+  const int f = s.f, y0 = s.y0, y1 = s.y1, y2 = s.y2, r = s.r, acc = s.acc, acc2 = s.acc2, T = s.T;
   // easy part: r = f^((p^6-1)(p^2+1))
   f12_copy(cx, r, f);
   f12_conj(cx, r);                                // f1 = conj(f)
@@ -875,19 +922,19 @@ B381_DEV void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
   f12_frobenius(cx, r, 2);
   f12_mul(cx, r, r, f, T);
   // hard part
-  f12_copy(cx, y0, r); f12_cyclotomic_square(cx, y0, T);            // y0 = r^2
-  f12_exp_by_x(cx, y1, r, acc, T);                                       // y1 = r^x
+  f12_cyclotomic_square(cx, y0, r);                                 // y0 = r^2
+  f12_exp_by_x(cx, y1, r, acc, acc2, T);                                       // y1 = r^x
   f12_copy(cx, y2, r); f12_conj(cx, y2);                            // y2 = r^-1
   f12_mul(cx, y1, y1, y2, T);
-  f12_exp_by_x(cx, y2, y1, acc, T);
+  f12_exp_by_x(cx, y2, y1, acc, acc2, T);
   f12_conj(cx, y1);
   f12_mul(cx, y1, y1, y2, T);
-  f12_exp_by_x(cx, y2, y1, acc, T);
+  f12_exp_by_x(cx, y2, y1, acc, acc2, T);
   f12_frobenius(cx, y1, 1);
   f12_mul(cx, y1, y1, y2, T);
   f12_mul(cx, r, r, y0, T);
-  f12_exp_by_x(cx, y0, y1, acc, T);
-  f12_exp_by_x(cx, y2, y0, acc, T);
+  f12_exp_by_x(cx, y0, y1, acc, acc2, T);
+  f12_exp_by_x(cx, y2, y0, acc, acc2, T);
   f12_copy(cx, y0, y1); f12_frobenius(cx, y0, 2);
   f12_conj(cx, y1);
   f12_mul(cx, y1, y1, y2, T);

@@ -94,8 +94,8 @@ int hs_fp12_frobenius(const uint32_t* a, int k, uint32_t* out) {
 int hs_fp12_cyclotomic_square(const uint32_t* a, uint32_t* out) {
   Ctx cx = make_ctx();
   bool ok = f12_load_ext(cx, 0, a);
-  f12_cyclotomic_square(cx, 0, 6);
-  f12_store_ext(cx, out, 0);
+  f12_cyclotomic_square(cx, 6, 0);
+  f12_store_ext(cx, out, 6);
   return ok ? 0 : 1;
 }
 
@@ -141,7 +141,7 @@ int hs_tracking(void) {
 extern "C" int hs_fp12_exp_by_x(const uint32_t* a, uint32_t* out) {
   Ctx cx = make_ctx();
   bool ok = f12_load_ext(cx, FE_F, a);
-  f12_exp_by_x(cx, FE_Y0, FE_F, FE_ACC, FE_T);
+  f12_exp_by_x(cx, FE_Y0, FE_F, FE_ACC, FE_ACC2, FE_T);
   f12_store_ext(cx, out, FE_Y0);
   return ok ? 0 : 1;
 }
