@@ -184,8 +184,12 @@ B381_HD B381_INL void acc_zero(Acc& t) {
 // the sign in limb 13 only, so 169 of the 196 products of a 14 x 14 block are UNSIGNED: they compile
 // to one IMAD.WIDE.U32 each (ptxas emulates signed 32x32->64 with an unsigned multiply plus a
 // correction add, which doubled the ALU traffic of an all-signed formulation); only the 27 products
-// touching a top limb are signed.  B381_MAC_STYLE 1 emits volatile PTX in row-major order (the 14
-// IMADs of a row share their first operand -> operand-reuse cache), 0 leaves the order to ptxas.
+// touching a top limb are signed.  ptxas lowers every 64-bit multiply-accumulate to IMAD.WIDE (RZ
+// addend) plus a shared IADD3 / IADD3.X pair per two products, i.e. one multiplier-pipe and one
+// ALU-pipe instruction per MAC (both pipes issue 64 lanes/clk/SM), whatever the source form.
+// B381_MAC_STYLE 1 emits volatile PTX in row-major order (isolated MAC blocks then reach 59
+// IMAD/clk/SM instead of 30, tools/phase_probe.cu) but raises register pressure in the full
+// primitives and is not faster end to end; 0 (default) leaves the order to ptxas.
 #ifndef B381_MAC_STYLE
 #define B381_MAC_STYLE 0
 #endif
@@ -199,12 +203,14 @@ B381_HD B381_INL void acc_zero(Acc& t) {
 #define B381_MACI(c, a, imm) (c) = (int64_t)((uint64_t)(c) + (uint64_t)(uint32_t)(a) * (uint64_t)(uint32_t)(imm))
 #endif
 // one Montgomery row: t.c[i .. i+13] += m * p
-#define B381_ROW_P(t, i, m)                                                                          \
+#define B381_DECL_P
+#define B381_ROW_P_IMM(t, i, m)                                                                          \
   B381_MACI(t.c[(i) + 0], m, B381_P0);  B381_MACI(t.c[(i) + 1], m, B381_P1);  B381_MACI(t.c[(i) + 2], m, B381_P2);   \
   B381_MACI(t.c[(i) + 3], m, B381_P3);  B381_MACI(t.c[(i) + 4], m, B381_P4);  B381_MACI(t.c[(i) + 5], m, B381_P5);   \
   B381_MACI(t.c[(i) + 6], m, B381_P6);  B381_MACI(t.c[(i) + 7], m, B381_P7);  B381_MACI(t.c[(i) + 8], m, B381_P8);   \
   B381_MACI(t.c[(i) + 9], m, B381_P9);  B381_MACI(t.c[(i) + 10], m, B381_P10); B381_MACI(t.c[(i) + 11], m, B381_P11); \
   B381_MACI(t.c[(i) + 12], m, B381_P12); B381_MACI(t.c[(i) + 13], m, B381_P13)
+#define B381_ROW_P(t, i, m) B381_ROW_P_IMM(t, i, m)
 
 // t += a * b   (196 IMAD.WIDE, no carries)
 B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
@@ -251,6 +257,7 @@ B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
 B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
   B381_CHECK(t.cb + 14.0 + 1.0 < 127.0, "acc_redc: column overflow");
   B381_CHECK(t.mag < 1.5e6, "acc_redc: input too large");
+  B381_DECL_P;
 #pragma unroll
   for (int i = 0; i < NROWS; i++) {
     uint32_t m = ((uint32_t)t.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
@@ -271,6 +278,7 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
 B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
   B381_CHECK(t0.cb + 14.0 + 1.0 < 127.0 && t1.cb + 14.0 + 1.0 < 127.0, "acc_redc2: column overflow");
   B381_CHECK(t0.mag < 1.5e6 && t1.mag < 1.5e6, "acc_redc2: input too large");
+  B381_DECL_P;
 #pragma unroll
   for (int i = 0; i < NROWS; i++) {
     uint32_t m0 = ((uint32_t)t0.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;
@@ -298,6 +306,7 @@ B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
 B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
   B381_CHECK(t.cb + 14.0 + 1.0 < 127.0, "acc_redc384: column overflow");
   B381_CHECK(t.mag < 4.0, "acc_redc384: operands must be canonical");
+  B381_DECL_P;
 #pragma unroll
   for (int i = 0; i < NL - 1; i++) {
     uint32_t m = ((uint32_t)t.c[i] * (uint32_t)B381_N0P) & (uint32_t)MASK;

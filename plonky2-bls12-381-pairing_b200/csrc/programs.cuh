@@ -16,10 +16,10 @@ enum ErrBits { ERR_NOT_CANONICAL = 1, ERR_ZERO_DIVISION = 2 };
 // memory when NS = 16); R, Q, P are touched only by the curve steps.
 constexpr int ML_F = 0, ML_L = 6, ML_T = 9, ML_R = 19, ML_Q = 22, ML_P = 24, ML_ACC = 25, ML_NSLOTS = 31;
 // final exponentiation: ACC (the value being squared) and the first scratch slots are hot.
-constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_F = 28, FE_Y0 = 34, FE_Y1 = 40, FE_Y2 = 46, FE_R = 52, FE_NSLOTS = 58;
+constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_F = 28, FE_Y0 = 28 /* f is dead once y0 is first written */, FE_Y1 = 34, FE_Y2 = 40, FE_R = 46, FE_NSLOTS = 52;
 // literal loop
 constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
-constexpr int MAX_NSLOTS = 58;
+constexpr int MAX_NSLOTS = 52;
 
 #define S_(i) slot(cx, (i))
 

@@ -75,6 +75,17 @@ B381_DEV B381_INL void sync_point(const Ctx& c) {
 
 B381_DEV B381_INL u4* slot(const Ctx& c, int s) { return s < NS ? c.sm + s * SLOT : c.gm + (s - NS) * SLOT; }
 
+#ifndef B381_SYNC_LIN
+#define B381_SYNC_LIN 1
+#endif
+B381_DEV B381_INL void sync_point_lin(const Ctx& c) {
+#if B381_SYNC_LIN
+  sync_point(c);
+#else
+  (void)c;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // bound-tracking side table (host simulation only)
 // ---------------------------------------------------------------------------------------------
@@ -545,7 +556,7 @@ B381_NOINL void f2_store_ext(uint32_t* dst, const u4* a) {
 // ---------------------------------------------------------------------------------------------
 #define S_(i) slot(cx, (i))
 
-B381_DEV B381_INL void lin(const Ctx& cx, int r, int a, int b, int op) { sync_point(cx); f2_lin(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, op); }
+B381_DEV B381_INL void lin(const Ctx& cx, int r, int a, int b, int op) { sync_point_lin(cx); f2_lin(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, op); }
 B381_DEV B381_INL void mul(const Ctx& cx, int r, int a, int b) { sync_point(cx); f2_mul(S_(r), S_(a), S_(b)); }
 B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2) {
   sync_point(cx);
@@ -554,7 +565,7 @@ B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2
 B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { sync_point(cx); f2_sqr(S_(r), S_(a), nullptr); }
 B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { sync_point(cx); f2_sqr(S_(r), S_(a), S_(a2)); }
 B381_DEV B381_INL void kcomb(const Ctx& cx, int r, int a, int b, int c, int d, int mode) {
-  sync_point(cx);
+  sync_point_lin(cx);
   f2_kcomb(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, c >= 0 ? S_(c) : nullptr, d >= 0 ? S_(d) : nullptr, mode);
 }
 
