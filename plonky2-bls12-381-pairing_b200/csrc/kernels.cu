@@ -26,14 +26,53 @@ constexpr size_t SMEM_BYTES = (size_t)NS * GPS * sizeof(u4) * BLOCK;    // 16*7*
 constexpr size_t GARENA_U4_PER_CTA = (size_t)NG_SLOTS * GPS * BLOCK;
 constexpr int RAW_WORDS = 6 * 28;                                       // internal-format Fp12
 
-__device__ __forceinline__ Ctx make_ctx(u4* garena, int lockstep) {
+#ifndef B381_LOCKSTEP
+#define B381_LOCKSTEP 1
+#endif
+#ifndef B381_USE_TMEM
+#define B381_USE_TMEM 1
+#endif
+
+__device__ __forceinline__ Ctx make_ctx(u4* garena, int lockstep, uint32_t tmem_base = 0, int use_tmem = 0) {
   extern __shared__ u4 smem[];
   Ctx cx;
   cx.sm = smem + threadIdx.x;
   cx.gm = garena + (size_t)blockIdx.x * GARENA_U4_PER_CTA + threadIdx.x;
   cx.sync = lockstep;
+  const uint32_t warp = threadIdx.x >> 5;
+  cx.tm = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 256u;
+  cx.nt = use_tmem ? NT_MAX : 0;
   return cx;
 }
+
+// the whole tensor memory of the SM (512 columns) for this CTA; called by all threads
+__device__ __forceinline__ uint32_t tmem_alloc_all() {
+  __shared__ uint32_t s_tmem_base;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return s_tmem_base;
+}
+
+__device__ __forceinline__ void tmem_free_all(uint32_t base) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+
+#if B381_USE_TMEM && (B381_BLOCK == 256)
+#define B381_TMEM_BEGIN() const uint32_t tmem_base_ = tmem_alloc_all()
+#define B381_TMEM_CTX(garena) make_ctx(garena, B381_LOCKSTEP, tmem_base_, 1)
+#define B381_TMEM_END() tmem_free_all(tmem_base_)
+#else
+#define B381_TMEM_BEGIN()
+#define B381_TMEM_CTX(garena) make_ctx(garena, B381_LOCKSTEP)
+#define B381_TMEM_END()
+#endif
 
 __device__ __forceinline__ void report(int e, int* err) {
   if (e) atomicOr(err, e);
@@ -42,13 +81,10 @@ __device__ __forceinline__ void report(int e, int* err) {
 // ---- tower kernels (persistent, one CTA per SM) ---------------------------------------------------
 // Lock-step kernels: every thread of the CTA executes the same program (threads past the end of the
 // batch recompute the last element and drop the result), so sync_point() barriers are legal.
-#ifndef B381_LOCKSTEP
-#define B381_LOCKSTEP 1
-#endif
-
 __global__ void __launch_bounds__(BLOCK, 1)
 k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
-  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
@@ -57,11 +93,13 @@ k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* o
     int e = prog_miller(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode);
     if (active) report(e, err);
   }
+  B381_TMEM_END();
 }
 
 __global__ void __launch_bounds__(BLOCK, 1)
 k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err, uint32_t* dump) {
-  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
@@ -70,11 +108,13 @@ k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err, u
     int e = prog_final_exp(cx, in + 144 * i, active ? out + 144 * i : dump + 144 * threadIdx.x);
     if (active) report(e, err);
   }
+  B381_TMEM_END();
 }
 
 __global__ void __launch_bounds__(BLOCK, 1)
 k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
-  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
@@ -83,14 +123,17 @@ k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* 
     int e = prog_pairing(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode);
     if (active) report(e, err);
   }
+  B381_TMEM_END();
 }
 
 // every thread multiplies the Miller values of its pairs into a private accumulator and dumps it
 // (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
-k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
-  f12_set_one(cx, ML_ACC);
+k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, int accumulate, u4* garena, int* err) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  if (accumulate) f12_load_raw(cx, ML_ACC, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x));
+  else f12_set_one(cx, ML_ACC);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
@@ -101,6 +144,7 @@ k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_
     f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);        // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
   }
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), ML_ACC);
+  B381_TMEM_END();
 }
 
 // out[j] = product of in[j*K .. min((j+1)K, n_in))   (internal format; trip counts differ -> no lock step)
@@ -140,7 +184,8 @@ k_raw_finish(const uint32_t* in_raw, uint32_t* out_ext, int do_final_exp, u4* ga
 
 __global__ void __launch_bounds__(BLOCK, 1)
 k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis, u4* garena, int* err, uint32_t* dump) {
-  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
@@ -150,6 +195,7 @@ k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wba
     int e = wbasis ? prog_wbasis_mul(cx, a + 144 * i, b + 144 * i, o) : prog_f12_mul(cx, a + 144 * i, b + 144 * i, o);
     if (active) report(e, err);
   }
+  B381_TMEM_END();
 }
 
 // LITERAL loop: data-dependent branches (the reference's three line-function cases) -> no lock step
@@ -351,21 +397,36 @@ int read_err(cudaStream_t s) {
 constexpr size_t CHUNK = 1u << 17;    // pairs per pipelined chunk of the host-pointer API
 
 // launch helpers (device pointers) ----------------------------------------------------------------------
+// A launch is limited to a few rounds per CTA: CTAs of different SMs are only aligned at launch
+// start, and per-round time creeps up by ~8 % once they have drifted apart (tools/gpu_exp3.py);
+// back-to-back launches of <= 4 rounds keep the whole chip on one instruction stream.
+constexpr size_t MAX_ROUNDS_PER_LAUNCH = 4;
+size_t pairs_per_launch() { return MAX_ROUNDS_PER_LAUNCH * (size_t)g.sm_count * BLOCK; }
+
 int launch_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  k_miller<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
-  g.launches++;
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_miller<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
+    g.launches++;
+  }
   CU(cudaGetLastError());
   return 0;
 }
 int launch_final_exp(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t s, int lane) {
-  k_final_exp<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(in, out, n, g.garena[lane], g.d_err, g.d_dump[lane]);
-  g.launches++;
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_final_exp<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(in + 144 * off, out + 144 * off, m, g.garena[lane], g.d_err, g.d_dump[lane]);
+    g.launches++;
+  }
   CU(cudaGetLastError());
   return 0;
 }
 int launch_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  k_pairing<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, out, n, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
-  g.launches++;
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_pairing<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
+    g.launches++;
+  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -398,8 +459,11 @@ int launch_multi(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uin
   size_t nthreads = (size_t)grid * BLOCK;
   uint32_t* ping = g.d_partial[lane];
   uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
-  k_multi_miller<<<grid, BLOCK, SMEM_BYTES, s>>>(g1, g2, inf, n, mode, ping, g.garena[lane], g.d_err);
-  g.launches++;
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {     // every launch uses the same grid and keeps accumulating
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_multi_miller<<<grid, BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, m, mode, ping, off != 0, g.garena[lane], g.d_err);
+    g.launches++;
+  }
   CU(cudaGetLastError());
   uint32_t* res = nullptr;
   int rc = reduce_raw(ping, pong, nthreads, s, lane, &res);

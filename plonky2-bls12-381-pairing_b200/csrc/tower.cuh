@@ -52,7 +52,17 @@ struct Ctx {
   u4* sm;   // this thread's shared-memory slots
   u4* gm;   // this thread's global-memory slots
   int sync; // 1: the whole CTA runs the same program in lock step -> barrier before every primitive
+  uint32_t tm;  // tensor-memory address (lane base << 16 | first column) of this warp's scratch columns
+  int nt;       // number of slots held in tensor memory (0 = none); slots [NS, NS + nt)
 };
+
+// Tensor memory (TMEM, 256 KB per SM) as a per-thread scratchpad.  The pairing kernels issue no MMA,
+// so the whole TMEM of the SM is free: a CTA allocates all 512 columns; warp w owns TMEM lanes
+// 32 (w % 4) .. +31 (the only lanes it may address) and columns 256 (w / 4) .. +255, i.e. every
+// thread owns 256 words = 9 Fp2 slots, moved with tcgen05.ld/st.32x32b (one thread per lane).
+// Pointers into TMEM are tagged (bit 62) so the slot primitives can take either kind.
+constexpr int NT_MAX = 9;
+constexpr unsigned long long TMEM_TAG = 1ull << 62;
 
 // Warps of a CTA execute the identical instruction stream (control flow does not depend on the
 // data).  Left alone they drift apart and each SM sub-partition streams the ~0.5 MB kernel through
@@ -73,7 +83,39 @@ B381_DEV B381_INL void sync_point(const Ctx& c) {
 #endif
 }
 
-B381_DEV B381_INL u4* slot(const Ctx& c, int s) { return s < NS ? c.sm + s * SLOT : c.gm + (s - NS) * SLOT; }
+B381_DEV B381_INL u4* slot(const Ctx& c, int s) {
+  if (s < NS) return c.sm + s * SLOT;
+#if defined(__CUDA_ARCH__)
+  if (s < NS + c.nt) return reinterpret_cast<u4*>(TMEM_TAG | (unsigned long long)(c.tm + (uint32_t)(s - NS) * 28u));
+#endif
+  return c.gm + (s - NS) * SLOT;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ bool is_tmem(const u4* p) { return (reinterpret_cast<unsigned long long>(p) & TMEM_TAG) != 0; }
+__device__ __forceinline__ void tmem_ld28(uint32_t (&w)[28], uint32_t ta) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                 "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+               : "r"(ta));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23])
+               : "r"(ta + 16));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]) : "r"(ta + 24));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st28(uint32_t ta, const uint32_t (&w)[28]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(ta), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+                  "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(ta + 16), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               :: "r"(ta + 24), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+#endif
 
 #ifndef B381_SYNC_LIN
 #define B381_SYNC_LIN 1
@@ -112,6 +154,15 @@ inline void track_st(const u4* p, int h, const Fp& a) {
 // slot loads / stores
 // ---------------------------------------------------------------------------------------------
 B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
+#if defined(__CUDA_ARCH__)
+  if (is_tmem(p)) {
+    uint32_t w[28];
+    tmem_ld28(w, (uint32_t)reinterpret_cast<unsigned long long>(p));
+#pragma unroll
+    for (int k = 0; k < NL; k++) { c0.l[k] = (int32_t)w[k]; c1.l[k] = (int32_t)w[NL + k]; }
+    return;
+  }
+#endif
   u4 g[GPS];
 #pragma unroll
   for (int i = 0; i < GPS; i++) g[i] = p[i * B381_GS];
@@ -126,6 +177,15 @@ B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
 }
 
 B381_DEV B381_INL void st_f2(u4* p, const Fp& c0, const Fp& c1) {
+#if defined(__CUDA_ARCH__)
+  if (is_tmem(p)) {
+    uint32_t w[28];
+#pragma unroll
+    for (int k = 0; k < NL; k++) { w[k] = (uint32_t)c0.l[k]; w[NL + k] = (uint32_t)c1.l[k]; }
+    tmem_st28((uint32_t)reinterpret_cast<unsigned long long>(p), w);
+    return;
+  }
+#endif
   u4 g[GPS];
   g[0].x = c0.l[0]; g[0].y = c0.l[1]; g[0].z = c0.l[2]; g[0].w = c0.l[3];
   g[1].x = c0.l[4]; g[1].y = c0.l[5]; g[1].z = c0.l[6]; g[1].w = c0.l[7];
