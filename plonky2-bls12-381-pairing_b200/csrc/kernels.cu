@@ -141,7 +141,7 @@ k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_
     if (!active) i = n - 1;
     int e = miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, active ? (inf ? inf[i] : 0) : 3, mode);   // inactive: contributes 1
     if (active) report(e, err);
-    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);        // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
+    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T, ML_T + 6);   // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
   }
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), ML_ACC);
   B381_TMEM_END();
@@ -399,8 +399,9 @@ constexpr size_t CHUNK = 1u << 17;    // pairs per pipelined chunk of the host-p
 // launch helpers (device pointers) ----------------------------------------------------------------------
 // A launch is limited to a few rounds per CTA: CTAs of different SMs are only aligned at launch
 // start, and per-round time creeps up by ~8 % once they have drifted apart (tools/gpu_exp3.py);
-// back-to-back launches of <= 4 rounds keep the whole chip on one instruction stream.
-constexpr size_t MAX_ROUNDS_PER_LAUNCH = 4;
+// back-to-back launches of one round each keep the whole chip on one instruction stream
+// (34.2 ms/round against 34.8 at four rounds and 37.6 at 28 rounds per launch).
+constexpr size_t MAX_ROUNDS_PER_LAUNCH = 1;
 size_t pairs_per_launch() { return MAX_ROUNDS_PER_LAUNCH * (size_t)g.sm_count * BLOCK; }
 
 int launch_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {

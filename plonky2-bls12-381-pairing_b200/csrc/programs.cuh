@@ -109,7 +109,7 @@ B381_DEV B381_INL void prog_f12_product_raw(const Ctx& cx, const uint32_t* in, s
   f12_load_raw(cx, 0, in);
   for (size_t i = 1; i < cnt; i++) {
     f12_load_raw(cx, 6, in + i * stride);
-    f12_mul(cx, 0, 0, 6, 12);
+    f12_mul(cx, 0, 0, 6, 12, 18);
   }
   f12_store_raw(cx, out, 0);
 }
@@ -119,7 +119,7 @@ B381_DEV B381_INL int prog_f12_mul(const Ctx& cx, const uint32_t* a, const uint3
   int err = 0;
   if (!f12_load_ext(cx, 0, a)) err |= ERR_NOT_CANONICAL;
   if (!f12_load_ext(cx, 6, b)) err |= ERR_NOT_CANONICAL;
-  f12_mul(cx, 0, 0, 6, 12);
+  f12_mul(cx, 0, 0, 6, 12, 18);
   f12_store_ext(cx, out, 0);
   return err;
 }
@@ -148,7 +148,7 @@ B381_DEV B381_INL int prog_wbasis_mul(const Ctx& cx, const uint32_t* a, const ui
   }
   if (!f12_load_ext(cx, 0, ta)) err |= ERR_NOT_CANONICAL;
   if (!f12_load_ext(cx, 6, tb)) err |= ERR_NOT_CANONICAL;
-  f12_mul(cx, 0, 0, 6, 12);
+  f12_mul(cx, 0, 0, 6, 12, 18);
   f12_store_ext(cx, ta, 0);
   for (int idx = 0; idx < 12; idx++) {
     int s, h;

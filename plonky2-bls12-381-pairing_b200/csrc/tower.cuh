@@ -659,9 +659,9 @@ B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
 }
 
 // Fp12 multiplication r = a * b (3 Fp6 muls); fq12_target_tree.rs:130-141.
-// r may alias a or b.  t = 16 scratch slots.
-B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t) {
-  const int aa = t, bb = t + 3, sa = t + 6, sb = t + 9, w = t + 12;   // w: 4 slots
+// r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 10 slots (sa, sb, 4 for f6_mul).
+B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
+  const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3, w = t2 + 6;   // w: 4 slots
   f6_mul(cx, aa, a, b, w);
   f6_mul(cx, bb, a + 3, b + 3, w);
   for (int i = 0; i < 3; i++) {
@@ -675,9 +675,10 @@ B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t) {
   lin(cx, r + 2, aa + 2, bb + 1, L_ADD);
 }
 
-// Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  t = 10 scratch slots.
-B381_DEV void f12_sqr(const Ctx& cx, int f, int t) {
-  const int ab = t, s = t + 3, w = t + 6;         // w: 4 slots
+// Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  Scratch: t = 7 slots, s3 = 3 more
+// slots (the Miller loops pass the line-coefficient slots, which are dead while f is squared).
+B381_DEV void f12_sqr(const Ctx& cx, int f, int t, int s3) {
+  const int ab = t, s = s3, w = t + 3;            // w: 4 slots
   f6_mul(cx, ab, f, f + 3, w);                    // ab = a0 a1
   for (int i = 0; i < 3; i++) lin(cx, s + i, f + i, f + 3 + i, L_ADD);      // s = a0 + a1
   // u = a0 + v a1 = (a00 + xi a12, a01 + a10, a02 + a11), built in place over a1
@@ -809,7 +810,7 @@ B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int acc2, int t
   for (int b = 62; b >= 0; b--) {
     f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur);
     const int sw = cur; cur = nxt; nxt = sw;
-    if ((xabs >> b) & 1) f12_mul(cx, cur, cur, a, t);
+    if ((xabs >> b) & 1) f12_mul(cx, cur, cur, a, t, t + 6);
   }
   for (int i = 0; i < 3; i++) lin(cx, r + i, cur + i, -1, L_COPY);
   for (int i = 3; i < 6; i++) lin(cx, r + i, cur + i, -1, L_NEG);
@@ -879,7 +880,7 @@ B381_DEV void ark_miller_loop(const Ctx& cx, const MillerSlots& s) {
   f2_set_small(S_(s.R + 2), 1);
   const uint64_t xabs = B381_X_ABS;
   for (int b = 62; b >= 0; b--) {
-    if (b != 62) f12_sqr(cx, s.f, s.T);           // first squaring is 1^2
+    if (b != 62) f12_sqr(cx, s.f, s.T, s.L);      // first squaring is 1^2
     ark_double_step(cx, s.R, s.L, s.T);
     ark_ell(cx, s.f, s.L, s.P, s.T);
     if ((xabs >> b) & 1) {
@@ -967,7 +968,7 @@ B381_DEV void zk_miller_loop(const Ctx& cx, const MillerSlots& s) {
       zk_add_step(cx, s.R, s.Q, s.L, s.T);
       zk_ell(cx, s.f, s.L, s.P, s.T);
     }
-    f12_sqr(cx, s.f, s.T);
+    f12_sqr(cx, s.f, s.T, s.L);
   }
   zk_double_step(cx, s.R, s.L, s.T);
   zk_ell(cx, s.f, s.L, s.P, s.T);
@@ -988,29 +989,29 @@ B381_DEV void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
   f12_copy(cx, r, f);
   f12_conj(cx, r);                                // f1 = conj(f)
   f12_inv(cx, f, T);                              // f2 = f^-1
-  f12_mul(cx, r, r, f, T);                        // r = f1 f2
+  f12_mul(cx, r, r, f, T, T + 6);                        // r = f1 f2
   f12_copy(cx, f, r);                             // f2 = r
   f12_frobenius(cx, r, 2);
-  f12_mul(cx, r, r, f, T);
+  f12_mul(cx, r, r, f, T, T + 6);
   // hard part
   f12_cyclotomic_square(cx, y0, r);                                 // y0 = r^2
   f12_exp_by_x(cx, y1, r, acc, acc2, T);                                       // y1 = r^x
   f12_copy(cx, y2, r); f12_conj(cx, y2);                            // y2 = r^-1
-  f12_mul(cx, y1, y1, y2, T);
+  f12_mul(cx, y1, y1, y2, T, T + 6);
   f12_exp_by_x(cx, y2, y1, acc, acc2, T);
   f12_conj(cx, y1);
-  f12_mul(cx, y1, y1, y2, T);
+  f12_mul(cx, y1, y1, y2, T, T + 6);
   f12_exp_by_x(cx, y2, y1, acc, acc2, T);
   f12_frobenius(cx, y1, 1);
-  f12_mul(cx, y1, y1, y2, T);
-  f12_mul(cx, r, r, y0, T);
+  f12_mul(cx, y1, y1, y2, T, T + 6);
+  f12_mul(cx, r, r, y0, T, T + 6);
   f12_exp_by_x(cx, y0, y1, acc, acc2, T);
   f12_exp_by_x(cx, y2, y0, acc, acc2, T);
   f12_copy(cx, y0, y1); f12_frobenius(cx, y0, 2);
   f12_conj(cx, y1);
-  f12_mul(cx, y1, y1, y2, T);
-  f12_mul(cx, y1, y1, y0, T);
-  f12_mul(cx, f, r, y1, T);
+  f12_mul(cx, y1, y1, y2, T, T + 6);
+  f12_mul(cx, y1, y1, y0, T, T + 6);
+  f12_mul(cx, f, r, y1, T, T + 6);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -70,7 +70,7 @@ int hs_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out) { Ct
 int hs_fp12_sqr(const uint32_t* a, uint32_t* out) {
   Ctx cx = make_ctx();
   bool ok = f12_load_ext(cx, 0, a);
-  f12_sqr(cx, 0, 6);
+  f12_sqr(cx, 0, 6, 13);
   f12_store_ext(cx, out, 0);
   return ok ? 0 : 1;
 }
@@ -122,7 +122,7 @@ int hs_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, 
   f12_set_one(cx, ML_ACC);
   for (size_t i = 0; i < n; i++) {
     err |= miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, mode);
-    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T);
+    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T, ML_T + 6);
   }
   f12_store_ext(cx, out, ML_ACC);
   return err;
