@@ -394,7 +394,9 @@ int read_err(cudaStream_t s) {
   return map_err(h);
 }
 
-constexpr size_t CHUNK = 1u << 17;    // pairs per pipelined chunk of the host-pointer API
+constexpr size_t CHUNK = 1u << 17;    // elements per pipelined chunk of the element-wise host-pointer API
+// pair kernels: chunks are whole rounds (4 x #SM x 256 pairs) so that no launch runs a partly filled round
+size_t pair_chunk() { return 4 * (size_t)g.sm_count * BLOCK; }
 
 // launch helpers (device pointers) ----------------------------------------------------------------------
 // A launch is limited to a few rounds per CTA: CTAs of different SMs are only aligned at launch
@@ -483,6 +485,7 @@ bool bad_mode(int mode) { return mode != B381_MODE_ARK && mode != B381_MODE_ZK &
 enum PairKind { PK_MILLER, PK_PAIRING };
 
 int host_pairs(PairKind kind, const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  const size_t CHUNK = pair_chunk();
   size_t c = n < CHUNK ? n : CHUNK;
   int rc;
   if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * 24 * 4))) return rc;
@@ -714,7 +717,7 @@ int b381_final_exp(const uint32_t* f, uint32_t* out, size_t n) {
   REQUIRE_INIT();
   if (!f || !out || n == 0) return fail_arg("b381_final_exp: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(f, nullptr, out, n, 144, 0, 144, CHUNK,
+  return host_binary(f, nullptr, out, n, 144, 0, 144, pair_chunk(),
                      [](uint32_t* a, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) { return launch_final_exp(a, o, m, s, lane); });
 }
 
