@@ -294,11 +294,11 @@ def main():
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile))
-            traffic = tj.get("k_pairing_dram_bytes_per_launch_2p20")
+            traffic = tj.get("k_pairing_dram_bytes_per_step_2p20") if n == PAIRS_PER_GPU else None
         except Exception:
             traffic = None
     roofline = {"bound": "imad", "achieved": alg_ginst, "peak": pk.value, "unit": "G IMAD.WIDE/s", "frac": alg_ginst / pk.value,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_note": "DRAM bytes per step (28 launches) from profiles/ncu_traffic.json; algorithmic bytes per step = pairs x 864",
                 "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
                         "peak = IMAD.WIDE issue rate measured live by b381_imad_peak (%.0f MHz); the kernel executes 421 IMAD per Fp mul "
                         "(14 x 28-bit limbs + 15-row reduction), i.e. executed-instruction fraction = frac x 1.40; HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
