@@ -226,6 +226,21 @@ B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
   B381_CHECK(t.cb < 120.0, "acc_mac: column overflow");
 }
 
+// Same as acc_mac but without the conservative column bookkeeping: used only for the Karatsuba
+// cross terms of a sum of products, where the bound is established algebraically by the caller
+// (f2_sop in tower.cuh).
+B381_HD B381_INL void acc_mac_cross(Acc& t, const Fp& a, const Fp& b) {
+#pragma unroll
+  for (int i = 0; i < NL; i++)
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      if (i == NL - 1 || j == NL - 1) B381_MACS(t.c[i + j], a.l[i], b.l[j]);
+      else B381_MACU(t.c[i + j], a.l[i], b.l[j]);
+    }
+  B381_TB(t.mag += a.mag * b.mag;)
+  B381_CHECK(a.nonneg && b.nonneg, "acc_mac_cross: operand limbs 0..12 must be non-negative");
+}
+
 B381_HD B381_INL void acc_add(Acc& r, const Acc& a, const Acc& b) {
 #pragma unroll
   for (int k = 0; k < 2 * NL - 1; k++) r.c[k] = a.c[k] + b.c[k];

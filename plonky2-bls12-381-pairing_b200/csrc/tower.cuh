@@ -344,6 +344,53 @@ B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u
   st_f2(r, r0, r1);
 }
 
+// Sum of products with ONE reduction per coefficient:  r = sum_{i<n} a_i * b_i  (n <= 3).
+//   P = sum a_i0 b_i0,  Q = sum a_i1 b_i1;   re = P - Q;   im = sum (a_i0+a_i1)(b_i0+b_i1) - P - Q
+// 3n MAC blocks + 2 reductions instead of n Fp2 multiplications (3n blocks + 2n reductions) followed
+// by memory-to-memory additions: the row-serial Montgomery reduction is the expensive half of a
+// multiplication, so the tower formulas are arranged as sums of products.
+// Column bound: limbs 0..12 of every stored value are non-negative, hence every partial sum of
+// -(P+Q) + sum_i (a_i0+a_i1)(b_i0+b_i1) lies between -(P+Q) and the final value
+// sum_i (a_i0 b_i1 + a_i1 b_i0), i.e. within 28 n units of 2^56, plus the (signed, tiny) products
+// of the top limbs, which the bound tracker adds from the operand magnitudes.
+B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
+  Acc P, Q;
+  acc_zero(P); acc_zero(Q);
+  B381_TB(double slack = 0;)
+  for (int i = 0; i < n; i++) {
+    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
+    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
+    Fp a0, a1, b0, b1;
+    ld_f2(a0, a1, ap);
+    ld_f2(b0, b1, bp);
+    acc_mac(P, a0, b0);
+    acc_mac(Q, a1, b1);
+    B381_TB(slack += 2 * 3.97e-4 * ((a0.mag + a1.mag + 2) * 2 + (b0.mag + b1.mag + 2) * 2) + 0.01;)
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * NL - 1; k++) {
+    const int64_t x = P.c[k], y = Q.c[k];
+    P.c[k] = x - y;                                 // re
+    Q.c[k] = -x - y;
+  }
+  B381_TB(P.cb = P.cb + Q.cb; Q.cb = P.cb; P.mag = P.mag + Q.mag; Q.mag = P.mag;)
+  for (int i = 0; i < n; i++) {
+    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
+    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
+    Fp a0, a1, b0, b1, sa, sb;
+    ld_f2(a0, a1, ap);
+    ld_f2(b0, b1, bp);
+    fp_add(sa, a0, a1);
+    fp_add(sb, b0, b1);
+    acc_mac_cross(Q, sa, sb);
+  }
+  B381_TB(Q.cb = 28.0 * n + slack;)                 // see the bound argument above
+  B381_CHECK(28.0 * n + slack + 16.0 < 127.0, "f2_sop: column bound");
+  Fp r0, r1;
+  acc_redc2(r0, P, r1, Q);
+  st_f2(r, r0, r1);
+}
+
 // r = (a + a2)^2 ; a2 may be null
 B381_NOINL void f2_sqr(u4* r, const u4* a, const u4* a2) {
   Fp a0, a1, r0, r1;
@@ -622,6 +669,10 @@ B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2
   sync_point(cx);
   f2_mul_ss(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, S_(b), b2 >= 0 ? S_(b2) : nullptr);
 }
+B381_DEV B381_INL void sop3(const Ctx& cx, int r, int a0, int b0, int a1, int b1, int a2, int b2) {
+  sync_point(cx);
+  f2_sop(S_(r), 3, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2));
+}
 B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { sync_point(cx); f2_sqr(S_(r), S_(a), nullptr); }
 B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { sync_point(cx); f2_sqr(S_(r), S_(a), S_(a2)); }
 B381_DEV B381_INL void kcomb(const Ctx& cx, int r, int a, int b, int c, int d, int mode) {
@@ -629,19 +680,17 @@ B381_DEV B381_INL void kcomb(const Ctx& cx, int r, int a, int b, int c, int d, i
   f2_kcomb(S_(r), S_(a), b >= 0 ? S_(b) : nullptr, c >= 0 ? S_(c) : nullptr, d >= 0 ? S_(d) : nullptr, mode);
 }
 
-// Fp6 multiplication r = a * b (Karatsuba, 6 Fp2 muls); fq6_target_tree.rs:172-214.
-// r must not alias a or b; t = 4 scratch slots.
+// Fp6 multiplication r = a * b; same value as the Karatsuba of fq6_target_tree.rs:172-214, arranged
+// as three sums of three products (schoolbook over v with v^3 = xi, one reduction per coefficient):
+//   c0 = a0 b0 + a1 (xi b2) + a2 (xi b1);  c1 = a0 b1 + a1 b0 + a2 (xi b2);  c2 = a0 b2 + a1 b1 + a2 b0
+// 27 MAC blocks + 6 reductions instead of 18 + 12.  r must not alias a or b; t = 2 scratch slots.
 B381_DEV B381_INL void f6_mul(const Ctx& cx, int r, int a, int b, int t) {
-  const int v0 = t, v1 = t + 1, v2 = t + 2, m = t + 3;
-  mul(cx, v0, a, b);
-  mul(cx, v1, a + 1, b + 1);
-  mul(cx, v2, a + 2, b + 2);
-  mul_ss(cx, m, a + 1, a + 2, b + 1, b + 2);
-  kcomb(cx, r, m, v1, v2, v0, K_XI_INNER);        // c0 = xi((a1+a2)(b1+b2) - v1 - v2) + v0
-  mul_ss(cx, m, a, a + 1, b, b + 1);
-  kcomb(cx, r + 1, m, v0, v1, v2, K_XI_D);        // c1 = (a0+a1)(b0+b1) - v0 - v1 + xi v2
-  mul_ss(cx, m, a, a + 2, b, b + 2);
-  kcomb(cx, r + 2, m, v0, v2, v1, K_PLAIN);       // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+  const int xb1 = t, xb2 = t + 1;
+  lin(cx, xb1, b + 1, -1, L_MULXI);
+  lin(cx, xb2, b + 2, -1, L_MULXI);
+  sop3(cx, r, a, b, a + 1, xb2, a + 2, xb1);
+  sop3(cx, r + 1, a, b + 1, a + 1, b, a + 2, xb2);
+  sop3(cx, r + 2, a, b + 2, a + 1, b + 1, a + 2, b);
 }
 
 // Fp6 squaring via f6_mul-style Karatsuba with squarings (3 sqr + 3 mul)
@@ -659,9 +708,9 @@ B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
 }
 
 // Fp12 multiplication r = a * b (3 Fp6 muls); fq12_target_tree.rs:130-141.
-// r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 10 slots (sa, sb, 4 for f6_mul).
+// r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 8 slots (sa, sb, 2 for f6_mul).
 B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
-  const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3, w = t2 + 6;   // w: 4 slots
+  const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3, w = t2 + 6;   // w: 2 slots
   f6_mul(cx, aa, a, b, w);
   f6_mul(cx, bb, a + 3, b + 3, w);
   for (int i = 0; i < 3; i++) {
@@ -675,10 +724,10 @@ B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
   lin(cx, r + 2, aa + 2, bb + 1, L_ADD);
 }
 
-// Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  Scratch: t = 7 slots, s3 = 3 more
+// Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  Scratch: t = 5 slots, s3 = 3 more
 // slots (the Miller loops pass the line-coefficient slots, which are dead while f is squared).
 B381_DEV void f12_sqr(const Ctx& cx, int f, int t, int s3) {
-  const int ab = t, s = s3, w = t + 3;            // w: 4 slots
+  const int ab = t, s = s3, w = t + 3;            // w: 2 slots
   f6_mul(cx, ab, f, f + 3, w);                    // ab = a0 a1
   for (int i = 0; i < 3; i++) lin(cx, s + i, f + i, f + 3 + i, L_ADD);      // s = a0 + a1
   // u = a0 + v a1 = (a00 + xi a12, a01 + a10, a02 + a11), built in place over a1
@@ -693,44 +742,25 @@ B381_DEV void f12_sqr(const Ctx& cx, int f, int t, int s3) {
   for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, ab + i, -1, L_DBL);        // c1 = 2 ab
 }
 
-// sparse multiplication f *= (c0 + c1 v + c4 v w), in place; fq12_target_tree.rs:157-176 and
-// the native twin /root/reference/src/miller_loop_native.rs:118-137.  13 Fp2 muls.
-// t = 9 scratch slots.
+// sparse multiplication f *= (c0 + c1 v + c4 v w), in place; same value as fq12_target_tree.rs:157-176
+// and the native twin /root/reference/src/miller_loop_native.rs:118-137 (mul_by_01 / mul_by_1
+// Karatsuba, 13 Fp2 muls), arranged as six sums of three products (18 products, 12 reductions
+// instead of 26).  With f = (a0,a1,a2 | b0,b1,b2):
+//   f0' = (a0 c0 + a2 xi c1 + b1 xi c4,  a0 c1 + a1 c0 + b2 xi c4,  a1 c1 + a2 c0 + b0 c4)
+//   f1' = (b0 c0 + b2 xi c1 + a2 xi c4,  b0 c1 + b1 c0 + a0 c4,     b1 c1 + b2 c0 + a1 c4)
+// t = 8 scratch slots (six outputs, xi c1, xi c4); the result is copied back over f.
 B381_DEV void f12_mul_by_014(const Ctx& cx, int f, int c0, int c1, int c4, int t) {
-  const int b0 = t, b1 = t + 1, b2 = t + 2, o = t + 3, p0 = t + 4, p1 = t + 5, m0 = t + 6, m1 = t + 7, m2 = t + 8;
-  // bb = f1.mul_by_1(c4) = (xi f12 c4, f10 c4, f11 c4)     (fq6_target_tree.rs:261-268)
-  mul(cx, b0, f + 5, c4);
-  lin(cx, b0, b0, -1, L_MULXI);
-  mul(cx, b1, f + 3, c4);
-  mul(cx, b2, f + 4, c4);
-  // s = f1 + f0 (in place over f1), o = c1 + c4
-  for (int i = 0; i < 3; i++) lin(cx, f + 3 + i, f + 3 + i, f + i, L_ADD);
-  lin(cx, o, c1, c4, L_ADD);
-  // n = s.mul_by_01(c0, o)                                   (fq6_target_tree.rs:232-259)
-  mul(cx, p0, f + 3, c0);
-  mul(cx, p1, f + 4, o);
-  mul_ss(cx, m0, f + 4, f + 5, o, -1);
-  mul_ss(cx, m1, f + 3, f + 4, c0, o);
-  mul_ss(cx, m2, f + 3, f + 5, c0, -1);
-  kcomb(cx, f + 3, m0, p1, -1, p0, K_XI_INNER);   // n0 = xi(o (s1+s2) - p1) + p0
-  kcomb(cx, f + 4, m1, p0, p1, -1, K_PLAIN);      // n1 = (c0+o)(s0+s1) - p0 - p1
-  kcomb(cx, f + 5, m2, p0, -1, p1, K_PLAIN);      // n2 = c0 (s0+s2) - p0 + p1
-  // aa = f0.mul_by_01(c0, c1), written over f0
-  mul(cx, p0, f, c0);
-  mul(cx, p1, f + 1, c1);
-  mul_ss(cx, m0, f + 1, f + 2, c1, -1);
-  mul_ss(cx, m1, f, f + 1, c0, c1);
-  mul_ss(cx, m2, f, f + 2, c0, -1);
-  kcomb(cx, f, m0, p1, -1, p0, K_XI_INNER);
-  kcomb(cx, f + 1, m1, p0, p1, -1, K_PLAIN);
-  kcomb(cx, f + 2, m2, p0, -1, p1, K_PLAIN);
-  // new c1 = n - aa - bb ; new c0 = aa + v bb = aa + (xi bb2, bb0, bb1)
-  kcomb(cx, f + 3, f + 3, f, b0, -1, K_PLAIN);
-  kcomb(cx, f + 4, f + 4, f + 1, b1, -1, K_PLAIN);
-  kcomb(cx, f + 5, f + 5, f + 2, b2, -1, K_PLAIN);
-  lin(cx, f, f, b2, L_XIADD);
-  lin(cx, f + 1, f + 1, b0, L_ADD);
-  lin(cx, f + 2, f + 2, b1, L_ADD);
+  const int a0 = f, a1 = f + 1, a2 = f + 2, b0 = f + 3, b1 = f + 4, b2 = f + 5;
+  const int xc1 = t + 6, xc4 = t + 7;
+  lin(cx, xc1, c1, -1, L_MULXI);
+  lin(cx, xc4, c4, -1, L_MULXI);
+  sop3(cx, t + 0, a0, c0, a2, xc1, b1, xc4);
+  sop3(cx, t + 1, a0, c1, a1, c0, b2, xc4);
+  sop3(cx, t + 2, a1, c1, a2, c0, b0, c4);
+  sop3(cx, t + 3, b0, c0, b2, xc1, a2, xc4);
+  sop3(cx, t + 4, b0, c1, b1, c0, a0, c4);
+  sop3(cx, t + 5, b1, c1, b2, c0, a1, c4);
+  for (int i = 0; i < 6; i++) lin(cx, f + i, t + i, -1, L_COPY);
 }
 
 B381_DEV B381_INL void f12_set_one(const Ctx& cx, int f) {
