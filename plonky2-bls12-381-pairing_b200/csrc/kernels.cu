@@ -330,7 +330,9 @@ struct State {
   bool init = false;
   int device = -1;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
-  cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaStream_t stream[2] = {nullptr, nullptr};   // stream[0]: all kernels of the host-pointer API; stream[1]: spare lane
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined host-pointer API
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   u4* garena[2] = {nullptr, nullptr};
   int* d_err = nullptr;
   uint32_t* d_in1[2] = {nullptr, nullptr};      // staging (device) per lane
@@ -449,6 +451,32 @@ int reduce_raw(uint32_t* ping, uint32_t* pong, size_t cnt, cudaStream_t s, int l
   return 0;
 }
 
+// accumulate the Miller values of `n` device-resident pairs into the per-thread partial products
+// (every launch uses the full grid so that partial[] always has sm_count * BLOCK entries)
+int launch_multi_accumulate(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, bool first, cudaStream_t s, int lane) {
+  uint32_t* ping = g.d_partial[lane];
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_multi_miller<<<g.sm_count, BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, m, mode, ping, !(first && off == 0), g.garena[lane], g.d_err);
+    g.launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// tree-reduce the partial products, optional final exponentiation, result (external format) -> out144
+int launch_multi_finish(uint32_t* out144, int do_fe, cudaStream_t s, int lane) {
+  uint32_t* ping = g.d_partial[lane];
+  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
+  uint32_t* res = nullptr;
+  int rc = reduce_raw(ping, pong, (size_t)g.sm_count * BLOCK, s, lane, &res);
+  if (rc) return rc;
+  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, out144, do_fe, g.garena[lane], g.d_err);
+  g.launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // product of all Miller values of device-resident pairs -> out144 (device, external format), optional final exp
 int launch_multi(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe, cudaStream_t s, int lane) {
   if (mode == B381_MODE_LITERAL) {                 // the reference's multi_miller_loop as written returns 1
@@ -458,23 +486,9 @@ int launch_multi(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uin
     if (do_fe) { int rc = launch_final_exp(out144, out144, 1, s, lane); if (rc) return rc; }
     return 0;
   }
-  int grid = grid_for(n);
-  size_t nthreads = (size_t)grid * BLOCK;
-  uint32_t* ping = g.d_partial[lane];
-  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {     // every launch uses the same grid and keeps accumulating
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_multi_miller<<<grid, BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, m, mode, ping, off != 0, g.garena[lane], g.d_err);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  uint32_t* res = nullptr;
-  int rc = reduce_raw(ping, pong, nthreads, s, lane, &res);
+  int rc = launch_multi_accumulate(g1, g2, inf, n, mode, true, s, lane);
   if (rc) return rc;
-  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, out144, do_fe, g.garena[lane], g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
+  return launch_multi_finish(out144, do_fe, s, lane);
 }
 
 bool bad_mode(int mode) { return mode != B381_MODE_ARK && mode != B381_MODE_ZK && mode != B381_MODE_LITERAL; }
@@ -499,21 +513,32 @@ int host_pairs(PairKind kind, const uint32_t* g1, const uint32_t* g2, const uint
       g.cap_inf = c;
     }
   }
+  // three-stream pipeline over double-buffered staging: copies of chunk c+1 / c-1 overlap the kernels
+  // of chunk c, and ALL kernels run on one stream (two kernels sharing the chip would break the
+  // chip-wide lock step the launches rely on).
+  cudaStream_t sk = g.stream[0];
   int lane = 0;
-  for (size_t off = 0; off < n; off += CHUNK, lane ^= 1) {
+  size_t nchunks = 0;
+  for (size_t off = 0; off < n; off += CHUNK, lane ^= 1, nchunks++) {
     size_t m = n - off < CHUNK ? n - off : CHUNK;
-    cudaStream_t s = g.stream[lane];
-    CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, s));
-    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, s));
+    if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));        // staging inputs free again
+    CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, g.s_in));
+    CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, g.s_in));
+    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
+    CU(cudaEventRecord(g.ev_in[lane], g.s_in));
+    CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
+    if (nchunks >= 2) CU(cudaStreamWaitEvent(sk, g.ev_out[lane], 0));          // staging output drained
     const uint8_t* dinf = inf ? g.d_inf[lane] : nullptr;
-    if (kind == PK_MILLER) rc = launch_miller(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, s, lane);
-    else rc = launch_pairing(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, s, lane);
+    if (kind == PK_MILLER) rc = launch_miller(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, sk, 0);
+    else rc = launch_pairing(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, sk, 0);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out + off * 144, g.d_out[lane], m * 144 * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(g.ev_k[lane], sk));
+    CU(cudaStreamWaitEvent(g.s_out, g.ev_k[lane], 0));
+    CU(cudaMemcpyAsync(out + off * 144, g.d_out[lane], m * 144 * 4, cudaMemcpyDeviceToHost, g.s_out));
+    CU(cudaEventRecord(g.ev_out[lane], g.s_out));
   }
-  CU(cudaStreamSynchronize(g.stream[1]));
-  return read_err(g.stream[0]);
+  CU(cudaStreamSynchronize(g.s_out));
+  return read_err(sk);
 }
 
 // generic element-wise host pipeline: two inputs of wi words, one output of wo words per element
@@ -524,17 +549,25 @@ int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, s
   if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * wa * 4))) return rc;
   if (b && (rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * wb * 4))) return rc;
   if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * wo * 4))) return rc;
+  cudaStream_t sk = g.stream[0];                    // same three-stream pipeline as host_pairs
   int lane = 0;
-  for (size_t off = 0; off < n; off += chunk, lane ^= 1) {
+  size_t nchunks = 0;
+  for (size_t off = 0; off < n; off += chunk, lane ^= 1, nchunks++) {
     size_t m = n - off < chunk ? n - off : chunk;
-    cudaStream_t s = g.stream[lane];
-    CU(cudaMemcpyAsync(g.d_in1[lane], a + off * wa, m * wa * 4, cudaMemcpyHostToDevice, s));
-    if (b) CU(cudaMemcpyAsync(g.d_in2[lane], b + off * wb, m * wb * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = launch(g.d_in1[lane], g.d_in2[lane], g.d_out[lane], m, s, lane))) return rc;
-    CU(cudaMemcpyAsync(out + off * wo, g.d_out[lane], m * wo * 4, cudaMemcpyDeviceToHost, s));
+    if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));
+    CU(cudaMemcpyAsync(g.d_in1[lane], a + off * wa, m * wa * 4, cudaMemcpyHostToDevice, g.s_in));
+    if (b) CU(cudaMemcpyAsync(g.d_in2[lane], b + off * wb, m * wb * 4, cudaMemcpyHostToDevice, g.s_in));
+    CU(cudaEventRecord(g.ev_in[lane], g.s_in));
+    CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
+    if (nchunks >= 2) CU(cudaStreamWaitEvent(sk, g.ev_out[lane], 0));
+    if ((rc = launch(g.d_in1[lane], g.d_in2[lane], g.d_out[lane], m, sk, 0))) return rc;
+    CU(cudaEventRecord(g.ev_k[lane], sk));
+    CU(cudaStreamWaitEvent(g.s_out, g.ev_k[lane], 0));
+    CU(cudaMemcpyAsync(out + off * wo, g.d_out[lane], m * wo * 4, cudaMemcpyDeviceToHost, g.s_out));
+    CU(cudaEventRecord(g.ev_out[lane], g.s_out));
   }
-  CU(cudaStreamSynchronize(g.stream[1]));
-  return read_err(g.stream[0]);
+  CU(cudaStreamSynchronize(g.s_out));
+  return read_err(sk);
 }
 
 int elem_grid(size_t n, int threads, int per_sm) {
@@ -575,7 +608,12 @@ int b381_init(int device) {
     g.last_error = "device lacks 224 KB opt-in shared memory per block (built for sm_100a)";
     return B381_E_CUDA;
   }
+  CU(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
   for (int l = 0; l < 2; l++) {
+    CU(cudaEventCreateWithFlags(&g.ev_in[l], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.ev_k[l], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.ev_out[l], cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&g.stream[l], cudaStreamNonBlocking));
     CU(cudaMalloc((void**)&g.garena[l], GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count));
     CU(cudaMalloc((void**)&g.d_partial[l], 2 * (size_t)g.sm_count * BLOCK * RAW_WORDS * sizeof(uint32_t)));
@@ -600,6 +638,7 @@ int b381_shutdown(void) {
   cudaDeviceSynchronize();
   for (int l = 0; l < 2; l++) {
     if (g.stream[l]) cudaStreamDestroy(g.stream[l]);
+    if (g.ev_in[l]) { cudaEventDestroy(g.ev_in[l]); cudaEventDestroy(g.ev_k[l]); cudaEventDestroy(g.ev_out[l]); g.ev_in[l] = g.ev_k[l] = g.ev_out[l] = nullptr; }
     cudaFree(g.garena[l]); cudaFree(g.d_partial[l]); cudaFree(g.d_dump[l]); g.d_dump[l] = nullptr;
     cudaFree(g.d_in1[l]); cudaFree(g.d_in2[l]); cudaFree(g.d_inf[l]); cudaFree(g.d_out[l]);
     g.stream[l] = nullptr; g.garena[l] = nullptr; g.d_partial[l] = nullptr;
@@ -607,6 +646,7 @@ int b381_shutdown(void) {
   }
   cudaFree(g.d_err);
   g.d_err = nullptr;
+  if (g.s_in) { cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out); g.s_in = g.s_out = nullptr; }
   g.cap_in1 = g.cap_in2 = g.cap_inf = g.cap_out = 0;
   g.init = false;
   return B381_OK;
@@ -722,24 +762,41 @@ int b381_final_exp(const uint32_t* f, uint32_t* out, size_t n) {
 }
 
 static int multi_host(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe) {
-  // stage the whole batch (288 B per pair), run on lane 0
+  // chunked like host_pairs: H2D of chunk c+1 overlaps the Miller kernels of chunk c; the per-thread
+  // partial products stay on the device and are reduced once at the end.
+  const size_t CHUNK = pair_chunk();
+  size_t c = n < CHUNK ? n : CHUNK;
   int rc;
-  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * 24 * 4))) return rc;
-  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, n * 48 * 4))) return rc;
+  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * 24 * 4))) return rc;
+  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * 48 * 4))) return rc;
   if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, 144 * 4))) return rc;
-  if (inf && n > g.cap_inf) {
+  if (inf && c > g.cap_inf) {
     for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
     g.cap_inf = 0;
-    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], n));
-    g.cap_inf = n;
+    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
+    g.cap_inf = c;
   }
-  cudaStream_t s = g.stream[0];
-  CU(cudaMemcpyAsync(g.d_in1[0], g1, n * 24 * 4, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(g.d_in2[0], g2, n * 48 * 4, cudaMemcpyHostToDevice, s));
-  if (inf) CU(cudaMemcpyAsync(g.d_inf[0], inf, n, cudaMemcpyHostToDevice, s));
-  if ((rc = launch_multi(g.d_in1[0], g.d_in2[0], inf ? g.d_inf[0] : nullptr, g.d_out[0], n, mode, do_fe, s, 0))) return rc;
-  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, s));
-  return read_err(s);
+  cudaStream_t sk = g.stream[0];
+  if (mode == B381_MODE_LITERAL) {
+    if ((rc = launch_multi(nullptr, nullptr, nullptr, g.d_out[0], n, mode, do_fe, sk, 0))) return rc;
+  } else {
+    int lane = 0;
+    size_t nchunks = 0;
+    for (size_t off = 0; off < n; off += CHUNK, lane ^= 1, nchunks++) {
+      size_t m = n - off < CHUNK ? n - off : CHUNK;
+      if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));
+      CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, g.s_in));
+      CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, g.s_in));
+      if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
+      CU(cudaEventRecord(g.ev_in[lane], g.s_in));
+      CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
+      if ((rc = launch_multi_accumulate(g.d_in1[lane], g.d_in2[lane], inf ? g.d_inf[lane] : nullptr, m, mode, off == 0, sk, 0))) return rc;
+      CU(cudaEventRecord(g.ev_k[lane], sk));
+    }
+    if ((rc = launch_multi_finish(g.d_out[0], do_fe, sk, 0))) return rc;
+  }
+  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, sk));
+  return read_err(sk);
 }
 
 int b381_multi_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode) {
