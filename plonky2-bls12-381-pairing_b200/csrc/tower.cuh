@@ -557,8 +557,9 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
 // a^2 + xi b^2 is accumulated in the column domain (4 MAC blocks, one reduction per coefficient)
 // and 2ab is one Karatsuba product: 7 x 196 + 4 x 225 + 4 x 15 IMAD instead of three separate
 // squarings (6 x 196 + 6 x 225) plus seven memory-to-memory linear operations.  The linear feedback
-// of z is absorbed by the weak reduction, so every output has magnitude <= 2.02 p.
-B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode) {
+// of z (magnitude M -> 9 + 2M) is absorbed by the weak reduction when `reduce` is set; callers set it
+// at least every sixth squaring (2 -> 13 -> 35 -> 79 -> 167 -> 343 stays far below the 14-limb range).
+B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
   Fp a0, a1, b0, b1, t00, t01, t10, t11;
   ld_f2(a0, a1, a);
   ld_f2(b0, b1, b);
@@ -592,7 +593,7 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
     Fp w0, w1;
     fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
     fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
-    fp_wreduce(w0); fp_wreduce(w1);
+    if (reduce) { fp_wreduce(w0); fp_wreduce(w1); } else f2_norm(w0, w1);
     st_f2(mode == 0 ? ra : rb, w0, w1);
   }
   f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
@@ -603,7 +604,7 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
   Fp x0, x1;
   fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
   fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
-  fp_wreduce(x0); fp_wreduce(x1);
+  if (reduce) { fp_wreduce(x0); fp_wreduce(x1); } else f2_norm(x0, x1);
   fp_dbl(x0, x0); fp_dbl(x1, x1);
   f2_norm(x0, x1);
   st_f2(mode == 0 ? rb : ra, x0, x1);
@@ -822,14 +823,14 @@ B381_DEV void f12_inv(const Ctx& cx, int f, int t) {
 // /root/reference/src/fields_as_trees/miller_loop.rs:46-104.  With z0=c0.c0, z4=c0.c1, z3=c0.c2,
 // z2=c1.c0, z1=c1.c1, z5=c1.c2:  (z0',z1') from fp4(z0,z1); (z4',z5') from fp4(z2,z3);
 // (z2',z3') from fp4(z4,z5) with the xi twist.  Three fused primitive calls, no scratch.
-B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s) {
+B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s, int reduce = 1) {
   const int z0 = 0, z4 = 1, z3 = 2, z2 = 3, z1 = 4, z5 = 5;
   sync_point(cx);
-  f2_cyc_fp4(S_(d + z0), S_(d + z1), S_(s + z0), S_(s + z1), S_(s + z0), S_(s + z1), 0);
+  f2_cyc_fp4(S_(d + z0), S_(d + z1), S_(s + z0), S_(s + z1), S_(s + z0), S_(s + z1), 0, reduce);
   sync_point(cx);
-  f2_cyc_fp4(S_(d + z4), S_(d + z5), S_(s + z2), S_(s + z3), S_(s + z4), S_(s + z5), 0);
+  f2_cyc_fp4(S_(d + z4), S_(d + z5), S_(s + z2), S_(s + z3), S_(s + z4), S_(s + z5), 0, reduce);
   sync_point(cx);
-  f2_cyc_fp4(S_(d + z2), S_(d + z3), S_(s + z4), S_(s + z5), S_(s + z2), S_(s + z3), 1);
+  f2_cyc_fp4(S_(d + z2), S_(d + z3), S_(s + z4), S_(s + z5), S_(s + z2), S_(s + z3), 1, reduce);
 }
 
 // r = conj(a^|x|): ark Bls12::exp_by_x (x < 0).  The running value ping-pongs between the two
@@ -837,10 +838,13 @@ B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s) {
 B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int acc2, int t) {
   int cur = acc, nxt = acc2;
   const uint64_t xabs = B381_X_ABS;
+  int since = 0;                                  // squarings since the last weak reduction
   for (int b = 62; b >= 0; b--) {
-    f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur);
+    const int red = (++since == 4) || b == 0;     // input magnitude <= ~30 -> 69 -> 147 -> 303 -> reduced (bound-tracked)
+    f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur, red);
+    if (red) since = 0;
     const int sw = cur; cur = nxt; nxt = sw;
-    if ((xabs >> b) & 1) f12_mul(cx, cur, cur, a, t, t + 6);
+    if ((xabs >> b) & 1) { f12_mul(cx, cur, cur, a, t, t + 6); since = 0; }
   }
   for (int i = 0; i < 3; i++) lin(cx, r + i, cur + i, -1, L_COPY);
   for (int i = 3; i < 6; i++) lin(cx, r + i, cur + i, -1, L_NEG);
