@@ -126,24 +126,26 @@ k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* 
   B381_TMEM_END();
 }
 
-// every thread multiplies the Miller values of its pairs into a private accumulator and dumps it
-// (internal format) to partial[global thread id]
+// every thread runs the Miller loops of TWO pairs per round with shared squarings, multiplies the
+// result into a private accumulator and dumps it (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
 k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, int accumulate, u4* garena, int* err) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  if (accumulate) f12_load_raw(cx, ML_ACC, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x));
-  else f12_set_one(cx, ML_ACC);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  if (accumulate) f12_load_raw(cx, M2_ACC, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x));
+  else f12_set_one(cx, M2_ACC);
+  for (size_t base = (size_t)blockIdx.x * BLOCK * 2; base < n; base += (size_t)gridDim.x * BLOCK * 2) {
     __syncthreads();
-    size_t i = base + threadIdx.x;
-    const bool active = i < n;
-    if (!active) i = n - 1;
-    int e = miller_to_slots(cx, g1 + 24 * i, g2 + 48 * i, active ? (inf ? inf[i] : 0) : 3, mode);   // inactive: contributes 1
-    if (active) report(e, err);
-    f12_mul(cx, ML_ACC, ML_ACC, ML_F, ML_T, ML_T + 6);   // scratch ML_T..ML_T+15 overlaps R/Q/P, reloaded per pair
+    size_t i0 = base + 2 * (size_t)threadIdx.x, i1 = i0 + 1;
+    const bool act0 = i0 < n, act1 = i1 < n;        // inactive slots contribute 1
+    if (!act0) i0 = n - 1;
+    if (!act1) i1 = n - 1;
+    int e = miller2_to_slots(cx, g1 + 24 * i0, g2 + 48 * i0, act0 ? (inf ? inf[i0] : 0) : 3,
+                             g1 + 24 * i1, g2 + 48 * i1, act1 ? (inf ? inf[i1] : 0) : 3, mode);
+    if (act0) report(e, err);
+    f12_mul(cx, M2_ACC, M2_ACC, ML_F, ML_T, ML_T + 6);   // scratch ML_T .. ML_T+13 overlaps R/Q/P of pair one, reloaded per round
   }
-  f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), ML_ACC);
+  f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), M2_ACC);
   B381_TMEM_END();
 }
 
@@ -455,8 +457,9 @@ int reduce_raw(uint32_t* ping, uint32_t* pong, size_t cnt, cudaStream_t s, int l
 // (every launch uses the full grid so that partial[] always has sm_count * BLOCK entries)
 int launch_multi_accumulate(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, bool first, cudaStream_t s, int lane) {
   uint32_t* ping = g.d_partial[lane];
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+  const size_t per = 2 * pairs_per_launch();        // two pairs per thread per round
+  for (size_t off = 0; off < n; off += per) {
+    size_t m = n - off < per ? n - off : per;
     k_multi_miller<<<g.sm_count, BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, m, mode, ping, !(first && off == 0), g.garena[lane], g.d_err);
     g.launches++;
   }

@@ -19,6 +19,8 @@ constexpr int ML_F = 0, ML_L = 6, ML_T = 9, ML_R = 19, ML_Q = 22, ML_P = 24, ML_
 constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_F = 28, FE_Y0 = 28 /* f is dead once y0 is first written */, FE_Y1 = 34, FE_Y2 = 40, FE_R = 46, FE_NSLOTS = 52;
 // literal loop
 constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
+// shared-squaring multi-Miller (two pairs per thread): second pair's R, Q, P and the running product
+constexpr int M2_R2 = 25, M2_Q2 = 28, M2_P2 = 30, M2_ACC = 31, M2_NSLOTS = 37;
 constexpr int MAX_NSLOTS = 52;
 
 #define S_(i) slot(cx, (i))
@@ -68,6 +70,32 @@ B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const u
   if (mode == MODE_ZK) zk_miller_loop(cx, s);
   else ark_miller_loop(cx, s);
   if (ident) f12_set_one(cx, ML_F);
+  return err;
+}
+
+// Miller loops of TWO pairs with shared squarings into slots ML_F.. ; identity pairs contribute 1.
+B381_DEV B381_INL int miller2_to_slots(const Ctx& cx, const uint32_t* g1a, const uint32_t* g2a, int infa,
+                                       const uint32_t* g1b, const uint32_t* g2b, int infb, int mode) {
+  int err = 0;
+  bool ident[2] = {(infa & 3) != 0, (infb & 3) != 0};
+  const int Pj[2] = {ML_P, M2_P2}, Qj[2] = {ML_Q, M2_Q2};
+  const uint32_t* g1[2] = {g1a, g1b};
+  const uint32_t* g2[2] = {g2a, g2b};
+  for (int j = 0; j < 2; j++) {
+    if (ident[j]) {
+      f2_set_small(S_(Pj[j]), 0); f2_set_small(S_(Qj[j]), 0); f2_set_small(S_(Qj[j] + 1), 0);
+    } else {
+      if (!f2_load_ext(S_(Pj[j]), g1[j])) err |= ERR_NOT_CANONICAL;
+      if (!f2_load_ext(S_(Qj[j]), g2[j])) err |= ERR_NOT_CANONICAL;
+      if (!f2_load_ext(S_(Qj[j] + 1), g2[j] + 24)) err |= ERR_NOT_CANONICAL;
+    }
+  }
+  MultiSlots s;
+  s.f = ML_F; s.L = ML_L; s.T = ML_T;
+  s.R[0] = ML_R; s.Q[0] = ML_Q; s.P[0] = ML_P;
+  s.R[1] = M2_R2; s.Q[1] = M2_Q2; s.P[1] = M2_P2;
+  if (mode == MODE_ZK) zk_miller_loop_multi(cx, s, 2, ident);
+  else ark_miller_loop_multi(cx, s, 2, ident);
   return err;
 }
 

@@ -619,6 +619,23 @@ B381_NOINL void f2_set_small(u4* r, int one) {
   st_f2(r, c0, c1);
 }
 
+// r = cond ? (one ? 1 : 0) : r, executed by EVERY thread (the load and the store are warp-uniform,
+// only the selected value is per-thread): slots may live in tensor memory, whose tcgen05.ld/st are
+// .sync.aligned and must never sit under a divergent branch.
+B381_NOINL void f2_override_if(u4* r, int cond, int one) {
+  Fp c0, c1, k0, k1;
+  ld_f2(c0, c1, r);
+  fp_zero(k0); fp_zero(k1);
+  if (one) fp_const(k0, g_ct.one);
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    c0.l[i] = cond ? k0.l[i] : c0.l[i];
+    c1.l[i] = cond ? k1.l[i] : c1.l[i];
+  }
+  B381_TB(if (cond) { c0.mag = c1.mag = 1; c0.lb = c1.lb = 1; c0.nonneg = c1.nonneg = true; })
+  st_f2(r, c0, c1);
+}
+
 // canonical test a == 0 (full reduction; rare path)
 B381_NOINL bool f2_is_zero(const u4* a) {
   Fp a0, a1;
@@ -925,6 +942,42 @@ B381_DEV void ark_miller_loop(const Ctx& cx, const MillerSlots& s) {
   f12_conj(cx, s.f);
 }
 
+// Multi-Miller loop with SHARED squarings (ark Bls12::multi_miller_loop squares f once per bit for
+// a whole chunk of pairs): k pairs per thread accumulate into one f.  Pair j uses
+// R at s.R + 6 j? no: slot bases are given per pair.  A pair flagged as identity multiplies by the
+// line (1, 0, 0), i.e. by one, so control flow stays uniform.
+struct MultiSlots { int f, L, T; int R[2], Q[2], P[2]; };
+
+B381_DEV B381_INL void line_to_one_if(const Ctx& cx, int L, bool ident, int one_at) {
+  for (int i = 0; i < 3; i++) f2_override_if(S_(L + i), ident, i == one_at);   // uniform: L + 2 is a TMEM slot
+}
+
+B381_DEV void ark_miller_loop_multi(const Ctx& cx, const MultiSlots& s, int k, const bool* ident) {
+  f12_set_one(cx, s.f);
+  for (int j = 0; j < k; j++) {
+    lin(cx, s.R[j], s.Q[j], -1, L_COPY);
+    lin(cx, s.R[j] + 1, s.Q[j] + 1, -1, L_COPY);
+    f2_set_small(S_(s.R[j] + 2), 1);
+  }
+  const uint64_t xabs = B381_X_ABS;
+  for (int b = 62; b >= 0; b--) {
+    if (b != 62) f12_sqr(cx, s.f, s.T, s.L);
+    for (int j = 0; j < k; j++) {
+      ark_double_step(cx, s.R[j], s.L, s.T);
+      line_to_one_if(cx, s.L, ident[j], 0);
+      ark_ell(cx, s.f, s.L, s.P[j], s.T);
+    }
+    if ((xabs >> b) & 1) {
+      for (int j = 0; j < k; j++) {
+        ark_add_step(cx, s.R[j], s.Q[j], s.L, s.T);
+        line_to_one_if(cx, s.L, ident[j], 0);
+        ark_ell(cx, s.f, s.L, s.P[j], s.T);
+      }
+    }
+  }
+  f12_conj(cx, s.f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // ZK mode: /root/reference/src/miller_loop_native.rs:27-116 with ell (:139-152) wired in.
 // ---------------------------------------------------------------------------------------------
@@ -1006,6 +1059,38 @@ B381_DEV void zk_miller_loop(const Ctx& cx, const MillerSlots& s) {
   }
   zk_double_step(cx, s.R, s.L, s.T);
   zk_ell(cx, s.f, s.L, s.P, s.T);
+  f12_conj(cx, s.f);
+}
+
+// ZK-mode multi-Miller loop with shared squarings (the Adder driver of
+// /root/reference/src/miller_loop_native.rs:154-212 loops over all terms inside each step).
+B381_DEV void zk_miller_loop_multi(const Ctx& cx, const MultiSlots& s, int k, const bool* ident) {
+  f12_set_one(cx, s.f);
+  for (int j = 0; j < k; j++) {
+    lin(cx, s.R[j], s.Q[j], -1, L_COPY);
+    lin(cx, s.R[j] + 1, s.Q[j] + 1, -1, L_COPY);
+    f2_set_small(S_(s.R[j] + 2), 1);
+  }
+  const uint64_t xh = B381_X_ABS >> 1;
+  bool found_one = false;
+  for (int b = 63; b >= -1; b--) {
+    bool bit = b >= 0 ? ((xh >> b) & 1) : false;
+    if (b >= 0 && !found_one) { found_one = bit; continue; }
+    for (int j = 0; j < k; j++) {
+      zk_double_step(cx, s.R[j], s.L, s.T);
+      line_to_one_if(cx, s.L, ident[j], 2);          // zk_ell uses (L+2, L+1, L) as (c0, c1, c4)
+      zk_ell(cx, s.f, s.L, s.P[j], s.T);
+    }
+    if (b < 0) break;                              // the trailing doubling step of the driver (:109)
+    if (bit) {
+      for (int j = 0; j < k; j++) {
+        zk_add_step(cx, s.R[j], s.Q[j], s.L, s.T);
+        line_to_one_if(cx, s.L, ident[j], 2);
+        zk_ell(cx, s.f, s.L, s.P[j], s.T);
+      }
+    }
+    f12_sqr(cx, s.f, s.T, s.L);
+  }
   f12_conj(cx, s.f);
 }
 

@@ -275,6 +275,42 @@ def test_full_size_pairing_2p20_and_bls_shape(L, lib, z):
     assert list(o144) == o.f12_to_limbs32(o.F12_ONE)
 
 
+def test_field_microbench_sizes_against_c_port(L, lib):
+    """BASELINE config #2 shape at 2^22 elements: Fp products compared in full with the oracle's C
+    port; Fp12 products (2^14) likewise; plus commutativity as a size-independent property."""
+    rng = np.random.default_rng(49)
+    n = 1 << 22
+    base = rng.integers(0, 1 << 32, size=(4096, 12), dtype=np.uint64).astype(np.uint32)
+    base[:, 11] &= 0x0FFFFFFF                                 # < 2^380 < p: canonical Montgomery limbs
+    a = np.ascontiguousarray(base[rng.integers(0, 4096, size=n)]).reshape(-1)
+    b = np.ascontiguousarray(base[rng.integers(0, 4096, size=n)]).reshape(-1)
+    out = np.zeros(n * 12, dtype=np.uint32)
+    out2 = np.zeros(n * 12, dtype=np.uint32)
+    L.check(lib.b381_fp_mul(util.p32(a), util.p32(b), util.p32(out), n))
+    L.check(lib.b381_fp_mul(util.p32(b), util.p32(a), util.p32(out2), n))
+    assert np.array_equal(out, out2)
+    ref = util.load_ref_lib()
+    chk = np.zeros(n * 12, dtype=np.uint32)
+    ref.ref_fp_mul(util.p32(a), util.p32(b), util.p32(chk), n, 8)
+    assert np.array_equal(out, chk)
+    m = 1 << 14
+    x = np.ascontiguousarray(base[rng.integers(0, 4096, size=m * 12)]).reshape(-1)
+    y = np.ascontiguousarray(base[rng.integers(0, 4096, size=m * 12)]).reshape(-1)
+    o12 = np.zeros(m * 144, dtype=np.uint32)
+    c12 = np.zeros(m * 144, dtype=np.uint32)
+    L.check(lib.b381_fp12_mul(util.p32(x), util.p32(y), util.p32(o12), m))
+    ref.ref_fp12_mul(util.p32(x), util.p32(y), util.p32(c12), m, 8)
+    assert np.array_equal(o12, c12)
+    f2n = 1 << 18
+    xa = np.ascontiguousarray(base[rng.integers(0, 4096, size=f2n * 2)]).reshape(-1)
+    xb = np.ascontiguousarray(base[rng.integers(0, 4096, size=f2n * 2)]).reshape(-1)
+    o2 = np.zeros(f2n * 24, dtype=np.uint32)
+    L.check(lib.b381_fp2_mul(util.p32(xa), util.p32(xb), util.p32(o2), f2n))
+    for i in rng.integers(0, f2n, size=64):
+        A = util.f2_from_words(xa[24 * i:24 * i + 24]); B = util.f2_from_words(xb[24 * i:24 * i + 24])
+        assert util.f2_from_words(o2[24 * i:24 * i + 24]) == o.f2_mul(A, B)
+
+
 def test_device_pointer_api_and_launch_counter(L, lib, z):
     import torch
     n = 300

@@ -133,6 +133,17 @@ def test_multi_miller_and_literal(hs):
     for i in range(n):
         pr = o.f12_mul(pr, o.f12_from_limbs32(z["miller_ark"][i]))
     assert o.f12_eq(o.f12_from_limbs32(list(out)), pr)
+    # shared squarings, ZK mode, identity flags in both positions of a pair-of-pairs, odd count
+    pairs = []
+    for i in range(n):
+        P = (o.fp_from_limbs32(z["g1"][i][:12]), o.fp_from_limbs32(z["g1"][i][12:]))
+        Q = (util.f2_from_words(z["g2"][i][:24]), util.f2_from_words(z["g2"][i][24:]))
+        pairs.append((P, Q))
+    inf = (ctypes.c_uint8 * n)(0, 1, 2, 0, 0)
+    live = [pq for k, pq in enumerate(pairs) if inf[k] == 0]
+    for mode, fn in ((0, o.ark_multi_miller_loop), (1, o.zk_multi_miller_loop)):
+        assert hs.hs_multi_miller(g1, g2, inf, ctypes.c_size_t(n), out, mode) == 0
+        assert o.f12_eq(o.f12_from_limbs32(list(out)), fn(live)), mode
     kv = util.pairing_vectors()
     g1p = o.fp_to_limbs32(o.G1_X) + o.fp_to_limbs32(o.G1_Y) + o.fp_to_limbs32(1)
     g2p = util.f2_words(o.G2_X) + util.f2_words(o.G2_Y) + util.f2_words((1, 0))
