@@ -301,8 +301,10 @@ def main():
     roofline = {"bound": "imad", "achieved": alg_ginst, "peak": pk.value, "unit": "G IMAD.WIDE/s", "frac": alg_ginst / pk.value,
                 "traffic": traffic, "traffic_note": "DRAM bytes per step (28 launches) from profiles/ncu_traffic.json; algorithmic bytes per step = pairs x 864",
                 "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
-                        "peak = IMAD.WIDE issue rate measured live by b381_imad_peak (%.0f MHz); the kernel executes 421 IMAD per Fp mul "
-                        "(14 x 28-bit limbs + 15-row reduction), i.e. executed-instruction fraction = frac x 1.40; HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
+                        "peak = fused IMAD.WIDE.U32 rate measured live by b381_imad_peak (8x16 blocks of distinct products, SASS-checked; "
+                        "32 IMAD.WIDE/clk/SM at %.0f MHz -- round-1 lines up to commit 357fec7 divided by a probe that ptxas had strength-reduced "
+                        "to IADD3 chains, i.e. by twice the real multiplier peak); the kernel executes 421 IMAD.WIDE per Fp mul (14 x 28-bit limbs "
+                        "+ 15-row reduction), i.e. multiplier-pipe busy fraction = frac x 1.40; HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
 
     cpu = None
     if not args.no_cpu:

@@ -303,20 +303,32 @@ k_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* er
   }
 }
 
-// integer-pipe roofline probe: independent IMAD.WIDE chains, all SMs, register only
+// integer-pipe roofline probe: what the multiplier pipe sustains on 32 x 32 -> 64-bit multiply-accumulates.
+// Eight accumulator chains; the multiplicand of every multiply-accumulate is the low word of the
+// neighbouring chain's accumulator, so it changes with every instruction and ptxas cannot hoist or
+// strength-reduce anything: the loop body is 128 fused IMAD.WIDE.U32 and nothing else (checked in the
+// SASS by tests/test_capi_symbols.py).  The first version multiplied loop-invariant operands; ptxas
+// computed a*b once and turned the 128 "multiply-accumulates" into IADD3 chains, i.e. it measured the
+// ALU pipe (64 adds/clk/SM) and overstated the multiplier peak twofold.  Measured: 32.0 IMAD.WIDE/clk/SM
+// (a warp-wide IMAD.WIDE occupies the FMA-heavy pipe of its sub-partition for 4 cycles; plain 32-bit
+// IMAD: 64/clk/SM, IMAD.HI: 25.6/clk/SM -- tools/imad_probe5.cu, profiles/imad_probe5_r01.jsonl).
 __global__ void __launch_bounds__(1024)
 k_imad_peak(uint32_t* out, const uint32_t* in, unsigned long long* cyc, int iters) {
-  uint32_t a = in[threadIdx.x & 31], b = in[32 + (threadIdx.x & 31)];
+  const uint32_t b = in[32 + (threadIdx.x & 31)] | 1u;
   unsigned long long d[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) d[j] = in[64 + j] + threadIdx.x;
+  for (int j = 0; j < 8; j++) d[j] = ((unsigned long long)in[64 + j] << 20) + threadIdx.x;
   __syncthreads();
   unsigned long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(d[j]) : "r"(a), "r"(b));
+      for (int j = 0; j < 8; j++) {
+        unsigned long long p;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"((uint32_t)d[(j + 1) & 7]), "r"(b));
+        asm volatile("add.u64 %0, %0, %1;" : "+l"(d[j]) : "l"(p));
+      }
     }
   }
   unsigned long long t1 = clock64();

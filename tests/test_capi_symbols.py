@@ -47,3 +47,26 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dp, f)).read()
                 for needle in ("b381_oracle", "b381_ref", "libb381_hostsim", "oracle/_build", "oracle/_ref"):
                     assert needle not in text, (f, needle)
+
+
+def test_roofline_probe_executes_multiplies():
+    """The roofline denominator must come from real multiplier instructions: the loop body of
+    k_imad_peak has to contain its 128 fused IMAD.WIDE.U32 (the first version of the probe was
+    strength-reduced by ptxas to IADD3 chains and overstated the multiplier peak twofold)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(util.ROOT, "plonky2-bls12-381-pairing_b200", "libb381.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    body, on = [], False
+    for line in sass.split("\n"):
+        if "Function :" in line:
+            on = "k_imad_peak" in line
+        elif on:
+            body.append(line)
+    wide = [l for l in body if "IMAD.WIDE.U32" in l]
+    fused = [l for l in wide if not re.search(r", RZ ;", l)]
+    adds = [l for l in body if re.search(r"\bIADD3", l)]
+    assert len(fused) >= 128, "probe multiplies were optimised away (%d fused IMAD.WIDE)" % len(fused)
+    assert len(adds) < 40, "probe was turned into adds (%d IADD3)" % len(adds)
