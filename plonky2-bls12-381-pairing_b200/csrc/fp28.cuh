@@ -43,6 +43,7 @@
 
 namespace b381 {
 
+typedef int32_t limb_t;
 constexpr int NL = B381_NL;          // 14 limbs
 constexpr int W = B381_W;            // 28 bits
 constexpr int32_t MASK = B381_MASK;
@@ -442,6 +443,16 @@ B381_HD B381_INL void fp_pack32(uint32_t (&w)[12], const Fp& a) {
     if (W - s + W < 32 && k + 2 < NL) v |= (uint32_t)a.l[k + 2] << (2 * W - s);
     w[j] = v;
   }
+}
+
+// range check of an unpacked plain integer: X < p
+B381_HD B381_INL bool fp_below_p(const Fp& x) {
+  Fp t;
+#pragma unroll
+  for (int k = 0; k < NL; k++) t.l[k] = x.l[k] - plimb(k);
+  B381_TB(t.mag = 11; t.lb = 2; t.nonneg = false;)
+  fp_carry_exact(t);
+  return (t.l[NL - 1] >> 31) != 0;
 }
 
 // X (12 x u32, Montgomery R = 2^384, canonical) -> internal.  Returns false if X >= p.

@@ -1,0 +1,490 @@
+// fp32.cuh -- BLS12-381 base-field arithmetic for sm_100a, 13 x 32-bit two's-complement words with
+// carry chains (B381_FMT == 32).  Same interface and the same lazy semantics as fp28.cuh, so
+// tower.cuh / programs.cuh / kernels.cu are shared between the two formats.
+//
+// Why this format.  Measured on B200 (tools/imad_probe5.cu, profiles/imad_probe5_r01.jsonl): a warp-wide
+// IMAD.WIDE occupies the multiplier pipe of its SM sub-partition for 4 cycles (32 thread-ops/clk/SM)
+// whether or not it carries (IMAD.WIDE.U32.X: 31/clk/SM), and the pairing kernel already keeps that
+// pipe 75 % busy.  What is left is the NUMBER of wide multiplies per field multiplication:
+//   14 x 28-bit limbs, carry-free columns (fp28.cuh):  196 + 15*14+15 = 421 per Fp multiplication
+//   13 x 32-bit words, carry chains (this file):       169 + 13*12    = 325 (+13 narrow IMAD)
+// and the accumulators shrink from 29 x 64-bit columns (58 registers) to 26 words.
+//
+//   value   = two's-complement integer of 13 x 32-bit words (sign in bit 415), |v| < 2^20 p by the
+//             bound tracker; additions / subtractions / negations are plain carry chains (no modular
+//             correction: "lazy"), products of two such values are 26-word two's-complement integers.
+//   radix   R' = 2^416: 13 Montgomery rows over the 12 words of p.  (T + M p) / 2^416 lies in
+//             (T / 2^416, T / 2^416 + p]: any product of operands below 2^17 p reduces to (-eps, p + eps).
+//
+// Carry chains are PTX add.cc / madc.{lo,hi}.cc sequences (one asm statement per instruction, in the
+// style of the public sppark / blst GPU field code; ptxas fuses each mad.lo.cc / madc.hi.cc pair into
+// one IMAD.WIDE.U32(.X)).  On the host the same macros expand to uint64 arithmetic with an explicit
+// carry variable, so tests/hostsim/ runs the identical algorithm bit for bit, with optional
+// magnitude tracking under B381_TRACK_BOUNDS.
+//
+// External format at the C ABI (include/b381.h): 12 x u32 little-endian words, Montgomery R = 2^384
+// (= ark_ff Fp384 in-memory layout used by /root/reference/src/fields/helpers.rs:8-11).
+#pragma once
+#include <stdint.h>
+#include "b381_consts32.h"
+
+#if defined(__CUDACC__)
+#define B381_HD __host__ __device__
+#define B381_INL __forceinline__
+#else
+#define B381_HD
+#define B381_INL inline __attribute__((always_inline))
+#endif
+
+#ifdef B381_TRACK_BOUNDS
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#define B381_TB(x) x
+#define B381_CHECK(cond, msg) do { if (!(cond)) { fprintf(stderr, "bound violation: %s (%s:%d)\n", msg, __FILE__, __LINE__); abort(); } } while (0)
+#else
+#define B381_TB(x)
+#define B381_CHECK(cond, msg)
+#endif
+
+// ---- carry-chain instruction macros ------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define B381_CC_DECL
+#define ADD_CC(r, a, b)   asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define ADDC_CC(r, a, b)  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define ADDC(r, a, b)     asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define SUB_CC(r, a, b)   asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define SUBC_CC(r, a, b)  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define SUBC(r, a, b)     asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define MUL_WIDE(lo, hi, a, b) asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b))
+#define MAD_LO_CC(r, a, b)   asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
+#define MADC_LO_CC(r, a, b)  asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
+#define MADC_HI_CC(r, a, b)  asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
+#define MADC_HI(r, a, b)     asm volatile("madc.hi.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(a), "r"(b))
+#else
+#define B381_CC_DECL uint32_t cc_ = 0; (void)cc_
+#define ADD_CC(r, a, b)   do { uint64_t t_ = (uint64_t)(uint32_t)(a) + (uint32_t)(b); (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 32); } while (0)
+#define ADDC_CC(r, a, b)  do { uint64_t t_ = (uint64_t)(uint32_t)(a) + (uint32_t)(b) + cc_; (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 32); } while (0)
+#define ADDC(r, a, b)     do { (r) = (uint32_t)(a) + (uint32_t)(b) + cc_; } while (0)
+#define SUB_CC(r, a, b)   do { uint64_t t_ = (uint64_t)(uint32_t)(a) - (uint32_t)(b); (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 63); } while (0)
+#define SUBC_CC(r, a, b)  do { uint64_t t_ = (uint64_t)(uint32_t)(a) - (uint32_t)(b) - cc_; (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 63); } while (0)
+#define SUBC(r, a, b)     do { (r) = (uint32_t)(a) - (uint32_t)(b) - cc_; } while (0)
+#define MUL_WIDE(lo, hi, a, b) do { uint64_t t_ = (uint64_t)(uint32_t)(a) * (uint32_t)(b); (lo) = (uint32_t)t_; (hi) = (uint32_t)(t_ >> 32); } while (0)
+#define MAD_LO_CC(r, a, b)   do { uint64_t t_ = (uint64_t)(uint32_t)((uint64_t)(uint32_t)(a) * (uint32_t)(b)) + (r); (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 32); } while (0)
+#define MADC_LO_CC(r, a, b)  do { uint64_t t_ = (uint64_t)(uint32_t)((uint64_t)(uint32_t)(a) * (uint32_t)(b)) + (r) + cc_; (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 32); } while (0)
+#define MADC_HI_CC(r, a, b)  do { uint64_t t_ = (((uint64_t)(uint32_t)(a) * (uint32_t)(b)) >> 32) + (r) + cc_; (r) = (uint32_t)t_; cc_ = (uint32_t)(t_ >> 32); } while (0)
+#define MADC_HI(r, a, b)     do { (r) = (uint32_t)((((uint64_t)(uint32_t)(a) * (uint32_t)(b)) >> 32) + (r) + cc_); } while (0)
+#endif
+
+namespace b381 {
+
+typedef uint32_t limb_t;
+constexpr int NL = 13;               // 32-bit words per field element (two's complement)
+constexpr int NW = 2 * NL;           // words of a double-width accumulator
+constexpr int NPW = 12;              // words of p
+
+struct Fp {
+  uint32_t l[NL];
+#ifdef B381_TRACK_BOUNDS
+  double mag;   // bound on |value| / p
+  double lb;    // unused in this format (kept so the shared tracking code compiles)
+  bool nonneg;
+#endif
+};
+
+struct Acc {
+  uint32_t c[NW];
+#ifdef B381_TRACK_BOUNDS
+  double cb;    // unused in this format
+  double mag;   // bound on |value| / p^2
+#endif
+};
+
+constexpr double FP_MAG_MAX = 1048576.0;        // 2^20 p < 2^401: far inside the 2^415 word range
+constexpr double MUL_MAG_MAX = 131072.0;        // operands of a multiplication: |v| < 2^17 p
+constexpr double ACC_MAG_MAX = 1.0e9;           // reduction input: result < (1 + 1e9 / 4.2e10) p
+
+B381_HD B381_INL constexpr uint32_t pword(int j) {
+  switch (j) {
+    case 0: return B381_Q0;   case 1: return B381_Q1;   case 2: return B381_Q2;   case 3: return B381_Q3;
+    case 4: return B381_Q4;   case 5: return B381_Q5;   case 6: return B381_Q6;   case 7: return B381_Q7;
+    case 8: return B381_Q8;   case 9: return B381_Q9;   case 10: return B381_Q10; case 11: return B381_Q11;
+    default: return 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// linear operations (lazy: no modular correction; carry chains are exact)
+// ---------------------------------------------------------------------------------------------
+B381_HD B381_INL void fp_zero(Fp& r) {
+#pragma unroll
+  for (int k = 0; k < NL; k++) r.l[k] = 0;
+  B381_TB(r.mag = 0; r.lb = 0; r.nonneg = true;)
+}
+
+B381_HD B381_INL void fp_add(Fp& r, const Fp& a, const Fp& b) {
+  B381_CC_DECL;
+  ADD_CC(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], a.l[k], b.l[k]);
+  ADDC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
+  B381_TB(r.mag = a.mag + b.mag; r.lb = 1; r.nonneg = true;)
+  B381_CHECK(r.mag < FP_MAG_MAX, "fp_add: magnitude");
+}
+
+B381_HD B381_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) {
+  B381_CC_DECL;
+  SUB_CC(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], a.l[k], b.l[k]);
+  SUBC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
+  B381_TB(r.mag = a.mag + b.mag; r.lb = 1; r.nonneg = true;)
+  B381_CHECK(r.mag < FP_MAG_MAX, "fp_sub: magnitude");
+}
+
+B381_HD B381_INL void fp_neg(Fp& r, const Fp& a) {
+  B381_CC_DECL;
+  SUB_CC(r.l[0], 0u, a.l[0]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], 0u, a.l[k]);
+  SUBC(r.l[NL - 1], 0u, a.l[NL - 1]);
+  B381_TB(r.mag = a.mag; r.lb = 1; r.nonneg = true;)
+}
+
+B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
+  // shift left by one (funnel shifts; r may alias a: go from the top down)
+#pragma unroll
+  for (int k = NL - 1; k > 0; k--) r.l[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
+  r.l[0] = a.l[0] << 1;
+  B381_TB(r.mag = 2 * a.mag; r.lb = 1; r.nonneg = true;)
+  B381_CHECK(r.mag < FP_MAG_MAX, "fp_dbl: magnitude");
+}
+
+// words are always exact in this format
+B381_HD B381_INL void fp_norm(Fp&) {}
+B381_HD B381_INL void fp_carry_exact(Fp&) {}
+
+B381_HD B381_INL void fp_set(Fp& r, const uint32_t (&v)[NL]) {
+#pragma unroll
+  for (int k = 0; k < NL; k++) r.l[k] = v[k];
+  B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
+}
+
+// exact halving mod p: (v + (v odd ? p : 0)) >> 1 (arithmetic).  Equals multiplication by 2^-1
+// (ark-ec g2.rs double_in_place's mul_assign_by_fp(two_inv)).
+B381_HD B381_INL void fp_half(Fp& r, const Fp& a) {
+  const uint32_t odd = 0u - (a.l[0] & 1u);
+  Fp t;
+  B381_CC_DECL;
+  ADD_CC(t.l[0], a.l[0], pword(0) & odd);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(t.l[k], a.l[k], pword(k) & odd);
+  ADDC(t.l[NL - 1], a.l[NL - 1], 0u);
+#pragma unroll
+  for (int k = 0; k < NL - 1; k++) r.l[k] = (t.l[k] >> 1) | (t.l[k + 1] << 31);
+  r.l[NL - 1] = (uint32_t)((int32_t)t.l[NL - 1] >> 1);
+  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = 1; r.nonneg = true;)
+}
+
+// ---------------------------------------------------------------------------------------------
+// double-width accumulators
+// ---------------------------------------------------------------------------------------------
+B381_HD B381_INL void acc_zero(Acc& t) {
+#pragma unroll
+  for (int k = 0; k < NW; k++) t.c[k] = 0;
+  B381_TB(t.cb = 0; t.mag = 0;)
+}
+
+B381_HD B381_INL void acc_add(Acc& r, const Acc& a, const Acc& b) {
+  B381_CC_DECL;
+  ADD_CC(r.c[0], a.c[0], b.c[0]);
+#pragma unroll
+  for (int k = 1; k < NW - 1; k++) ADDC_CC(r.c[k], a.c[k], b.c[k]);
+  ADDC(r.c[NW - 1], a.c[NW - 1], b.c[NW - 1]);
+  B381_TB(r.cb = 0; r.mag = a.mag + b.mag;)
+}
+
+B381_HD B381_INL void acc_sub(Acc& r, const Acc& a, const Acc& b) {
+  B381_CC_DECL;
+  SUB_CC(r.c[0], a.c[0], b.c[0]);
+#pragma unroll
+  for (int k = 1; k < NW - 1; k++) SUBC_CC(r.c[k], a.c[k], b.c[k]);
+  SUBC(r.c[NW - 1], a.c[NW - 1], b.c[NW - 1]);
+  B381_TB(r.cb = 0; r.mag = a.mag + b.mag;)
+}
+
+// t = a * b as a 26-word two's-complement integer: 169 IMAD.WIDE.  Row i multiplies a by word i of
+// b; the even words of a land on 64-bit slots (i+2k, i+2k+1) and form one carry chain, the odd words
+// form a second one on (i+2k+1, i+2k+2).  The partial sum after row i fits words 0..i+13, so the
+// chains end in the two words above their last product and never ripple further.  The signed
+// interpretation (v = u - 2^416 s) costs two masked 13-word subtractions from the high half.
+B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) {
+  B381_CC_DECL;
+  uint32_t (&T)[NW] = t.c;
+#pragma unroll
+  for (int k = 14; k < NW; k++) T[k] = 0;
+  {
+    const uint32_t b0 = b.l[0];
+#pragma unroll
+    for (int k = 0; k < 7; k++) MUL_WIDE(T[2 * k], T[2 * k + 1], a.l[2 * k], b0);
+    MAD_LO_CC(T[1], a.l[1], b0); MADC_HI_CC(T[2], a.l[1], b0);
+#pragma unroll
+    for (int k = 1; k < 6; k++) { MADC_LO_CC(T[2 * k + 1], a.l[2 * k + 1], b0); MADC_HI_CC(T[2 * k + 2], a.l[2 * k + 1], b0); }
+    ADDC(T[13], T[13], 0u);
+  }
+#pragma unroll
+  for (int i = 1; i < NL; i++) {
+    const uint32_t bi = b.l[i];
+    MAD_LO_CC(T[i], a.l[0], bi); MADC_HI_CC(T[i + 1], a.l[0], bi);
+#pragma unroll
+    for (int k = 1; k < 7; k++) { MADC_LO_CC(T[i + 2 * k], a.l[2 * k], bi); MADC_HI_CC(T[i + 2 * k + 1], a.l[2 * k], bi); }
+    if (i + 14 < NW) ADDC(T[i + 14], T[i + 14], 0u);
+    MAD_LO_CC(T[i + 1], a.l[1], bi); MADC_HI_CC(T[i + 2], a.l[1], bi);
+#pragma unroll
+    for (int k = 1; k < 6; k++) { MADC_LO_CC(T[i + 2 * k + 1], a.l[2 * k + 1], bi); MADC_HI_CC(T[i + 2 * k + 2], a.l[2 * k + 1], bi); }
+    if (i + 14 < NW) { ADDC_CC(T[i + 13], T[i + 13], 0u); ADDC(T[i + 14], T[i + 14], 0u); }
+    else ADDC(T[i + 13], T[i + 13], 0u);
+  }
+  // sign corrections: (ua - 2^416 sa)(ub - 2^416 sb) = ua ub - 2^416 (sa ub + sb ua)   (mod 2^832)
+  const uint32_t ma = (uint32_t)((int32_t)a.l[NL - 1] >> 31), mb = (uint32_t)((int32_t)b.l[NL - 1] >> 31);
+  SUB_CC(T[NL], T[NL], b.l[0] & ma);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], b.l[k] & ma);
+  SUBC(T[NW - 1], T[NW - 1], b.l[NL - 1] & ma);
+  SUB_CC(T[NL], T[NL], a.l[0] & mb);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], a.l[k] & mb);
+  SUBC(T[NW - 1], T[NW - 1], a.l[NL - 1] & mb);
+  B381_TB(t.cb = 0; t.mag = a.mag * b.mag;)
+  B381_CHECK(a.mag < MUL_MAG_MAX && b.mag < MUL_MAG_MAX, "acc_mul: operand magnitude");
+}
+
+// t += a * b
+B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
+  Acc u;
+  B381_TB(u.mag = 0; u.cb = 0;)
+  acc_mul(u, a, b);
+  acc_add(t, t, u);
+}
+B381_HD B381_INL void acc_mac_cross(Acc& t, const Fp& a, const Fp& b) { acc_mac(t, a, b); }
+
+B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
+  B381_CC_DECL;
+  SUB_CC(r.c[0], 0u, a.c[0]);
+#pragma unroll
+  for (int k = 1; k < NW - 1; k++) SUBC_CC(r.c[k], 0u, a.c[k]);
+  SUBC(r.c[NW - 1], 0u, a.c[NW - 1]);
+  B381_TB(r.cb = 0; r.mag = a.mag;)
+}
+
+// one Montgomery row on the window U[i .. i+13]: U += m p 2^(32 i) with m = U[i] n0'.  The even
+// words of p form one carry chain, the odd words a second one; both end in U[i+12], U[i+13].
+#define B381_REDC_ROW(U, i)                                                                            \
+  {                                                                                                    \
+    const uint32_t m_ = U[(i)] * (uint32_t)B381_N0Q;                                                   \
+    MAD_LO_CC(U[(i) + 0], m_, (uint32_t)B381_Q0);  MADC_HI_CC(U[(i) + 1], m_, (uint32_t)B381_Q0);       \
+    MADC_LO_CC(U[(i) + 2], m_, (uint32_t)B381_Q2); MADC_HI_CC(U[(i) + 3], m_, (uint32_t)B381_Q2);       \
+    MADC_LO_CC(U[(i) + 4], m_, (uint32_t)B381_Q4); MADC_HI_CC(U[(i) + 5], m_, (uint32_t)B381_Q4);       \
+    MADC_LO_CC(U[(i) + 6], m_, (uint32_t)B381_Q6); MADC_HI_CC(U[(i) + 7], m_, (uint32_t)B381_Q6);       \
+    MADC_LO_CC(U[(i) + 8], m_, (uint32_t)B381_Q8); MADC_HI_CC(U[(i) + 9], m_, (uint32_t)B381_Q8);       \
+    MADC_LO_CC(U[(i) + 10], m_, (uint32_t)B381_Q10); MADC_HI_CC(U[(i) + 11], m_, (uint32_t)B381_Q10);   \
+    ADDC_CC(U[(i) + 12], U[(i) + 12], 0u); ADDC(U[(i) + 13], U[(i) + 13], 0u);                          \
+    MAD_LO_CC(U[(i) + 1], m_, (uint32_t)B381_Q1);  MADC_HI_CC(U[(i) + 2], m_, (uint32_t)B381_Q1);       \
+    MADC_LO_CC(U[(i) + 3], m_, (uint32_t)B381_Q3); MADC_HI_CC(U[(i) + 4], m_, (uint32_t)B381_Q3);       \
+    MADC_LO_CC(U[(i) + 5], m_, (uint32_t)B381_Q5); MADC_HI_CC(U[(i) + 6], m_, (uint32_t)B381_Q5);       \
+    MADC_LO_CC(U[(i) + 7], m_, (uint32_t)B381_Q7); MADC_HI_CC(U[(i) + 8], m_, (uint32_t)B381_Q7);       \
+    MADC_LO_CC(U[(i) + 9], m_, (uint32_t)B381_Q9); MADC_HI_CC(U[(i) + 10], m_, (uint32_t)B381_Q9);      \
+    MADC_LO_CC(U[(i) + 11], m_, (uint32_t)B381_Q11); MADC_HI_CC(U[(i) + 12], m_, (uint32_t)B381_Q11);   \
+    ADDC(U[(i) + 13], U[(i) + 13], 0u);                                                                \
+  }
+
+// r = t / 2^(32 ROWS) mod p, result in (t / 2^(32 ROWS), t / 2^(32 ROWS) + p].  Only the low ROWS
+// words of t enter the rows: U = t_low + M p grows into fresh (zero) words above them, so every
+// chain ends in words nothing else has written yet, and the high half of t (signed) is added to
+// U >> (32 ROWS) at the end.  ROWS * 12 IMAD.WIDE + ROWS IMAD.
+template <int ROWS>
+B381_HD B381_INL void acc_redc_rows(Fp& r, Acc& t) {
+  B381_CC_DECL;
+  uint32_t U[ROWS + 14];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) U[k] = t.c[k];
+#pragma unroll
+  for (int k = ROWS; k < ROWS + 14; k++) U[k] = 0;
+#pragma unroll
+  for (int i = 0; i < ROWS; i++) B381_REDC_ROW(U, i);
+  ADD_CC(r.l[0], U[ROWS], t.c[ROWS]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], U[ROWS + k], t.c[ROWS + k]);
+  ADDC(r.l[NL - 1], U[ROWS + NL - 1], t.c[ROWS + NL - 1]);
+}
+
+B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
+  B381_CHECK(t.mag < ACC_MAG_MAX, "acc_redc: input too large");
+  acc_redc_rows<NL>(r, t);
+  B381_TB(r.mag = 1.0 + t.mag / 4.2e10 + 1e-9; r.lb = 1.0; r.nonneg = true;)
+}
+
+// two independent reductions with their rows interleaved in source order
+B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
+  B381_CHECK(t0.mag < ACC_MAG_MAX && t1.mag < ACC_MAG_MAX, "acc_redc2: input too large");
+  B381_CC_DECL;
+  constexpr int ROWS = NL;
+  uint32_t U0[ROWS + 14], U1[ROWS + 14];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) { U0[k] = t0.c[k]; U1[k] = t1.c[k]; }
+#pragma unroll
+  for (int k = ROWS; k < ROWS + 14; k++) { U0[k] = 0; U1[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < ROWS; i++) {
+    B381_REDC_ROW(U0, i);
+    B381_REDC_ROW(U1, i);
+  }
+  ADD_CC(r0.l[0], U0[ROWS], t0.c[ROWS]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r0.l[k], U0[ROWS + k], t0.c[ROWS + k]);
+  ADDC(r0.l[NL - 1], U0[ROWS + NL - 1], t0.c[NW - 1]);
+  ADD_CC(r1.l[0], U1[ROWS], t1.c[ROWS]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r1.l[k], U1[ROWS + k], t1.c[ROWS + k]);
+  ADDC(r1.l[NL - 1], U1[ROWS + NL - 1], t1.c[NW - 1]);
+  B381_TB(r0.mag = 1.0 + t0.mag / 4.2e10 + 1e-9; r0.lb = 1.0; r1.mag = 1.0 + t1.mag / 4.2e10 + 1e-9; r1.lb = 1.0; r0.nonneg = r1.nonneg = true;)
+}
+
+// r = t / 2^384 mod p: reduction in the EXTERNAL domain (12 rows), for the element-wise Fp / Fp2
+// multiply entry points, which then need no domain conversion.  Canonical operands give (−p, 2p).
+B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
+  B381_CHECK(t.mag < 4.0, "acc_redc384: operands must be canonical");
+  acc_redc_rows<12>(r, t);
+  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = 1.0; r.nonneg = true;)
+}
+
+B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+  Acc t;
+  B381_TB(t.mag = 0; t.cb = 0;)
+  acc_mul(t, a, b);
+  acc_redc(r, t);
+}
+
+// weak reduction: any |v| < 2^20 p comes out in [0, 11 p).  v' = v + 2^21 p >= 0; q = floor-estimate
+// of v' / p from the top word; r = v' - q p.  12 IMAD.WIDE.  Needed wherever a value feeds back
+// LINEARLY into itself (the -2z term of the cyclotomic squaring).
+B381_HD B381_INL void fp_wreduce(Fp& a) {
+  B381_CHECK(a.mag < FP_MAG_MAX, "fp_wreduce: value out of range");
+  const uint32_t off[NL] = B381_WRED_OFF;       // 2^21 p
+  uint32_t v[NL];
+  B381_CC_DECL;
+  ADD_CC(v[0], a.l[0], off[0]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(v[k], a.l[k], off[k]);
+  ADDC(v[NL - 1], a.l[NL - 1], off[NL - 1]);
+  // q <= floor(h 2^384 / p), h = top word (v' < 2^22 p < 2^404: h < 2^20)
+  const uint32_t q = (uint32_t)(((uint64_t)v[NL - 1] * (uint64_t)B381_WRED_C) >> 20);
+  uint32_t Q[NL];
+#pragma unroll
+  for (int k = 0; k < 6; k++) MUL_WIDE(Q[2 * k], Q[2 * k + 1], q, pword(2 * k));
+  Q[12] = 0;
+  MAD_LO_CC(Q[1], q, pword(1)); MADC_HI_CC(Q[2], q, pword(1));
+#pragma unroll
+  for (int k = 1; k < 6; k++) { MADC_LO_CC(Q[2 * k + 1], q, pword(2 * k + 1)); MADC_HI_CC(Q[2 * k + 2], q, pword(2 * k + 1)); }
+  SUB_CC(a.l[0], v[0], Q[0]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(a.l[k], v[k], Q[k]);
+  SUBC(a.l[NL - 1], v[NL - 1], Q[NL - 1]);
+  B381_TB(a.mag = 11.0; a.lb = 1.0; a.nonneg = true;)
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical form, comparisons, external format (12 x u32, Montgomery R = 2^384)
+// ---------------------------------------------------------------------------------------------
+// bring a value in (-p, 2p) to [0, p)
+B381_HD B381_INL void fp_canon_small(Fp& a) {
+  B381_CHECK(a.mag < 2.0, "fp_canon_small: input range");
+  B381_CC_DECL;
+  const uint32_t neg = (uint32_t)((int32_t)a.l[NL - 1] >> 31);
+  ADD_CC(a.l[0], a.l[0], pword(0) & neg);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(a.l[k], a.l[k], pword(k) & neg);
+  ADDC(a.l[NL - 1], a.l[NL - 1], 0u);
+  Fp t;
+  SUB_CC(t.l[0], a.l[0], pword(0));
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(t.l[k], a.l[k], pword(k));
+  SUBC(t.l[NL - 1], a.l[NL - 1], 0u);
+  const uint32_t ge = ~(uint32_t)((int32_t)t.l[NL - 1] >> 31);       // all ones if a >= p
+#pragma unroll
+  for (int k = 0; k < NL; k++) a.l[k] = (t.l[k] & ge) | (a.l[k] & ~ge);
+  B381_TB(a.mag = 1.0; a.lb = 1.0; a.nonneg = true;)
+}
+
+// full reduction of any stored value to canonical [0,p): one Montgomery multiplication by R' mod p
+B381_HD B381_INL void fp_canon(Fp& a) {
+  const uint32_t one[NL] = B381_ONE;
+  Fp o, n = a;
+  fp_set(o, one);
+  fp_mul(a, n, o);
+  fp_canon_small(a);
+}
+
+B381_HD B381_INL bool fp_is_zero_canon(const Fp& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < NL; k++) o |= a.l[k];
+  return o == 0;
+}
+
+B381_HD B381_INL bool fp_eq_canon(const Fp& a, const Fp& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < NL; k++) o |= a.l[k] ^ b.l[k];
+  return o == 0;
+}
+
+// 12 x u32 (plain integer X < 2^384) -> words (top word zero)
+B381_HD B381_INL void fp_unpack32(Fp& r, const uint32_t (&w)[12]) {
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.l[k] = w[k];
+  r.l[12] = 0;
+  B381_TB(r.mag = 9.9; r.lb = 1.0; r.nonneg = true;)     // any 384-bit integer
+}
+
+// canonical words -> 12 x u32
+B381_HD B381_INL void fp_pack32(uint32_t (&w)[12], const Fp& a) {
+#pragma unroll
+  for (int j = 0; j < 12; j++) w[j] = a.l[j];
+}
+
+// range check of an unpacked plain integer (top word zero): X < p
+B381_HD B381_INL bool fp_below_p(const Fp& x) {
+  uint32_t t;
+  B381_CC_DECL;
+  SUB_CC(t, x.l[0], pword(0));
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) SUBC_CC(t, x.l[k], pword(k));
+  SUBC(t, 0u, 0u);                                   // 0 - borrow: all ones if X < p
+  return t != 0;
+}
+
+// X (12 x u32, Montgomery R = 2^384, canonical) -> internal.  Returns false if X >= p.
+B381_HD B381_INL bool fp_from_ext(Fp& r, const uint32_t (&w)[12]) {
+  Fp x;
+  fp_unpack32(x, w);
+  const bool ok = fp_below_p(x);
+  const uint32_t cin[NL] = B381_CIN;
+  Fp c;
+  fp_set(c, cin);
+  fp_mul(r, x, c);
+  return ok;
+}
+
+// internal -> 12 x u32, Montgomery R = 2^384, canonical
+B381_HD B381_INL void fp_to_ext(uint32_t (&w)[12], const Fp& a) {
+  const uint32_t cout[NL] = B381_COUT;
+  Fp c, o;
+  fp_set(c, cout);
+  B381_CHECK(a.mag < MUL_MAG_MAX, "fp_to_ext: magnitude");
+  fp_mul(o, a, c);
+  fp_canon_small(o);
+  fp_pack32(w, o);
+}
+
+}  // namespace b381

@@ -226,11 +226,7 @@ __device__ __forceinline__ bool load_canon(Fp& x, const uint32_t* src) {
   w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
   w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
   fp_unpack32(x, w);
-  Fp t;
-#pragma unroll
-  for (int k = 0; k < NL; k++) t.l[k] = x.l[k] - plimb(k);
-  fp_carry_exact(t);
-  return (t.l[NL - 1] >> 31) != 0;
+  return fp_below_p(x);
 }
 
 __device__ __forceinline__ void store_canon(uint32_t* dst, Fp& x) {   // x in (-p, 2p)

@@ -47,7 +47,7 @@ B381_DEV B381_INL void f12_store_raw(const Ctx& cx, uint32_t* dst, int f) {
 B381_DEV B381_INL void f12_load_raw(const Ctx& cx, int f, const uint32_t* src) {
   for (int i = 0; i < 6; i++) {
     Fp c0, c1;
-    for (int k = 0; k < NL; k++) { c0.l[k] = (int32_t)src[28 * i + k]; c1.l[k] = (int32_t)src[28 * i + NL + k]; }
+    for (int k = 0; k < NL; k++) { c0.l[k] = (limb_t)src[28 * i + k]; c1.l[k] = (limb_t)src[28 * i + NL + k]; }
     B381_TB(c0.mag = c1.mag = 40.0; c0.lb = c1.lb = 1.0; c0.nonneg = c1.nonneg = true;)
     st_f2(S_(f + i), c0, c1);
   }

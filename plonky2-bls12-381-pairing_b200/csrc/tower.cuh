@@ -15,7 +15,14 @@
 // orchestration.  Formulas follow the reference's tower twins (cited per function) and, for the
 // ARK mode, arkworks 0.4; values are bit-identical to the oracle.
 #pragma once
+#ifndef B381_FMT
+#define B381_FMT 28
+#endif
+#if B381_FMT == 32
+#include "fp32.cuh"
+#else
 #include "fp28.cuh"
+#endif
 
 #if defined(__CUDACC__)
 typedef uint4 u4;
@@ -159,13 +166,21 @@ B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
     uint32_t w[28];
     tmem_ld28(w, (uint32_t)reinterpret_cast<unsigned long long>(p));
 #pragma unroll
-    for (int k = 0; k < NL; k++) { c0.l[k] = (int32_t)w[k]; c1.l[k] = (int32_t)w[NL + k]; }
+    for (int k = 0; k < NL; k++) { c0.l[k] = (limb_t)w[k]; c1.l[k] = (limb_t)w[NL + k]; }
     return;
   }
 #endif
   u4 g[GPS];
 #pragma unroll
   for (int i = 0; i < GPS; i++) g[i] = p[i * B381_GS];
+#if B381_FMT == 32
+  {
+    const uint32_t w[28] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w, g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y,
+                            g[3].z, g[3].w, g[4].x, g[4].y, g[4].z, g[4].w, g[5].x, g[5].y, g[5].z, g[5].w, g[6].x, g[6].y, g[6].z, g[6].w};
+#pragma unroll
+    for (int k = 0; k < NL; k++) { c0.l[k] = w[k]; c1.l[k] = w[NL + k]; }
+  }
+#else
   c0.l[0] = g[0].x; c0.l[1] = g[0].y; c0.l[2] = g[0].z; c0.l[3] = g[0].w;
   c0.l[4] = g[1].x; c0.l[5] = g[1].y; c0.l[6] = g[1].z; c0.l[7] = g[1].w;
   c0.l[8] = g[2].x; c0.l[9] = g[2].y; c0.l[10] = g[2].z; c0.l[11] = g[2].w;
@@ -173,6 +188,7 @@ B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
   c1.l[2] = g[4].x; c1.l[3] = g[4].y; c1.l[4] = g[4].z; c1.l[5] = g[4].w;
   c1.l[6] = g[5].x; c1.l[7] = g[5].y; c1.l[8] = g[5].z; c1.l[9] = g[5].w;
   c1.l[10] = g[6].x; c1.l[11] = g[6].y; c1.l[12] = g[6].z; c1.l[13] = g[6].w;
+#endif
   B381_TB(track_ld(p, 0, c0); track_ld(p, 1, c1);)
 }
 
@@ -181,12 +197,26 @@ B381_DEV B381_INL void st_f2(u4* p, const Fp& c0, const Fp& c1) {
   if (is_tmem(p)) {
     uint32_t w[28];
 #pragma unroll
+    for (int k = 2 * NL; k < 28; k++) w[k] = 0;
+#pragma unroll
     for (int k = 0; k < NL; k++) { w[k] = (uint32_t)c0.l[k]; w[NL + k] = (uint32_t)c1.l[k]; }
     tmem_st28((uint32_t)reinterpret_cast<unsigned long long>(p), w);
     return;
   }
 #endif
   u4 g[GPS];
+#if B381_FMT == 32
+  {
+    uint32_t w[28];
+#pragma unroll
+    for (int k = 0; k < NL; k++) { w[k] = c0.l[k]; w[NL + k] = c1.l[k]; }
+    w[26] = 0; w[27] = 0;
+    g[0].x = w[0]; g[0].y = w[1]; g[0].z = w[2]; g[0].w = w[3]; g[1].x = w[4]; g[1].y = w[5]; g[1].z = w[6]; g[1].w = w[7];
+    g[2].x = w[8]; g[2].y = w[9]; g[2].z = w[10]; g[2].w = w[11]; g[3].x = w[12]; g[3].y = w[13]; g[3].z = w[14]; g[3].w = w[15];
+    g[4].x = w[16]; g[4].y = w[17]; g[4].z = w[18]; g[4].w = w[19]; g[5].x = w[20]; g[5].y = w[21]; g[5].z = w[22]; g[5].w = w[23];
+    g[6].x = w[24]; g[6].y = w[25]; g[6].z = w[26]; g[6].w = w[27];
+  }
+#else
   g[0].x = c0.l[0]; g[0].y = c0.l[1]; g[0].z = c0.l[2]; g[0].w = c0.l[3];
   g[1].x = c0.l[4]; g[1].y = c0.l[5]; g[1].z = c0.l[6]; g[1].w = c0.l[7];
   g[2].x = c0.l[8]; g[2].y = c0.l[9]; g[2].z = c0.l[10]; g[2].w = c0.l[11];
@@ -194,6 +224,7 @@ B381_DEV B381_INL void st_f2(u4* p, const Fp& c0, const Fp& c1) {
   g[4].x = c1.l[2]; g[4].y = c1.l[3]; g[4].z = c1.l[4]; g[4].w = c1.l[5];
   g[5].x = c1.l[6]; g[5].y = c1.l[7]; g[5].z = c1.l[8]; g[5].w = c1.l[9];
   g[6].x = c1.l[10]; g[6].y = c1.l[11]; g[6].z = c1.l[12]; g[6].w = c1.l[13];
+#endif
 #pragma unroll
   for (int i = 0; i < GPS; i++) p[i * B381_GS] = g[i];
   B381_TB(track_st(p, 0, c0); track_st(p, 1, c1);)
@@ -210,8 +241,8 @@ B381_DEV B381_INL void ld_fp(Fp& a, const u4* p, int h) {
 // constants in device constant memory / host statics
 // ---------------------------------------------------------------------------------------------
 struct ConstTab {
-  int32_t frob[3][5][2][NL];   // gamma_k[j] = xi^(j (p^k-1)/6), k = 1..3, j = 1..5, (c0, c1)
-  int32_t one[NL];
+  limb_t frob[3][5][2][NL];   // gamma_k[j] = xi^(j (p^k-1)/6), k = 1..3, j = 1..5, (c0, c1)
+  limb_t one[NL];
   uint8_t pm2_nib[96];         // p - 2 as 4-bit windows, MSB first
 };
 #define B381_CONST_INIT { \
@@ -229,7 +260,7 @@ __constant__ ConstTab g_ct = B381_CONST_INIT;
 static const ConstTab g_ct = B381_CONST_INIT;
 #endif
 
-B381_DEV B381_INL void fp_const(Fp& r, const int32_t* v) {
+B381_DEV B381_INL void fp_const(Fp& r, const limb_t* v) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
   B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
@@ -238,6 +269,43 @@ B381_DEV B381_INL void fp_const(Fp& r, const int32_t* v) {
 // ---------------------------------------------------------------------------------------------
 // register-level Fp2 helpers
 // ---------------------------------------------------------------------------------------------
+#if B381_FMT == 32
+// (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba in the double-width domain, one reduction per
+// coefficient: 3 x 169 + 2 x 156 IMAD.WIDE.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
+B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
+  Acc A, B, X;
+  Fp sa, sb;
+  acc_mul(A, a0, b0);
+  acc_mul(B, a1, b1);
+  fp_add(sa, a0, a1);
+  fp_add(sb, b0, b1);
+  acc_mul(X, sa, sb);
+  acc_sub(X, X, A);
+  acc_sub(X, X, B);                                 // im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
+  acc_sub(A, A, B);                                 // re = a0 b0 - a1 b1
+  acc_redc2(r0, A, r1, X);
+}
+
+// ((a0+a1)(a0-a1), 2 a0 a1); fq2_target_tree.rs:80-91.  2 x 169 + 2 x 156 IMAD.WIDE.
+B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
+  Fp s, d, t;
+  fp_add(s, a0, a1);
+  fp_sub(d, a0, a1);
+  fp_dbl(t, a0);
+  Acc T, U;
+  acc_mul(T, s, d);
+  acc_mul(U, t, a1);
+  acc_redc2(r0, T, r1, U);
+}
+
+// (a0 s, a1 s) for an Fp scalar s
+B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& s) {
+  Acc T, U;
+  acc_mul(T, a0, s);
+  acc_mul(U, a1, s);
+  acc_redc2(r0, T, r1, U);
+}
+#else
 // (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba with one reduction per coefficient:
 // 3 x 196 + 2 x 225 = 1038 IMAD.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
 B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
@@ -281,6 +349,8 @@ B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, 
   acc_zero(U); acc_mac(U, a1, s);
   acc_redc2(r0, T, r1, U);
 }
+
+#endif
 
 B381_DEV B381_INL void f2_norm(Fp& a0, Fp& a1) { fp_norm(a0); fp_norm(a1); }
 
@@ -353,6 +423,28 @@ B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u
 // -(P+Q) + sum_i (a_i0+a_i1)(b_i0+b_i1) lies between -(P+Q) and the final value
 // sum_i (a_i0 b_i1 + a_i1 b_i0), i.e. within 28 n units of 2^56, plus the (signed, tiny) products
 // of the top limbs, which the bound tracker adds from the operand magnitudes.
+#if B381_FMT == 32
+B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
+  Acc P, Q, X;
+  for (int i = 0; i < n; i++) {
+    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
+    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
+    Fp a0, a1, b0, b1, sa, sb;
+    ld_f2(a0, a1, ap);
+    ld_f2(b0, b1, bp);
+    fp_add(sa, a0, a1);
+    fp_add(sb, b0, b1);
+    if (i == 0) { acc_mul(P, a0, b0); acc_mul(Q, a1, b1); acc_mul(X, sa, sb); }
+    else { acc_mac(P, a0, b0); acc_mac(Q, a1, b1); acc_mac(X, sa, sb); }
+  }
+  acc_sub(X, X, P);
+  acc_sub(X, X, Q);                                 // im
+  acc_sub(P, P, Q);                                 // re
+  Fp r0, r1;
+  acc_redc2(r0, P, r1, X);
+  st_f2(r, r0, r1);
+}
+#else
 B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
   Acc P, Q;
   acc_zero(P); acc_zero(Q);
@@ -390,6 +482,8 @@ B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p
   acc_redc2(r0, P, r1, Q);
   st_f2(r, r0, r1);
 }
+
+#endif
 
 // r = (a + a2)^2 ; a2 may be null
 B381_NOINL void f2_sqr(u4* r, const u4* a, const u4* a2) {
@@ -559,6 +653,50 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
 // squarings (6 x 196 + 6 x 225) plus seven memory-to-memory linear operations.  The linear feedback
 // of z (magnitude M -> 9 + 2M) is absorbed by the weak reduction when `reduce` is set; callers set it
 // at least every sixth squaring (2 -> 13 -> 35 -> 79 -> 167 -> 343 stays far below the 14-limb range).
+#if B381_FMT == 32
+B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
+  Fp a0, a1, b0, b1, t00, t01, t10, t11;
+  ld_f2(a0, a1, a);
+  ld_f2(b0, b1, b);
+  {
+    // t0 = a^2 + xi b^2:  re = PA + (PB - QB) ; im = QA + (PB + QB)   with
+    // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
+    Fp s, d, e;
+    Acc X, Y, U;
+    fp_add(s, b0, b1); fp_sub(d, b0, b1);
+    acc_mul(X, s, d);                               // PB
+    fp_dbl(e, b0);
+    acc_mul(U, e, b1);                              // QB
+    acc_add(Y, X, U);                               // PB + QB
+    acc_sub(X, X, U);                               // PB - QB
+    fp_add(s, a0, a1); fp_sub(d, a0, a1);
+    acc_mac(X, s, d);                               // + PA
+    fp_dbl(e, a0);
+    acc_mac(Y, e, a1);                              // + QA
+    acc_redc2(t00, X, t01, Y);
+  }
+  Fp z0, z1;
+  {
+    const u4* zt0 = mode == 0 ? za : zb;
+    if (zt0 == a) { z0 = a0; z1 = a1; } else ld_f2(z0, z1, zt0);
+    Fp w0, w1;
+    fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
+    fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
+    if (reduce) { fp_wreduce(w0); fp_wreduce(w1); }
+    st_f2(mode == 0 ? ra : rb, w0, w1);
+  }
+  f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
+  const u4* zt1 = mode == 0 ? zb : za;
+  if (zt1 == b) { z0 = b0; z1 = b1; } else ld_f2(z0, z1, zt1);
+  if (mode == 1) f2_mulxi_reg(t10, t11, t10, t11);
+  Fp x0, x1;
+  fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
+  fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
+  if (reduce) { fp_wreduce(x0); fp_wreduce(x1); }
+  fp_dbl(x0, x0); fp_dbl(x1, x1);
+  st_f2(mode == 0 ? rb : ra, x0, x1);
+}
+#else
 B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
   Fp a0, a1, b0, b1, t00, t01, t10, t11;
   ld_f2(a0, a1, a);
@@ -609,6 +747,8 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
   f2_norm(x0, x1);
   st_f2(mode == 0 ? rb : ra, x0, x1);
 }
+
+#endif
 
 // set slot to the Fp2 constant (one, 0) or (0, 0)
 B381_NOINL void f2_set_small(u4* r, int one) {

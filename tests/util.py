@@ -94,6 +94,9 @@ def load_ref_lib():
 
 def load_hostsim(track=False):
     name = "libb381_hostsim_track.so" if track else "libb381_hostsim.so"
+    over = os.environ.get("B381_HOSTSIM_LIB")       # development aid: try another build of the host simulation
+    if over:
+        return ctypes.CDLL(over + ("_track.so" if track else ".so"))
     return ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", name))
 
 
