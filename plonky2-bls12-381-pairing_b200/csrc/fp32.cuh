@@ -87,15 +87,15 @@ struct Fp {
   uint32_t l[NL];
 #ifdef B381_TRACK_BOUNDS
   double mag;   // bound on |value| / p
-  double lb;    // unused in this format (kept so the shared tracking code compiles)
-  bool nonneg;
+  double lb;    // LOWER bound on value / p (>= 0: provably non-negative)
+  bool nonneg;  // unused in this format
 #endif
 };
 
 struct Acc {
   uint32_t c[NW];
 #ifdef B381_TRACK_BOUNDS
-  double cb;    // unused in this format
+  double cb;    // LOWER bound on value / p^2
   double mag;   // bound on |value| / p^2
 #endif
 };
@@ -122,13 +122,34 @@ B381_HD B381_INL void fp_zero(Fp& r) {
   B381_TB(r.mag = 0; r.lb = 0; r.nonneg = true;)
 }
 
+// r = a + 128 p: makes a difference of two stored values (each below 128 p) non-negative
+B381_HD B381_INL void fp_add_p128(Fp& r, const Fp& a) {
+  const uint32_t k[NL] = B381_P128;
+  B381_CC_DECL;
+  ADD_CC(r.l[0], a.l[0], k[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], k[i]);
+  ADDC(r.l[NL - 1], a.l[NL - 1], k[NL - 1]);
+  B381_TB(r.mag = a.mag + 128; r.lb = a.lb + 128; r.nonneg = true;)
+}
+
+// r = a + p
+B381_HD B381_INL void fp_add_p(Fp& r, const Fp& a) {
+  B381_CC_DECL;
+  ADD_CC(r.l[0], a.l[0], pword(0));
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], pword(i));
+  ADDC(r.l[NL - 1], a.l[NL - 1], 0u);
+  B381_TB(r.mag = a.mag + 1; r.lb = a.lb + 1; r.nonneg = true;)
+}
+
 B381_HD B381_INL void fp_add(Fp& r, const Fp& a, const Fp& b) {
   B381_CC_DECL;
   ADD_CC(r.l[0], a.l[0], b.l[0]);
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], a.l[k], b.l[k]);
   ADDC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
-  B381_TB(r.mag = a.mag + b.mag; r.lb = 1; r.nonneg = true;)
+  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb; r.nonneg = true;)
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_add: magnitude");
 }
 
@@ -138,7 +159,7 @@ B381_HD B381_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], a.l[k], b.l[k]);
   SUBC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
-  B381_TB(r.mag = a.mag + b.mag; r.lb = 1; r.nonneg = true;)
+  B381_TB(r.lb = a.lb - b.mag; r.mag = a.mag + b.mag; r.nonneg = true;)
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_sub: magnitude");
 }
 
@@ -148,7 +169,7 @@ B381_HD B381_INL void fp_neg(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], 0u, a.l[k]);
   SUBC(r.l[NL - 1], 0u, a.l[NL - 1]);
-  B381_TB(r.mag = a.mag; r.lb = 1; r.nonneg = true;)
+  B381_TB(r.lb = -a.mag; r.mag = a.mag; r.nonneg = true;)
 }
 
 B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
@@ -156,7 +177,7 @@ B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = NL - 1; k > 0; k--) r.l[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
   r.l[0] = a.l[0] << 1;
-  B381_TB(r.mag = 2 * a.mag; r.lb = 1; r.nonneg = true;)
+  B381_TB(r.mag = 2 * a.mag; r.lb = 2 * a.lb; r.nonneg = true;)
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_dbl: magnitude");
 }
 
@@ -167,7 +188,7 @@ B381_HD B381_INL void fp_carry_exact(Fp&) {}
 B381_HD B381_INL void fp_set(Fp& r, const uint32_t (&v)[NL]) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
-  B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
+  B381_TB(r.mag = 1.0; r.lb = 0.0; r.nonneg = true;)
 }
 
 // exact halving mod p: (v + (v odd ? p : 0)) >> 1 (arithmetic).  Equals multiplication by 2^-1
@@ -183,7 +204,7 @@ B381_HD B381_INL void fp_half(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 0; k < NL - 1; k++) r.l[k] = (t.l[k] >> 1) | (t.l[k + 1] << 31);
   r.l[NL - 1] = (uint32_t)((int32_t)t.l[NL - 1] >> 1);
-  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = 1; r.nonneg = true;)
+  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = a.lb >= 0 ? 0 : a.lb; r.nonneg = true;)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +222,7 @@ B381_HD B381_INL void acc_add(Acc& r, const Acc& a, const Acc& b) {
 #pragma unroll
   for (int k = 1; k < NW - 1; k++) ADDC_CC(r.c[k], a.c[k], b.c[k]);
   ADDC(r.c[NW - 1], a.c[NW - 1], b.c[NW - 1]);
-  B381_TB(r.cb = 0; r.mag = a.mag + b.mag;)
+  B381_TB(r.cb = a.cb + b.cb; r.mag = a.mag + b.mag;)
 }
 
 B381_HD B381_INL void acc_sub(Acc& r, const Acc& a, const Acc& b) {
@@ -210,54 +231,81 @@ B381_HD B381_INL void acc_sub(Acc& r, const Acc& a, const Acc& b) {
 #pragma unroll
   for (int k = 1; k < NW - 1; k++) SUBC_CC(r.c[k], a.c[k], b.c[k]);
   SUBC(r.c[NW - 1], a.c[NW - 1], b.c[NW - 1]);
-  B381_TB(r.cb = 0; r.mag = a.mag + b.mag;)
+  B381_TB(r.cb = a.cb - b.mag; r.mag = a.mag + b.mag;)
 }
 
 // t = a * b as a 26-word two's-complement integer: 169 IMAD.WIDE.  Row i multiplies a by word i of
-// b; the even words of a land on 64-bit slots (i+2k, i+2k+1) and form one carry chain, the odd words
-// form a second one on (i+2k+1, i+2k+2).  The partial sum after row i fits words 0..i+13, so the
-// chains end in the two words above their last product and never ripple further.  The signed
-// interpretation (v = u - 2^416 s) costs two masked 13-word subtractions from the high half.
-B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) {
+// b; the even words of a form one carry chain of 64-bit products, the odd words a second one, one
+// word higher.  IMAD.WIDE reads and writes ALIGNED register pairs, so the chains that start on an
+// even word offset accumulate into E (E[k] = word k) and those on an odd offset into O (O[k] = word
+// k + 1): every product then lands on an aligned pair of its array (a single array costs two MOVs
+// per misaligned product).  The partial sums after row i fit words 0..i+13, so each chain ends in
+// the two words above its last product and never ripples further.  E and O are merged by one
+// 26-word addition; the signed interpretation (v = u - 2^416 s) costs two masked 13-word
+// subtractions from the high half.
+#define B381_MUL_CHAIN(X, s, a, first, cnt, bi, linked, tail)                                          \
+  {                                                                                                    \
+    if (linked) { MADC_LO_CC(X[(s)], a.l[(first)], bi); } else { MAD_LO_CC(X[(s)], a.l[(first)], bi); }  \
+    MADC_HI_CC(X[(s) + 1], a.l[(first)], bi);                                                          \
+    _Pragma("unroll") for (int k_ = 1; k_ < (cnt); k_++) {                                              \
+      MADC_LO_CC(X[(s) + 2 * k_], a.l[(first) + 2 * k_], bi); MADC_HI_CC(X[(s) + 2 * k_ + 1], a.l[(first) + 2 * k_], bi); \
+    }                                                                                                  \
+    if (tail) { ADDC_CC(X[(s) + 2 * (cnt)], X[(s) + 2 * (cnt)], 0u); }                                  \
+  }
+
+template <bool SIGNED>
+B381_HD B381_INL void acc_mul_t(Acc& t, const Fp& a, const Fp& b) {
   B381_CC_DECL;
-  uint32_t (&T)[NW] = t.c;
+  uint32_t E[30], O[30];
 #pragma unroll
-  for (int k = 14; k < NW; k++) T[k] = 0;
-  {
-    const uint32_t b0 = b.l[0];
+  for (int k = 0; k < 30; k++) { E[k] = 0; O[k] = 0; }
+  // Chain ends.  The 7-product chains end in a word nothing has written yet (no carry out); the
+  // 6-product chains end inside the previous chain's range and push their carry into the next word,
+  // which is fresh.  All chains of one array are LINKED through the carry flag (the flag handed on
+  // is always zero): the link is semantically void but makes each array one serial dependency chain,
+  // so ptxas interleaves exactly two chains (E and O) instead of a wavefront of thirteen, whose live
+  // carries exceed the seven predicate registers and get spilled through LOP3 bit twiddling.
 #pragma unroll
-    for (int k = 0; k < 7; k++) MUL_WIDE(T[2 * k], T[2 * k + 1], a.l[2 * k], b0);
-    MAD_LO_CC(T[1], a.l[1], b0); MADC_HI_CC(T[2], a.l[1], b0);
-#pragma unroll
-    for (int k = 1; k < 6; k++) { MADC_LO_CC(T[2 * k + 1], a.l[2 * k + 1], b0); MADC_HI_CC(T[2 * k + 2], a.l[2 * k + 1], b0); }
-    ADDC(T[13], T[13], 0u);
-  }
-#pragma unroll
-  for (int i = 1; i < NL; i++) {
+  for (int i = 0; i < NL; i++) {
     const uint32_t bi = b.l[i];
-    MAD_LO_CC(T[i], a.l[0], bi); MADC_HI_CC(T[i + 1], a.l[0], bi);
-#pragma unroll
-    for (int k = 1; k < 7; k++) { MADC_LO_CC(T[i + 2 * k], a.l[2 * k], bi); MADC_HI_CC(T[i + 2 * k + 1], a.l[2 * k], bi); }
-    if (i + 14 < NW) ADDC(T[i + 14], T[i + 14], 0u);
-    MAD_LO_CC(T[i + 1], a.l[1], bi); MADC_HI_CC(T[i + 2], a.l[1], bi);
-#pragma unroll
-    for (int k = 1; k < 6; k++) { MADC_LO_CC(T[i + 2 * k + 1], a.l[2 * k + 1], bi); MADC_HI_CC(T[i + 2 * k + 2], a.l[2 * k + 1], bi); }
-    if (i + 14 < NW) { ADDC_CC(T[i + 13], T[i + 13], 0u); ADDC(T[i + 14], T[i + 14], 0u); }
-    else ADDC(T[i + 13], T[i + 13], 0u);
+    if ((i & 1) == 0) { B381_MUL_CHAIN(E, i, a, 0, 7, bi, i != 0, 0); }     // a0, a2, .., a12 at words (i + 2k, i + 2k + 1)
+    else { B381_MUL_CHAIN(E, i + 1, a, 1, 6, bi, 1, 1); }                    // a1, a3, .., a11 at words (i + 2k + 1, i + 2k + 2)
   }
-  // sign corrections: (ua - 2^416 sa)(ub - 2^416 sb) = ua ub - 2^416 (sa ub + sb ua)   (mod 2^832)
-  const uint32_t ma = (uint32_t)((int32_t)a.l[NL - 1] >> 31), mb = (uint32_t)((int32_t)b.l[NL - 1] >> 31);
-  SUB_CC(T[NL], T[NL], b.l[0] & ma);
 #pragma unroll
-  for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], b.l[k] & ma);
-  SUBC(T[NW - 1], T[NW - 1], b.l[NL - 1] & ma);
-  SUB_CC(T[NL], T[NL], a.l[0] & mb);
+  for (int i = 0; i < NL; i++) {
+    const uint32_t bi = b.l[i];
+    if ((i & 1) == 0) { B381_MUL_CHAIN(O, i, a, 1, 6, bi, i != 0, 1); }
+    else { B381_MUL_CHAIN(O, i - 1, a, 0, 7, bi, 1, 0); }
+  }
+  uint32_t (&T)[NW] = t.c;
+  T[0] = E[0];
+  ADD_CC(T[1], E[1], O[0]);
 #pragma unroll
-  for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], a.l[k] & mb);
-  SUBC(T[NW - 1], T[NW - 1], a.l[NL - 1] & mb);
-  B381_TB(t.cb = 0; t.mag = a.mag * b.mag;)
+  for (int k = 2; k < NW - 1; k++) ADDC_CC(T[k], E[k], O[k - 1]);
+  ADDC(T[NW - 1], E[NW - 1], O[NW - 2]);
+  if (SIGNED) {
+    // sign corrections: (ua - 2^416 sa)(ub - 2^416 sb) = ua ub - 2^416 (sa ub + sb ua)   (mod 2^832)
+    const uint32_t ma = (uint32_t)((int32_t)a.l[NL - 1] >> 31), mb = (uint32_t)((int32_t)b.l[NL - 1] >> 31);
+    SUB_CC(T[NL], T[NL], b.l[0] & ma);
+#pragma unroll
+    for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], b.l[k] & ma);
+    SUBC(T[NW - 1], T[NW - 1], b.l[NL - 1] & ma);
+    SUB_CC(T[NL], T[NL], a.l[0] & mb);
+#pragma unroll
+    for (int k = 1; k < NL - 1; k++) SUBC_CC(T[NL + k], T[NL + k], a.l[k] & mb);
+    SUBC(T[NW - 1], T[NW - 1], a.l[NL - 1] & mb);
+  } else {
+    B381_CHECK(a.lb >= 0 && b.lb >= 0, "acc_mul: operands of the unsigned multiplication must be non-negative");
+  }
+  B381_TB(t.cb = SIGNED ? -(a.mag * b.mag) : 0; t.mag = a.mag * b.mag;)
   B381_CHECK(a.mag < MUL_MAG_MAX && b.mag < MUL_MAG_MAX, "acc_mul: operand magnitude");
 }
+
+// Stored values are kept NON-NEGATIVE (products are made so by adding p where the double-width value
+// can be negative, differences by the weak reduction or a 128 p offset), so the hot path multiplies
+// unsigned words and needs no sign correction; acc_mul_signed is for the rare canonicalisation paths.
+B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<false>(t, a, b); }
+B381_HD B381_INL void acc_mul_signed(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<true>(t, a, b); }
 
 // t += a * b
 B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
@@ -274,80 +322,122 @@ B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
 #pragma unroll
   for (int k = 1; k < NW - 1; k++) SUBC_CC(r.c[k], 0u, a.c[k]);
   SUBC(r.c[NW - 1], 0u, a.c[NW - 1]);
-  B381_TB(r.cb = 0; r.mag = a.mag;)
+  B381_TB(r.cb = -a.mag; r.mag = a.mag;)
 }
 
-// one Montgomery row on the window U[i .. i+13]: U += m p 2^(32 i) with m = U[i] n0'.  The even
-// words of p form one carry chain, the odd words a second one; both end in U[i+12], U[i+13].
-#define B381_REDC_ROW(U, i)                                                                            \
+// Montgomery reduction with a sliding two-array window (the even / odd scheme of the public sppark
+// field code, rearranged for a separate reduction of a double-width value).  At row i, A[k] is word
+// i + k and B[k] word i + k + 1 of U = t_low + M p; A[0] is the exact low word.  m = A[0] n0';
+// the odd words of p accumulate into B, the even words into A (both on aligned pairs); then A[0] = 0,
+// A[1] is folded into B[0] (its carry enters the next row's first chain), B becomes the new A and
+// A shifted by one PAIR the new B.  ROWS * 12 IMAD.WIDE + ROWS IMAD; nothing ever ripples.
+#define B381_REDC_ROW(A, B, cin)                                                                       \
   {                                                                                                    \
-    const uint32_t m_ = U[(i)] * (uint32_t)B381_N0Q;                                                   \
-    MAD_LO_CC(U[(i) + 0], m_, (uint32_t)B381_Q0);  MADC_HI_CC(U[(i) + 1], m_, (uint32_t)B381_Q0);       \
-    MADC_LO_CC(U[(i) + 2], m_, (uint32_t)B381_Q2); MADC_HI_CC(U[(i) + 3], m_, (uint32_t)B381_Q2);       \
-    MADC_LO_CC(U[(i) + 4], m_, (uint32_t)B381_Q4); MADC_HI_CC(U[(i) + 5], m_, (uint32_t)B381_Q4);       \
-    MADC_LO_CC(U[(i) + 6], m_, (uint32_t)B381_Q6); MADC_HI_CC(U[(i) + 7], m_, (uint32_t)B381_Q6);       \
-    MADC_LO_CC(U[(i) + 8], m_, (uint32_t)B381_Q8); MADC_HI_CC(U[(i) + 9], m_, (uint32_t)B381_Q8);       \
-    MADC_LO_CC(U[(i) + 10], m_, (uint32_t)B381_Q10); MADC_HI_CC(U[(i) + 11], m_, (uint32_t)B381_Q10);   \
-    ADDC_CC(U[(i) + 12], U[(i) + 12], 0u); ADDC(U[(i) + 13], U[(i) + 13], 0u);                          \
-    MAD_LO_CC(U[(i) + 1], m_, (uint32_t)B381_Q1);  MADC_HI_CC(U[(i) + 2], m_, (uint32_t)B381_Q1);       \
-    MADC_LO_CC(U[(i) + 3], m_, (uint32_t)B381_Q3); MADC_HI_CC(U[(i) + 4], m_, (uint32_t)B381_Q3);       \
-    MADC_LO_CC(U[(i) + 5], m_, (uint32_t)B381_Q5); MADC_HI_CC(U[(i) + 6], m_, (uint32_t)B381_Q5);       \
-    MADC_LO_CC(U[(i) + 7], m_, (uint32_t)B381_Q7); MADC_HI_CC(U[(i) + 8], m_, (uint32_t)B381_Q7);       \
-    MADC_LO_CC(U[(i) + 9], m_, (uint32_t)B381_Q9); MADC_HI_CC(U[(i) + 10], m_, (uint32_t)B381_Q9);      \
-    MADC_LO_CC(U[(i) + 11], m_, (uint32_t)B381_Q11); MADC_HI_CC(U[(i) + 12], m_, (uint32_t)B381_Q11);   \
-    ADDC(U[(i) + 13], U[(i) + 13], 0u);                                                                \
+    const uint32_t m_ = A[0] * (uint32_t)B381_N0Q;                                                     \
+    if (cin) { MADC_LO_CC(B[0], m_, (uint32_t)B381_Q1); } else { MAD_LO_CC(B[0], m_, (uint32_t)B381_Q1); }  \
+    MADC_HI_CC(B[1], m_, (uint32_t)B381_Q1);                                                           \
+    MADC_LO_CC(B[2], m_, (uint32_t)B381_Q3);  MADC_HI_CC(B[3], m_, (uint32_t)B381_Q3);                  \
+    MADC_LO_CC(B[4], m_, (uint32_t)B381_Q5);  MADC_HI_CC(B[5], m_, (uint32_t)B381_Q5);                  \
+    MADC_LO_CC(B[6], m_, (uint32_t)B381_Q7);  MADC_HI_CC(B[7], m_, (uint32_t)B381_Q7);                  \
+    MADC_LO_CC(B[8], m_, (uint32_t)B381_Q9);  MADC_HI_CC(B[9], m_, (uint32_t)B381_Q9);                  \
+    MADC_LO_CC(B[10], m_, (uint32_t)B381_Q11); MADC_HI_CC(B[11], m_, (uint32_t)B381_Q11);               \
+    ADDC_CC(B[12], B[12], 0u); ADDC_CC(B[13], B[13], 0u);   /* carry out is zero: links the chains */  \
+    MADC_LO_CC(A[0], m_, (uint32_t)B381_Q0);  MADC_HI_CC(A[1], m_, (uint32_t)B381_Q0);                  \
+    MADC_LO_CC(A[2], m_, (uint32_t)B381_Q2);  MADC_HI_CC(A[3], m_, (uint32_t)B381_Q2);                  \
+    MADC_LO_CC(A[4], m_, (uint32_t)B381_Q4);  MADC_HI_CC(A[5], m_, (uint32_t)B381_Q4);                  \
+    MADC_LO_CC(A[6], m_, (uint32_t)B381_Q6);  MADC_HI_CC(A[7], m_, (uint32_t)B381_Q6);                  \
+    MADC_LO_CC(A[8], m_, (uint32_t)B381_Q8);  MADC_HI_CC(A[9], m_, (uint32_t)B381_Q8);                  \
+    MADC_LO_CC(A[10], m_, (uint32_t)B381_Q10); MADC_HI_CC(A[11], m_, (uint32_t)B381_Q10);               \
+    ADDC_CC(A[12], A[12], 0u); ADDC_CC(A[13], A[13], 0u);                                               \
   }
 
 // r = t / 2^(32 ROWS) mod p, result in (t / 2^(32 ROWS), t / 2^(32 ROWS) + p].  Only the low ROWS
-// words of t enter the rows: U = t_low + M p grows into fresh (zero) words above them, so every
-// chain ends in words nothing else has written yet, and the high half of t (signed) is added to
-// U >> (32 ROWS) at the end.  ROWS * 12 IMAD.WIDE + ROWS IMAD.
+// words of t enter the rows; the (signed) high half of t is added at the end.
 template <int ROWS>
 B381_HD B381_INL void acc_redc_rows(Fp& r, Acc& t) {
   B381_CC_DECL;
-  uint32_t U[ROWS + 14];
+  uint32_t A[14], B[14];
 #pragma unroll
-  for (int k = 0; k < ROWS; k++) U[k] = t.c[k];
+  for (int k = 0; k < 14; k++) { A[k] = k < ROWS ? t.c[k] : 0u; B[k] = 0; }
 #pragma unroll
-  for (int k = ROWS; k < ROWS + 14; k++) U[k] = 0;
+  for (int i = 0; i < ROWS; i++) {
+    B381_REDC_ROW(A, B, i != 0);
+    if (i + 1 < ROWS) {
+      ADDC_CC(B[0], B[0], A[1]);                      // fold (flag in is zero); its carry enters the next row's first chain
+      uint32_t N[14];
 #pragma unroll
-  for (int i = 0; i < ROWS; i++) B381_REDC_ROW(U, i);
-  ADD_CC(r.l[0], U[ROWS], t.c[ROWS]);
+      for (int k = 0; k < 12; k++) N[k] = A[k + 2];
+      N[12] = 0; N[13] = 0;
 #pragma unroll
-  for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], U[ROWS + k], t.c[ROWS + k]);
-  ADDC(r.l[NL - 1], U[ROWS + NL - 1], t.c[ROWS + NL - 1]);
+      for (int k = 0; k < 14; k++) { A[k] = B[k]; B[k] = N[k]; }
+    }
+  }
+  // words ROWS + k of U are B[k] + A[k + 1]
+  uint32_t h[NL];
+  ADD_CC(h[0], B[0], A[1]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(h[k], B[k], A[k + 1]);
+  ADDC(h[NL - 1], B[NL - 1], A[NL]);
+  ADD_CC(r.l[0], h[0], t.c[ROWS]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], h[k], t.c[ROWS + k]);
+  ADDC(r.l[NL - 1], h[NL - 1], t.c[ROWS + NL - 1]);
 }
 
 B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
   B381_CHECK(t.mag < ACC_MAG_MAX, "acc_redc: input too large");
   acc_redc_rows<NL>(r, t);
-  B381_TB(r.mag = 1.0 + t.mag / 4.2e10 + 1e-9; r.lb = 1.0; r.nonneg = true;)
+  B381_TB(r.mag = 1.0 + t.mag / 4.2e10 + 1e-9; r.lb = t.cb < 0 ? t.cb / 4.2e10 : 0.0; r.nonneg = true;)
 }
 
-// two independent reductions with their rows interleaved in source order
+// two independent reductions with their rows interleaved in source order (the latency of one row's
+// m = A[0] n0' chain hides behind the other reduction's twelve multiplies).  The fold carry of each
+// reduction is parked in a register across the other reduction's row and put back into the carry
+// flag (c + 0xffffffff carries iff c = 1) in front of its next row.
+#define B381_REDC_STEP(A, B, c, i)                                                                     \
+  {                                                                                                    \
+    if ((i) != 0) { uint32_t d_; ADD_CC(d_, c, 0xffffffffu); (void)d_; }                                \
+    B381_REDC_ROW(A, B, (i) != 0);                                                                     \
+    if ((i) + 1 < ROWS) {                                                                              \
+      ADDC_CC(B[0], B[0], A[1]);                                                                       \
+      ADDC(c, 0u, 0u);                                                                                 \
+      uint32_t N_[14];                                                                                 \
+      _Pragma("unroll") for (int k_ = 0; k_ < 12; k_++) N_[k_] = A[k_ + 2];                             \
+      N_[12] = 0; N_[13] = 0;                                                                          \
+      _Pragma("unroll") for (int k_ = 0; k_ < 14; k_++) { A[k_] = B[k_]; B[k_] = N_[k_]; }              \
+    }                                                                                                  \
+  }
+
 B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
   B381_CHECK(t0.mag < ACC_MAG_MAX && t1.mag < ACC_MAG_MAX, "acc_redc2: input too large");
   B381_CC_DECL;
   constexpr int ROWS = NL;
-  uint32_t U0[ROWS + 14], U1[ROWS + 14];
+  uint32_t A0[14], B0[14], A1[14], B1[14], c0 = 0, c1 = 0;
 #pragma unroll
-  for (int k = 0; k < ROWS; k++) { U0[k] = t0.c[k]; U1[k] = t1.c[k]; }
-#pragma unroll
-  for (int k = ROWS; k < ROWS + 14; k++) { U0[k] = 0; U1[k] = 0; }
+  for (int k = 0; k < 14; k++) { A0[k] = k < ROWS ? t0.c[k] : 0u; B0[k] = 0; A1[k] = k < ROWS ? t1.c[k] : 0u; B1[k] = 0; }
 #pragma unroll
   for (int i = 0; i < ROWS; i++) {
-    B381_REDC_ROW(U0, i);
-    B381_REDC_ROW(U1, i);
+    B381_REDC_STEP(A0, B0, c0, i);
+    B381_REDC_STEP(A1, B1, c1, i);
   }
-  ADD_CC(r0.l[0], U0[ROWS], t0.c[ROWS]);
+  uint32_t h[NL];
+  ADD_CC(h[0], B0[0], A0[1]);
 #pragma unroll
-  for (int k = 1; k < NL - 1; k++) ADDC_CC(r0.l[k], U0[ROWS + k], t0.c[ROWS + k]);
-  ADDC(r0.l[NL - 1], U0[ROWS + NL - 1], t0.c[NW - 1]);
-  ADD_CC(r1.l[0], U1[ROWS], t1.c[ROWS]);
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(h[k], B0[k], A0[k + 1]);
+  ADDC(h[NL - 1], B0[NL - 1], A0[NL]);
+  ADD_CC(r0.l[0], h[0], t0.c[ROWS]);
 #pragma unroll
-  for (int k = 1; k < NL - 1; k++) ADDC_CC(r1.l[k], U1[ROWS + k], t1.c[ROWS + k]);
-  ADDC(r1.l[NL - 1], U1[ROWS + NL - 1], t1.c[NW - 1]);
-  B381_TB(r0.mag = 1.0 + t0.mag / 4.2e10 + 1e-9; r0.lb = 1.0; r1.mag = 1.0 + t1.mag / 4.2e10 + 1e-9; r1.lb = 1.0; r0.nonneg = r1.nonneg = true;)
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r0.l[k], h[k], t0.c[ROWS + k]);
+  ADDC(r0.l[NL - 1], h[NL - 1], t0.c[NW - 1]);
+  ADD_CC(h[0], B1[0], A1[1]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(h[k], B1[k], A1[k + 1]);
+  ADDC(h[NL - 1], B1[NL - 1], A1[NL]);
+  ADD_CC(r1.l[0], h[0], t1.c[ROWS]);
+#pragma unroll
+  for (int k = 1; k < NL - 1; k++) ADDC_CC(r1.l[k], h[k], t1.c[ROWS + k]);
+  ADDC(r1.l[NL - 1], h[NL - 1], t1.c[NW - 1]);
+  B381_TB(r0.mag = 1.0 + t0.mag / 4.2e10 + 1e-9; r0.lb = t0.cb < 0 ? t0.cb / 4.2e10 : 0.0; r1.mag = 1.0 + t1.mag / 4.2e10 + 1e-9; r1.lb = t1.cb < 0 ? t1.cb / 4.2e10 : 0.0; r0.nonneg = r1.nonneg = true;)
 }
 
 // r = t / 2^384 mod p: reduction in the EXTERNAL domain (12 rows), for the element-wise Fp / Fp2
@@ -355,7 +445,7 @@ B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
 B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
   B381_CHECK(t.mag < 4.0, "acc_redc384: operands must be canonical");
   acc_redc_rows<12>(r, t);
-  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = 1.0; r.nonneg = true;)
+  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = t.cb < 0 ? t.cb / 9.8 : 0.0; r.nonneg = true;)
 }
 
 B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
@@ -390,7 +480,7 @@ B381_HD B381_INL void fp_wreduce(Fp& a) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(a.l[k], v[k], Q[k]);
   SUBC(a.l[NL - 1], v[NL - 1], Q[NL - 1]);
-  B381_TB(a.mag = 11.0; a.lb = 1.0; a.nonneg = true;)
+  B381_TB(a.mag = 11.0; a.lb = 0.0; a.nonneg = true;)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -413,7 +503,7 @@ B381_HD B381_INL void fp_canon_small(Fp& a) {
   const uint32_t ge = ~(uint32_t)((int32_t)t.l[NL - 1] >> 31);       // all ones if a >= p
 #pragma unroll
   for (int k = 0; k < NL; k++) a.l[k] = (t.l[k] & ge) | (a.l[k] & ~ge);
-  B381_TB(a.mag = 1.0; a.lb = 1.0; a.nonneg = true;)
+  B381_TB(a.mag = 1.0; a.lb = 0.0; a.nonneg = true;)
 }
 
 // full reduction of any stored value to canonical [0,p): one Montgomery multiplication by R' mod p
@@ -421,7 +511,10 @@ B381_HD B381_INL void fp_canon(Fp& a) {
   const uint32_t one[NL] = B381_ONE;
   Fp o, n = a;
   fp_set(o, one);
-  fp_mul(a, n, o);
+  Acc t;
+  B381_TB(t.mag = 0; t.cb = 0;)
+  acc_mul_signed(t, n, o);
+  acc_redc(a, t);
   fp_canon_small(a);
 }
 
@@ -444,7 +537,7 @@ B381_HD B381_INL void fp_unpack32(Fp& r, const uint32_t (&w)[12]) {
 #pragma unroll
   for (int k = 0; k < 12; k++) r.l[k] = w[k];
   r.l[12] = 0;
-  B381_TB(r.mag = 9.9; r.lb = 1.0; r.nonneg = true;)     // any 384-bit integer
+  B381_TB(r.mag = 9.9; r.lb = 0.0; r.nonneg = true;)     // any 384-bit integer
 }
 
 // canonical words -> 12 x u32

@@ -16,7 +16,7 @@
 // ARK mode, arkworks 0.4; values are bit-identical to the oracle.
 #pragma once
 #ifndef B381_FMT
-#define B381_FMT 28
+#define B381_FMT 32      // 32: 13 x 32-bit words with carry chains (fp32.cuh, default); 28: 14 x 28-bit carry-free columns (fp28.cuh)
 #endif
 #if B381_FMT == 32
 #include "fp32.cuh"
@@ -146,11 +146,19 @@ struct TrackEnt { double mag[2], lb[2]; };
 inline std::unordered_map<const void*, TrackEnt>& track_tab() { static std::unordered_map<const void*, TrackEnt> t; return t; }
 inline void track_ld(const u4* p, int h, Fp& a) {
   auto it = track_tab().find(p);
+#if B381_FMT == 32
+  if (it == track_tab().end()) { a.mag = 1.0; a.lb = 0.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
+#else
   if (it == track_tab().end()) { a.mag = 1.0; a.lb = 1.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
+#endif
   a.nonneg = true;
 }
 inline void track_st(const u4* p, int h, const Fp& a) {
+#if B381_FMT == 32
+  B381_CHECK(a.lb >= 0, "store of a possibly negative value");
+#else
   B381_CHECK(a.lb < 1.01 && a.nonneg, "store of non-normalised limbs");
+#endif
   B381_CHECK(a.mag < 1000.0, "store of oversized value");
   auto& e = track_tab()[p];
   e.mag[h] = a.mag; e.lb[h] = a.lb;
@@ -282,8 +290,10 @@ B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, co
   acc_mul(X, sa, sb);
   acc_sub(X, X, A);
   acc_sub(X, X, B);                                 // im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
+  B381_TB(X.cb = 0;)                                // = a0 b1 + a1 b0 >= 0 for non-negative operands
   acc_sub(A, A, B);                                 // re = a0 b0 - a1 b1
   acc_redc2(r0, A, r1, X);
+  fp_add_p(r0, r0);                                 // re > -p/128 -> stored values stay non-negative
 }
 
 // ((a0+a1)(a0-a1), 2 a0 a1); fq2_target_tree.rs:80-91.  2 x 169 + 2 x 156 IMAD.WIDE.
@@ -291,6 +301,7 @@ B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
   Fp s, d, t;
   fp_add(s, a0, a1);
   fp_sub(d, a0, a1);
+  fp_add_p128(d, d);                                // a0 - a1 + 128 p >= 0 (same residue)
   fp_dbl(t, a0);
   Acc T, U;
   acc_mul(T, s, d);
@@ -438,10 +449,12 @@ B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p
     else { acc_mac(P, a0, b0); acc_mac(Q, a1, b1); acc_mac(X, sa, sb); }
   }
   acc_sub(X, X, P);
-  acc_sub(X, X, Q);                                 // im
+  acc_sub(X, X, Q);                                 // im = sum (a_i0 b_i1 + a_i1 b_i0) >= 0
+  B381_TB(X.cb = 0;)
   acc_sub(P, P, Q);                                 // re
   Fp r0, r1;
   acc_redc2(r0, P, r1, X);
+  fp_add_p(r0, r0);
   st_f2(r, r0, r1);
 }
 #else
@@ -512,7 +525,12 @@ B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h) {
 B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
   Fp a0, a1, g0, g1, r0, r1;
   ld_f2(a0, a1, a);
-  if (conj) { fp_neg(a1, a1); fp_norm(a1); }
+  if (conj) {
+    fp_neg(a1, a1); fp_norm(a1);
+#if B381_FMT == 32
+    fp_add_p128(a1, a1);
+#endif
+  }
   fp_const(g0, g_ct.frob[k - 1][j - 1][0]);
   fp_const(g1, g_ct.frob[k - 1][j - 1][1]);
   if (k == 2) {                     // gamma_2[j] lies in Fp
@@ -536,6 +554,9 @@ B381_NOINL void f2_inv(u4* r, const u4* a) {
   fp_mul(r0, a0, ni);
   fp_neg(a1, a1);
   fp_norm(a1);
+#if B381_FMT == 32
+  fp_add_p128(a1, a1);
+#endif
   fp_mul(r1, a1, ni);
   st_f2(r, r0, r1);
 }
@@ -613,8 +634,16 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
       fp_dbl(r0, a0); fp_dbl(r0, r0); fp_dbl(r1, a1); fp_dbl(r1, r1);
       break;
   }
+#if B381_FMT == 32
+  // stored values must be non-negative: the weak reduction (output in [0, 11 p)) where a difference occurs
+  const bool n0 = op == L_SUB || op == L_NEG || op == L_MULXI || op == L_XIADD || op == L_3A_M2B || op == L_3A_P2B || op == L_MUL12XI || op == L_2A_MB;
+  const bool n1 = op == L_SUB || op == L_NEG || op == L_CONJ || op == L_3A_M2B || op == L_3A_P2B || op == L_2A_MB;
+  if (n0) fp_wreduce(r0);
+  if (n1) fp_wreduce(r1);
+#else
   if (op == L_3A_M2B || op == L_3A_P2B) { fp_wreduce(r0); fp_wreduce(r1); }   // linear feedback of b (cyclotomic squaring)
   else f2_norm(r0, r1);
+#endif
   st_f2(r, r0, r1);
 }
 
@@ -641,6 +670,9 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
     fp_add(t0, t0, x0); fp_add(t1, t1, x1);
   }
   f2_norm(t0, t1);
+#if B381_FMT == 32
+  fp_wreduce(t0); fp_wreduce(t1);
+#endif
   st_f2(r, t0, t1);
 }
 
@@ -663,18 +695,21 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
     // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
     Fp s, d, e;
     Acc X, Y, U;
-    fp_add(s, b0, b1); fp_sub(d, b0, b1);
+    fp_add(s, b0, b1); fp_sub(d, b0, b1); fp_add_p128(d, d);
     acc_mul(X, s, d);                               // PB
     fp_dbl(e, b0);
     acc_mul(U, e, b1);                              // QB
     acc_add(Y, X, U);                               // PB + QB
     acc_sub(X, X, U);                               // PB - QB
-    fp_add(s, a0, a1); fp_sub(d, a0, a1);
+    fp_add(s, a0, a1); fp_sub(d, a0, a1); fp_add_p128(d, d);
     acc_mac(X, s, d);                               // + PA
     fp_dbl(e, a0);
     acc_mac(Y, e, a1);                              // + QA
     acc_redc2(t00, X, t01, Y);
   }
+  // In this format every output goes through the weak reduction (it also makes the value
+  // non-negative, which the unsigned multiplications require); `reduce` is ignored.
+  (void)reduce;
   Fp z0, z1;
   {
     const u4* zt0 = mode == 0 ? za : zb;
@@ -682,7 +717,7 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
     Fp w0, w1;
     fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
     fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
-    if (reduce) { fp_wreduce(w0); fp_wreduce(w1); }
+    fp_wreduce(w0); fp_wreduce(w1);
     st_f2(mode == 0 ? ra : rb, w0, w1);
   }
   f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
@@ -692,7 +727,7 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
   Fp x0, x1;
   fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
   fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
-  if (reduce) { fp_wreduce(x0); fp_wreduce(x1); }
+  fp_wreduce(x0); fp_wreduce(x1);
   fp_dbl(x0, x0); fp_dbl(x1, x1);
   st_f2(mode == 0 ? rb : ra, x0, x1);
 }
