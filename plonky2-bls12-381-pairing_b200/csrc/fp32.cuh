@@ -341,14 +341,14 @@ B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
     MADC_LO_CC(B[6], m_, (uint32_t)B381_Q7);  MADC_HI_CC(B[7], m_, (uint32_t)B381_Q7);                  \
     MADC_LO_CC(B[8], m_, (uint32_t)B381_Q9);  MADC_HI_CC(B[9], m_, (uint32_t)B381_Q9);                  \
     MADC_LO_CC(B[10], m_, (uint32_t)B381_Q11); MADC_HI_CC(B[11], m_, (uint32_t)B381_Q11);               \
-    ADDC_CC(B[12], B[12], 0u); ADDC_CC(B[13], B[13], 0u);   /* carry out is zero: links the chains */  \
+    ADDC_CC(B[12], B[12], 0u);           /* B[12] was zero: no carry out, the flag links the chains */  \
     MADC_LO_CC(A[0], m_, (uint32_t)B381_Q0);  MADC_HI_CC(A[1], m_, (uint32_t)B381_Q0);                  \
     MADC_LO_CC(A[2], m_, (uint32_t)B381_Q2);  MADC_HI_CC(A[3], m_, (uint32_t)B381_Q2);                  \
     MADC_LO_CC(A[4], m_, (uint32_t)B381_Q4);  MADC_HI_CC(A[5], m_, (uint32_t)B381_Q4);                  \
     MADC_LO_CC(A[6], m_, (uint32_t)B381_Q6);  MADC_HI_CC(A[7], m_, (uint32_t)B381_Q6);                  \
     MADC_LO_CC(A[8], m_, (uint32_t)B381_Q8);  MADC_HI_CC(A[9], m_, (uint32_t)B381_Q8);                  \
     MADC_LO_CC(A[10], m_, (uint32_t)B381_Q10); MADC_HI_CC(A[11], m_, (uint32_t)B381_Q10);               \
-    ADDC_CC(A[12], A[12], 0u); ADDC_CC(A[13], A[13], 0u);                                               \
+    ADDC_CC(A[12], A[12], 0u);           /* A[12] held at most one earlier carry: no carry out */        \
   }
 
 // r = t / 2^(32 ROWS) mod p, result in (t / 2^(32 ROWS), t / 2^(32 ROWS) + p].  Only the low ROWS
