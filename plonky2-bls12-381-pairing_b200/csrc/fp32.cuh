@@ -307,6 +307,44 @@ B381_HD B381_INL void acc_mul_t(Acc& t, const Fp& a, const Fp& b) {
 B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<false>(t, a, b); }
 B381_HD B381_INL void acc_mul_signed(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<true>(t, a, b); }
 
+// t = a0 b0 + a1 b1 + a2 b2 (non-negative operands) accumulated in ONE pair of even / odd arrays:
+// all three products of a row are chained before the next row starts, so the words above the row
+// only ever hold small carry counts and each chain still ends with a single carry add.  Compared
+// with three separate products this saves two 26-word merges and two 26-word additions.
+B381_HD B381_INL void acc_mul3(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2) {
+  B381_CC_DECL;
+  uint32_t E[30], O[30];
+#pragma unroll
+  for (int k = 0; k < 30; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t x0 = b0.l[i], x1 = b1.l[i], x2 = b2.l[i];
+    if ((i & 1) == 0) {
+      B381_MUL_CHAIN(E, i, a0, 0, 7, x0, i != 0, 1); B381_MUL_CHAIN(E, i, a1, 0, 7, x1, 1, 1); B381_MUL_CHAIN(E, i, a2, 0, 7, x2, 1, 1);
+    } else {
+      B381_MUL_CHAIN(E, i + 1, a0, 1, 6, x0, 1, 1); B381_MUL_CHAIN(E, i + 1, a1, 1, 6, x1, 1, 1); B381_MUL_CHAIN(E, i + 1, a2, 1, 6, x2, 1, 1);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t x0 = b0.l[i], x1 = b1.l[i], x2 = b2.l[i];
+    if ((i & 1) == 0) {
+      B381_MUL_CHAIN(O, i, a0, 1, 6, x0, i != 0, 1); B381_MUL_CHAIN(O, i, a1, 1, 6, x1, 1, 1); B381_MUL_CHAIN(O, i, a2, 1, 6, x2, 1, 1);
+    } else {
+      B381_MUL_CHAIN(O, i - 1, a0, 0, 7, x0, 1, 1); B381_MUL_CHAIN(O, i - 1, a1, 0, 7, x1, 1, 1); B381_MUL_CHAIN(O, i - 1, a2, 0, 7, x2, 1, 1);
+    }
+  }
+  uint32_t (&T)[NW] = t.c;
+  T[0] = E[0];
+  ADD_CC(T[1], E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < NW - 1; k++) ADDC_CC(T[k], E[k], O[k - 1]);
+  ADDC(T[NW - 1], E[NW - 1], O[NW - 2]);
+  B381_CHECK(a0.lb >= 0 && b0.lb >= 0 && a1.lb >= 0 && b1.lb >= 0 && a2.lb >= 0 && b2.lb >= 0, "acc_mul3: operands must be non-negative");
+  B381_CHECK(a0.mag < MUL_MAG_MAX && b0.mag < MUL_MAG_MAX && a1.mag < MUL_MAG_MAX && b1.mag < MUL_MAG_MAX && a2.mag < MUL_MAG_MAX && b2.mag < MUL_MAG_MAX, "acc_mul3: operand magnitude");
+  B381_TB(t.cb = 0; t.mag = a0.mag * b0.mag + a1.mag * b1.mag + a2.mag * b2.mag;)
+}
+
 // t += a * b
 B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
   Acc u;

@@ -435,19 +435,22 @@ B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u
 // sum_i (a_i0 b_i1 + a_i1 b_i0), i.e. within 28 n units of 2^56, plus the (signed, tiny) products
 // of the top limbs, which the bound tracker adds from the operand magnitudes.
 #if B381_FMT == 32
+// r = a0 b0 + a1 b1 + a2 b2 in Fp2 (n = 3 only: the tower code uses nothing else), Karatsuba over
+// the SUMS: P = sum a_i0 b_i0, Q = sum a_i1 b_i1, X = sum (a_i0 + a_i1)(b_i0 + b_i1), each one fused
+// three-product accumulation (acc_mul3); re = P - Q (+ p), im = X - P - Q.
 B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
+  (void)n;
+  Fp x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1;
+  ld_f2(x0, x1, a0p); ld_f2(u0, u1, b0p);
+  ld_f2(y0, y1, a1p); ld_f2(v0, v1, b1p);
+  ld_f2(z0, z1, a2p); ld_f2(w0, w1, b2p);
   Acc P, Q, X;
-  for (int i = 0; i < n; i++) {
-    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
-    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
-    Fp a0, a1, b0, b1, sa, sb;
-    ld_f2(a0, a1, ap);
-    ld_f2(b0, b1, bp);
-    fp_add(sa, a0, a1);
-    fp_add(sb, b0, b1);
-    if (i == 0) { acc_mul(P, a0, b0); acc_mul(Q, a1, b1); acc_mul(X, sa, sb); }
-    else { acc_mac(P, a0, b0); acc_mac(Q, a1, b1); acc_mac(X, sa, sb); }
-  }
+  acc_mul3(P, x0, u0, y0, v0, z0, w0);
+  acc_mul3(Q, x1, u1, y1, v1, z1, w1);
+  fp_add(x0, x0, x1); fp_add(u0, u0, u1);
+  fp_add(y0, y0, y1); fp_add(v0, v0, v1);
+  fp_add(z0, z0, z1); fp_add(w0, w0, w1);
+  acc_mul3(X, x0, u0, y0, v0, z0, w0);
   acc_sub(X, X, P);
   acc_sub(X, X, Q);                                 // im = sum (a_i0 b_i1 + a_i1 b_i0) >= 0
   B381_TB(X.cb = 0;)
