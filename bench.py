@@ -301,10 +301,11 @@ def main():
     roofline = {"bound": "imad", "achieved": alg_ginst, "peak": pk.value, "unit": "G IMAD.WIDE/s", "frac": alg_ginst / pk.value,
                 "traffic": traffic, "traffic_note": "DRAM bytes per step (28 launches) from profiles/ncu_traffic.json; algorithmic bytes per step = pairs x 864",
                 "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
-                        "peak = fused IMAD.WIDE.U32 rate measured live by b381_imad_peak (8x16 blocks of distinct products, SASS-checked; "
-                        "32 IMAD.WIDE/clk/SM at %.0f MHz -- round-1 lines up to commit 357fec7 divided by a probe that ptxas had strength-reduced "
-                        "to IADD3 chains, i.e. by twice the real multiplier peak); the kernel executes 421 IMAD.WIDE per Fp mul (14 x 28-bit limbs "
-                        "+ 15-row reduction), i.e. multiplier-pipe busy fraction = frac x 1.40; HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
+                        "peak = fused IMAD.WIDE.U32 rate measured live by b381_imad_peak (faster of two register allocations of the same "
+                        "128-multiply loop body, SASS-checked; 32 IMAD.WIDE/clk/SM at %.0f MHz -- bench lines up to commit 357fec7 divided by a probe "
+                        "that ptxas had strength-reduced to IADD3 chains, i.e. by twice the real multiplier peak); the kernel executes 325 "
+                        "IMAD.WIDE per Fp mul (13 x 13 words + 13 x 12 reduction), i.e. multiplier-pipe busy fraction = frac x 1.08; "
+                        "HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
 
     cpu = None
     if not args.no_cpu:
@@ -344,7 +345,7 @@ def main():
 
     line = {"metric": "pairings/sec (Miller loop + final exp)", "value": value, "unit": "pairings/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64 column accumulators over 14x28-bit limbs (IMAD.WIDE)",
+            "vs_baseline": None, "dtype": "u32 (13 x 32-bit words, IMAD.WIDE.U32.X carry chains, 64-bit products)",
             "data": "synthetic: 256 seeded pairs (a_i G1, b_i G2) tiled to 2^20 per GPU by a seeded permutation",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "mode": "ARK", "sharding": "contiguous per rank, no collective",
                        "l2": "inputs+outputs are 906 MB per step > 126 MB L2 (no flush needed)"},
