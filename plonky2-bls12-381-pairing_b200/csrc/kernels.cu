@@ -5,7 +5,8 @@
 // B381_BLOCK pairings.  Per-thread state is an arena of Fp2 slots: the hot 16 slots in shared
 // memory (224 KB per CTA, word-interleaved so every LDS.128/STS.128 is conflict-free), the cold
 // slots in a per-CTA global scratch region that stays L2-resident because only #SM CTAs exist.
-// The arithmetic (fp28.cuh) is carry-free IMAD.WIDE column accumulation; see DESIGN.md.
+// The arithmetic is fp32.cuh (13 x 32-bit words, IMAD.WIDE.U32.X carry chains; default) or fp28.cuh
+// (14 x 28-bit limbs, carry-free IMAD.WIDE column accumulation; -DB381_FMT=28); see DESIGN.md section 2.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>

@@ -1,5 +1,6 @@
-// hostsim.cpp -- TEST-ONLY host build of the device arithmetic (fp28.cuh / tower.cuh / programs.cuh).
-// The CUDA sources are plain C++ (no inline PTX), so compiling them with g++ gives a bit-exact
+// hostsim.cpp -- TEST-ONLY host build of the device arithmetic (fp32.cuh | fp28.cuh / tower.cuh / programs.cuh).
+// The CUDA sources are plain C++ on the host (the PTX carry-chain macros of fp32.cuh expand to uint64
+// arithmetic with an explicit carry variable), so compiling them with g++ gives a bit-exact
 // simulation of what every GPU thread computes.  tests/ use it on the CPU box to check the device
 // algorithms against the oracle without a GPU, and (built with -DB381_TRACK_BOUNDS) to verify the
 // worst-case limb / column / magnitude bounds of the lazy arithmetic along the executed path.

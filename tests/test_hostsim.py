@@ -1,6 +1,6 @@
-"""The device arithmetic (fp28.cuh / tower.cuh / programs.cuh are plain C++), compiled for the host
+"""The device arithmetic (fp32.cuh or fp28.cuh / tower.cuh / programs.cuh), compiled for the host
 by tests/hostsim/hostsim.cpp, checked bit-for-bit against the oracle -- and, in the
--DB381_TRACK_BOUNDS build, with every limb / column / magnitude bound of the lazy carry-free
+-DB381_TRACK_BOUNDS build, with every magnitude / sign bound of the lazy
 arithmetic asserted along the executed path (control flow is input-independent in ARK/ZK mode, so
 one run covers the worst case of every operation site)."""
 import ctypes
