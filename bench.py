@@ -333,6 +333,17 @@ def main():
         extras["config3_miller_loops_per_s_2p16"] = m / t * 1e3
         t = time_dev(lambda: L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), n, 0, st)), reps=2)
         extras["config5_multi_miller_pairs_per_s_2p20"] = n / t * 1e3
+        # G2Prepared stage: coefficients/s and Miller loops/s against prepared Q's, 2^16 pairs
+        co = torch.empty(m * L.G2PREP_WORDS, dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_g2_prepare_dev(d2.data_ptr(), co.data_ptr(), m, 0, st)), reps=2)
+        extras["g2_prepare_points_per_s_2p16"] = m / t * 1e3
+        t = time_dev(lambda: L.check(lib.b381_miller_loop_prepared_dev(d1.data_ptr(), co.data_ptr(), None, mout.data_ptr(), m, 0, 0, st)), reps=2)
+        extras["miller_loops_prepared_per_s_2p16"] = m / t * 1e3
+        mref = torch.empty(m * 144, dtype=torch.int32, device=dev)
+        L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mref.data_ptr(), m, 0, st))
+        torch.cuda.synchronize()
+        extras["miller_prepared_equals_unprepared"] = bool(torch.equal(mout, mref))
+        del co, mref
         k = 1 << 22
         fa = torch.from_numpy(np.tile(g1[:12], k).view(np.int32)).to(dev); fb = torch.from_numpy(np.tile(g1[12:24], k).view(np.int32)).to(dev)
         fo = torch.empty(k * 12, dtype=torch.int32, device=dev)

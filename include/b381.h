@@ -86,6 +86,21 @@ int b381_fp12_product(const uint32_t* in, uint32_t* out144, size_t n);
    exactly as written (LITERAL): only c0.c0 of the output is non-zero. */
 int b381_literal_optimized(const uint32_t* g1proj, const uint32_t* g2proj, uint32_t* out, size_t n);
 
+/* G2Prepared: the line coefficients of Q as a cached stage -------------------------------------------
+   ark-ec `G2Prepared { ell_coeffs: Vec<(Fp2, Fp2, Fp2)>, infinity }`, the shape the reference's circuit
+   side mirrors at src/miller_loop_target.rs:23-76 (G2PreparedTarget, 68 coefficient triples); the
+   native loop that would consume it is src/miller_loop_native.rs:154-212.  coeffs holds, per point,
+   B381_G2PREP_WORDS = 68 triples x 3 Fq2 x 24 words in the order the Miller loop of `mode` consumes
+   them (63 doublings, 5 additions).  A prepared Q is reused across any number of Miller loops. */
+#define B381_G2PREP_TRIPLES 68
+#define B381_G2PREP_WORDS (68 * 72)
+int b381_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode);
+/* out[i] = miller_loop(P_i, prepared Q_i); identical values to b381_miller_loop on (P_i, Q_i).
+   inf[i] bit0 = P_i is the identity, bit1 = Q_i is the identity (its coefficients are ignored). */
+int b381_miller_loop_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode);
+/* out[i] = final_exp(miller_loop(P_i, prepared Q_i)) */
+int b381_pairing_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode);
+
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);
 int b381_final_exp_dev(const uint32_t* f, uint32_t* out, size_t n, void* stream);
@@ -95,6 +110,8 @@ int b381_fp_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t 
 int b381_fp_mul_chain_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k, void* stream);
 int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
 int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
+int b381_g2_prepare_dev(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, void* stream);
+int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream);
 /* fetch-and-clear the device error word after synchronising `stream`; returns 0 or a B381_E_* code */
 int b381_check_dev(void* stream);
 

@@ -828,6 +828,29 @@ def zk_multi_miller_loop(pairs):
     return f
 
 
+def zk_g2_prepare(q):
+    """The 68 coefficient triples of the ZK loop in the order the driver consumes them
+    (src/miller_loop_native.rs:89-116): the G2Prepared shape of src/miller_loop_target.rs:23-76."""
+    if q is None:
+        return None
+    r = (q[0], q[1], F2_ONE)
+    coeffs = []
+    found_one = False
+    for b in range(63, -1, -1):
+        i = (((BLS_X >> 1) >> b) & 1) == 1
+        if not found_one:
+            found_one = i
+            continue
+        r, c = zk_double_step(r)
+        coeffs.append(c)
+        if i:
+            r, c = zk_add_step(r, q)
+            coeffs.append(c)
+    r, c = zk_double_step(r)
+    coeffs.append(c)
+    return coeffs
+
+
 def zk_miller_loop(p, q):
     return zk_multi_miller_loop([(p, q)])
 

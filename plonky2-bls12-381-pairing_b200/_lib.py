@@ -53,9 +53,15 @@ SIGNATURES = {
     "b381_fp_mul_chain_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
     "b381_fp2_mul_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
     "b381_fp12_mul_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    "b381_g2_prepare": [_u32p, _u32p, ctypes.c_size_t, ctypes.c_int],
+    "b381_miller_loop_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
+    "b381_pairing_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
+    "b381_g2_prepare_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
+    "b381_miller_loop_prepared_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_check_dev": [ctypes.c_void_p],
     "b381_imad_peak": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
 }
+G2PREP_WORDS = 68 * 72
 _RESTYPES = {"b381_last_error": ctypes.c_char_p, "b381_kernel_launches": ctypes.c_ulonglong}
 
 

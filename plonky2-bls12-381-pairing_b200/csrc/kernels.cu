@@ -127,6 +127,38 @@ k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* 
   B381_TMEM_END();
 }
 
+// G2Prepared stage: 68 line-coefficient triples per Q (external format, 4896 words per point)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, u4* garena, int* err, uint32_t* dump_coeffs) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_g2_prepare(cx, g2 + 48 * i, active ? coeffs + (size_t)G2PREP_WORDS * i : dump_coeffs + (size_t)G2PREP_WORDS * threadIdx.x, mode);
+    if (active) report(e, err);
+  }
+  B381_TMEM_END();
+}
+
+// Miller loop (optionally + final exponentiation) of (P, prepared Q)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, u4* garena, int* err, uint32_t* dump) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_miller_prepared(cx, g1 + 24 * i, coeffs + (size_t)G2PREP_WORDS * i, inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode, do_fe);
+    if (active) report(e, err);
+  }
+  B381_TMEM_END();
+}
+
 // every thread runs the Miller loops of TWO pairs per round with shared squarings, multiplies the
 // result into a private accumulator and dumps it (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
@@ -361,6 +393,8 @@ struct State {
   size_t cap_in1 = 0, cap_in2 = 0, cap_inf = 0, cap_out = 0;   // bytes per lane
   uint32_t* d_partial[2] = {nullptr, nullptr};  // raw partial products for multi_miller
   uint32_t* d_dump[2] = {nullptr, nullptr};     // sink for the outputs of padding threads (BLOCK x 144 words)
+  const uint8_t* cur_inf = nullptr;             // identity flags of the chunk host_binary is launching
+  uint32_t* d_dump_coeffs = nullptr;            // same for k_g2_prepare (BLOCK x 4896 words), allocated on first use
   unsigned long long launches = 0;
   std::string last_error;
   std::mutex mu;
@@ -449,6 +483,26 @@ int launch_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, u
   for (size_t off = 0; off < n; off += pairs_per_launch()) {
     size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
     k_pairing<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
+    g.launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, cudaStream_t s, int lane) {
+  if (!g.d_dump_coeffs) CU(cudaMalloc((void**)&g.d_dump_coeffs, (size_t)BLOCK * G2PREP_WORDS * sizeof(uint32_t)));
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_g2_prepare<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g2 + 48 * off, coeffs + (size_t)G2PREP_WORDS * off, m, mode, g.garena[lane], g.d_err, g.d_dump_coeffs);
+    g.launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+int launch_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, cudaStream_t s, int lane) {
+  for (size_t off = 0; off < n; off += pairs_per_launch()) {
+    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
+    k_miller_prepared<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, coeffs + (size_t)G2PREP_WORDS * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, do_fe, g.garena[lane], g.d_err, g.d_dump[lane]);
     g.launches++;
   }
   CU(cudaGetLastError());
@@ -562,10 +616,21 @@ int host_pairs(PairKind kind, const uint32_t* g1, const uint32_t* g2, const uint
 }
 
 // generic element-wise host pipeline: two inputs of wi words, one output of wo words per element
+int ensure_inf_staging(size_t c) {
+  if (c > g.cap_inf) {
+    for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
+    g.cap_inf = 0;
+    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
+    g.cap_inf = c;
+  }
+  return 0;
+}
+
 template <typename L>
-int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, size_t wa, size_t wb, size_t wo, size_t chunk, L launch) {
+int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, size_t wa, size_t wb, size_t wo, size_t chunk, L launch, const uint8_t* inf = nullptr) {
   size_t c = n < chunk ? n : chunk;
   int rc;
+  if (inf && (rc = ensure_inf_staging(c))) return rc;
   if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * wa * 4))) return rc;
   if (b && (rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * wb * 4))) return rc;
   if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * wo * 4))) return rc;
@@ -577,9 +642,11 @@ int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, s
     if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));
     CU(cudaMemcpyAsync(g.d_in1[lane], a + off * wa, m * wa * 4, cudaMemcpyHostToDevice, g.s_in));
     if (b) CU(cudaMemcpyAsync(g.d_in2[lane], b + off * wb, m * wb * 4, cudaMemcpyHostToDevice, g.s_in));
+    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
     CU(cudaEventRecord(g.ev_in[lane], g.s_in));
     CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
     if (nchunks >= 2) CU(cudaStreamWaitEvent(sk, g.ev_out[lane], 0));
+    g.cur_inf = inf ? g.d_inf[lane] : nullptr;
     if ((rc = launch(g.d_in1[lane], g.d_in2[lane], g.d_out[lane], m, sk, 0))) return rc;
     CU(cudaEventRecord(g.ev_k[lane], sk));
     CU(cudaStreamWaitEvent(g.s_out, g.ev_k[lane], 0));
@@ -644,7 +711,7 @@ int b381_init(int device) {
   int rc;
   if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
       (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)))
+      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)))
     return rc;
   CU(cudaDeviceSynchronize());
   g.launches = 0;
@@ -914,6 +981,50 @@ int b381_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out, si
   if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_wbasis: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return f12_mul_host(a, b, out, n, 1);
+}
+
+// ---- G2Prepared (cached line coefficients) ---------------------------------------------------------
+int b381_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g2 || !coeffs || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_g2_prepare: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return host_binary(g2, (const uint32_t*)nullptr, coeffs, n, 48, 0, G2PREP_WORDS, pairs_per_launch(),
+                     [mode](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) { return launch_g2_prepare(x, o, m, mode, s, lane); });
+}
+
+static int miller_prepared_host(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe) {
+  return host_binary(g1, coeffs, out, n, 24, G2PREP_WORDS, 144, pairs_per_launch(),
+                     [mode, do_fe](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                       return launch_miller_prepared(x, y, g.cur_inf, o, m, mode, do_fe, s, lane);
+                     }, inf);
+}
+
+int b381_miller_loop_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_miller_loop_prepared: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return miller_prepared_host(g1, coeffs, inf, out, n, mode, 0);
+}
+
+int b381_pairing_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
+  REQUIRE_INIT();
+  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing_prepared: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return miller_prepared_host(g1, coeffs, inf, out, n, mode, 1);
+}
+
+int b381_g2_prepare_dev(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, void* stream) {
+  REQUIRE_INIT();
+  if (!g2 || !coeffs || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_g2_prepare_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_g2_prepare(g2, coeffs, n, mode, (cudaStream_t)stream, 0);
+}
+
+int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream) {
+  REQUIRE_INIT();
+  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_miller_loop_prepared_dev: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return launch_miller_prepared(g1, coeffs, inf, out, n, mode, final_exp ? 1 : 0, (cudaStream_t)stream, 0);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

@@ -117,6 +117,93 @@ B381_DEV B381_INL int prog_miller(const Ctx& cx, const uint32_t* g1, const uint3
   return err;
 }
 
+// ---- G2Prepared: the line coefficients of Q as a cached stage --------------------
+// ark-ec G2Prepared { ell_coeffs: Vec<(Fp2, Fp2, Fp2)>, infinity } (the shape the reference's circuit
+// side mirrors at /root/reference/src/miller_loop_target.rs:23-76): 68 triples per Q in the order the
+// Miller loop consumes them (63 doublings, 5 additions), each triple 3 x Fq2 in the external format
+// = 72 words; B381_G2PREP_WORDS = 68 * 72 = 4896 words per point.
+constexpr int G2PREP_TRIPLES = 68;
+constexpr int G2PREP_WORDS = G2PREP_TRIPLES * 72;
+
+B381_DEV B381_INL void store_triple(const Ctx& cx, uint32_t* dst, int L) {
+  for (int k = 0; k < 3; k++) f2_store_ext(dst + 24 * k, S_(L + k));
+}
+B381_DEV B381_INL bool load_triple(const Ctx& cx, int L, const uint32_t* src) {
+  bool ok = true;
+  for (int k = 0; k < 3; k++) ok &= f2_load_ext(S_(L + k), src + 24 * k);
+  return ok;
+}
+
+// coefficients of one Q (affine, external format) -> coeffs[0 .. 4896)
+B381_DEV B381_INL int prog_g2_prepare(const Ctx& cx, const uint32_t* g2, uint32_t* coeffs, int mode) {
+  int err = 0;
+  if (!f2_load_ext(S_(ML_Q), g2)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(ML_Q + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
+  lin(cx, ML_R, ML_Q, -1, L_COPY);
+  lin(cx, ML_R + 1, ML_Q + 1, -1, L_COPY);
+  f2_set_small(S_(ML_R + 2), 1);
+  int idx = 0;
+  if (mode == MODE_ZK) {                           // schedule of zk_miller_loop
+    const uint64_t xh = B381_X_ABS >> 1;
+    bool found_one = false;
+    for (int b = 63; b >= 0; b--) {
+      bool bit = (xh >> b) & 1;
+      if (!found_one) { found_one = bit; continue; }
+      zk_double_step(cx, ML_R, ML_L, ML_T); store_triple(cx, coeffs + 72 * idx++, ML_L);
+      if (bit) { zk_add_step(cx, ML_R, ML_Q, ML_L, ML_T); store_triple(cx, coeffs + 72 * idx++, ML_L); }
+    }
+    zk_double_step(cx, ML_R, ML_L, ML_T); store_triple(cx, coeffs + 72 * idx++, ML_L);
+  } else {                                         // schedule of ark_miller_loop
+    const uint64_t xabs = B381_X_ABS;
+    for (int b = 62; b >= 0; b--) {
+      ark_double_step(cx, ML_R, ML_L, ML_T); store_triple(cx, coeffs + 72 * idx++, ML_L);
+      if ((xabs >> b) & 1) { ark_add_step(cx, ML_R, ML_Q, ML_L, ML_T); store_triple(cx, coeffs + 72 * idx++, ML_L); }
+    }
+  }
+  return err;
+}
+
+// Miller loop of (P, prepared Q) -> slots ML_F..; same values as miller_to_slots on (P, Q)
+B381_DEV B381_INL int miller_prepared_to_slots(const Ctx& cx, const uint32_t* g1, const uint32_t* coeffs, int inf, int mode) {
+  int err = 0;
+  const bool ident = (inf & 3) != 0;
+  if (ident) f2_set_small(S_(ML_P), 0);
+  else if (!f2_load_ext(S_(ML_P), g1)) err |= ERR_NOT_CANONICAL;
+  f12_set_one(cx, ML_F);
+  int idx = 0;
+  bool ok = true;
+  if (mode == MODE_ZK) {
+    const uint64_t xh = B381_X_ABS >> 1;
+    bool found_one = false;
+    for (int b = 63; b >= 0; b--) {
+      bool bit = (xh >> b) & 1;
+      if (!found_one) { found_one = bit; continue; }
+      ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); zk_ell(cx, ML_F, ML_L, ML_P, ML_T);
+      if (bit) { ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); zk_ell(cx, ML_F, ML_L, ML_P, ML_T); }
+      f12_sqr(cx, ML_F, ML_T, ML_L);
+    }
+    ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); zk_ell(cx, ML_F, ML_L, ML_P, ML_T);
+  } else {
+    const uint64_t xabs = B381_X_ABS;
+    for (int b = 62; b >= 0; b--) {
+      if (b != 62) f12_sqr(cx, ML_F, ML_T, ML_L);
+      ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); ark_ell(cx, ML_F, ML_L, ML_P, ML_T);
+      if ((xabs >> b) & 1) { ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); ark_ell(cx, ML_F, ML_L, ML_P, ML_T); }
+    }
+  }
+  f12_conj(cx, ML_F);
+  if (ident) f12_set_one(cx, ML_F);
+  else if (!ok) err |= ERR_NOT_CANONICAL;
+  return err;
+}
+
+B381_DEV B381_INL int prog_miller_prepared(const Ctx& cx, const uint32_t* g1, const uint32_t* coeffs, int inf, uint32_t* out, int mode, int do_fe) {
+  int err = miller_prepared_to_slots(cx, g1, coeffs, inf, mode);
+  if (do_fe) { err |= final_exp_slots(cx, ML_F); f12_store_ext(cx, out, FE_F); }
+  else f12_store_ext(cx, out, ML_F);
+  return err;
+}
+
 B381_DEV B381_INL int prog_final_exp(const Ctx& cx, const uint32_t* in, uint32_t* out) {
   int err = 0;
   if (!f12_load_ext(cx, FE_F, in)) err |= ERR_NOT_CANONICAL;

@@ -82,3 +82,59 @@ def multi_pairing(terms, mode: int = MODE_ARK) -> Fq12:
     lib = _lib.lib()
     _lib.check(lib.b381_multi_pairing(_lib.u32(g1)[1], _lib.u32(g2)[1], _lib.u8(inf)[1], _lib.u32(out)[1], n, mode))
     return Fq12.from_limbs(out)
+
+
+# ---- G2Prepared: cached line coefficients (shape of src/miller_loop_target.rs:23-76 / ark-ec G2Prepared) ----
+@dataclass(frozen=True)
+class G2Prepared:
+    """68 coefficient triples (Fq2, Fq2, Fq2) of one Q in the order the Miller loop of `mode`
+    consumes them, kept in the C-ABI layout (68 x 72 words); `infinity` as in ark-ec."""
+    coeffs: np.ndarray
+    infinity: bool
+    mode: int
+
+    @staticmethod
+    def from_affine(q: G2Affine, mode: int = MODE_ARK) -> "G2Prepared":
+        return g2_prepare_batch([q], mode)[0]
+
+
+def g2_prepare_batch(qs: Sequence[G2Affine], mode: int = MODE_ARK) -> List[G2Prepared]:
+    n = len(qs)
+    if n == 0:
+        raise ValueError("empty batch")
+    gen = G2Affine.generator().limbs()
+    g2 = np.array([gen if q.infinity else q.limbs() for q in qs], dtype=np.uint32).reshape(-1)
+    co = np.zeros(n * _lib.G2PREP_WORDS, dtype=np.uint32)
+    lib = _lib.lib()
+    _lib.check(lib.b381_g2_prepare(_lib.u32(g2)[1], _lib.u32(co)[1], n, mode))
+    W = _lib.G2PREP_WORDS
+    return [G2Prepared(co[W * i:W * (i + 1)].copy(), bool(q.infinity), mode) for i, q in enumerate(qs)]
+
+
+def _marshal_prepared(terms: Sequence[Tuple[G1Affine, G2Prepared]]):
+    n = len(terms)
+    if n == 0:
+        raise ValueError("empty batch")
+    mode = terms[0][1].mode
+    if any(q.mode != mode for _, q in terms):
+        raise ValueError("prepared points of different modes in one batch")
+    g1 = np.array([p.limbs() for p, _ in terms], dtype=np.uint32).reshape(-1)
+    co = np.concatenate([q.coeffs for _, q in terms]).astype(np.uint32)
+    inf = np.array([(1 if p.infinity else 0) | (2 if q.infinity else 0) for p, q in terms], dtype=np.uint8)
+    return n, g1, co, inf, mode
+
+
+def miller_loop_prepared_batch(terms: Sequence[Tuple[G1Affine, G2Prepared]]) -> List[MillerLoopResult]:
+    n, g1, co, inf, mode = _marshal_prepared(terms)
+    out = np.zeros(n * 144, dtype=np.uint32)
+    lib = _lib.lib()
+    _lib.check(lib.b381_miller_loop_prepared(_lib.u32(g1)[1], _lib.u32(co)[1], _lib.u8(inf)[1], _lib.u32(out)[1], n, mode))
+    return [MillerLoopResult(Fq12.from_limbs(out[144 * i:144 * i + 144])) for i in range(n)]
+
+
+def pairing_prepared_batch(terms: Sequence[Tuple[G1Affine, G2Prepared]]) -> List[Fq12]:
+    n, g1, co, inf, mode = _marshal_prepared(terms)
+    out = np.zeros(n * 144, dtype=np.uint32)
+    lib = _lib.lib()
+    _lib.check(lib.b381_pairing_prepared(_lib.u32(g1)[1], _lib.u32(co)[1], _lib.u8(inf)[1], _lib.u32(out)[1], n, mode))
+    return [Fq12.from_limbs(out[144 * i:144 * i + 144]) for i in range(n)]

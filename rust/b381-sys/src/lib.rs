@@ -42,6 +42,11 @@ extern "C" {
     pub fn b381_fp_mul_chain_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, k: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_fp2_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
     pub fn b381_fp12_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_g2_prepare(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_miller_loop_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_pairing_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
+    pub fn b381_g2_prepare_dev(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_miller_loop_prepared_dev(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, final_exp: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_check_dev(stream: *mut c_void) -> c_int;
     pub fn b381_imad_peak(imad_wide_ginst_per_s: *mut f64, sm_mhz: *mut f64) -> c_int;
 }

@@ -131,6 +131,12 @@ int hs_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, 
   return err;
 }
 
+int hs_g2_prepare(const uint32_t* g2, uint32_t* coeffs, int mode) { Ctx cx = make_ctx(); return prog_g2_prepare(cx, g2, coeffs, mode); }
+int hs_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, int inf, uint32_t* out, int mode, int do_fe) {
+  Ctx cx = make_ctx();
+  return prog_miller_prepared(cx, g1, coeffs, inf, out, mode, do_fe);
+}
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

@@ -349,9 +349,68 @@ def test_python_host_api(L):
     assert b381.multi_miller_loop([(P, Q)], mode=b381.miller_loop_native.MODE_LITERAL).f == Fq12.one()
     assert b381.multi_miller_loop([]).f == Fq12.one()
     assert b381.pairing_batch([(P, Q), (G1Affine.identity(), Q)])[1] == Fq12.one()
+    from b381.miller_loop_native import G2Prepared, miller_loop_prepared_batch, pairing_prepared_batch
+    qp = G2Prepared.from_affine(Q)
+    assert miller_loop_prepared_batch([(P, qp)])[0].f == res.f
+    assert pairing_prepared_batch([(P, qp), (G1Affine.identity(), qp)]) == [res.final_exponentiation(), Fq12.one()]
     lit = b381.optimized_miller_loop(G1Projective.generator(), G2Projective.generator())
     assert [lit.c0.c0.c0.v, lit.c0.c0.c1.v] == [int(h, 16) for h in kv["literal_g1_g2_c00"]]
     r = util.rng(48)
     a, b = util.rf12(r), util.rf12(r)
     am, bm = MyFq12.from_fq12(Fq12.from_flat(o.f12_flat(a))), MyFq12.from_fq12(Fq12.from_flat(o.f12_flat(b)))
     assert (am * bm).to_fq12().flat() == o.f12_flat(o.f12_mul(a, b))       # test_myfq12, helpers.rs:248-267
+
+
+def test_g2_prepared_stage(L, lib, z):
+    """b381_g2_prepare / b381_miller_loop_prepared / b381_pairing_prepared: coefficients equal the
+    oracle's G2Prepared, prepared loops equal the unprepared ones bit for bit (golden fixture),
+    ragged batch, identity flags, device-pointer variants, invalid input."""
+    n = 300                                           # > one CTA, not a multiple of anything
+    idx = np.arange(n) % 256
+    g1, g2 = _pairs(z, idx)
+    W = L.G2PREP_WORDS
+    for mode, prep in ((L.MODE_ARK, o.ark_g2_prepare), (L.MODE_ZK, o.zk_g2_prepare)):
+        co = np.zeros(n * W, dtype=np.uint32)
+        L.check(lib.b381_g2_prepare(L.u32(g2)[1], L.u32(co)[1], n, mode))
+        for i in (0, 5, 299):
+            Q = (util.f2_from_words(z["g2"][idx[i]][:24]), util.f2_from_words(z["g2"][idx[i]][24:]))
+            want = sum((util.f2_words(c) for t in prep(Q) for c in t), [])
+            assert co[i * W:(i + 1) * W].tolist() == want, (mode, i)
+        out = np.zeros(n * 144, dtype=np.uint32)
+        ref = np.zeros(n * 144, dtype=np.uint32)
+        L.check(lib.b381_miller_loop_prepared(L.u32(g1)[1], L.u32(co)[1], None, L.u32(out)[1], n, mode))
+        L.check(lib.b381_miller_loop(L.u32(g1)[1], L.u32(g2)[1], None, L.u32(ref)[1], n, mode))
+        assert np.array_equal(out, ref)
+        if mode == L.MODE_ARK:
+            assert np.array_equal(out.reshape(n, 144), z["miller_ark"][idx])
+        L.check(lib.b381_pairing_prepared(L.u32(g1)[1], L.u32(co)[1], None, L.u32(out)[1], n, mode))
+        assert np.array_equal(out.reshape(n, 144), z["pairing"][idx])
+        inf = np.zeros(n, dtype=np.uint8); inf[3] = 1; inf[4] = 2; inf[299] = 3
+        L.check(lib.b381_pairing_prepared(L.u32(g1)[1], L.u32(co)[1], inf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), L.u32(out)[1], n, mode))
+        one = np.array(o.f12_to_limbs32(o.F12_ONE), dtype=np.uint32)
+        got = out.reshape(n, 144)
+        for i in range(n):
+            assert np.array_equal(got[i], one if inf[i] else z["pairing"][idx[i]]), i
+    # one prepared Q reused against many P (the BLS-verify reuse the stage exists for)
+    import torch
+    dev = torch.device("cuda:0")
+    co1 = np.zeros(W, dtype=np.uint32)
+    L.check(lib.b381_g2_prepare(L.u32(np.ascontiguousarray(z["g2"][9]))[1], L.u32(co1)[1], 1, L.MODE_ARK))
+    m = 64
+    dco = torch.from_numpy(np.tile(co1, m).view(np.int32)).to(dev)
+    dg1 = torch.from_numpy(np.ascontiguousarray(z["g1"][:m]).reshape(-1).view(np.int32)).to(dev)
+    dout = torch.empty(m * 144, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b381_miller_loop_prepared_dev(dg1.data_ptr(), dco.data_ptr(), None, dout.data_ptr(), m, L.MODE_ARK, 1, st))
+    L.check(lib.b381_check_dev(st))
+    got = dout.cpu().numpy().view(np.uint32).reshape(m, 144)
+    for i in (0, 9, 63):
+        P = (o.fp_from_limbs32(z["g1"][i][:12].tolist()), o.fp_from_limbs32(z["g1"][i][12:].tolist()))
+        Q = (util.f2_from_words(z["g2"][9][:24]), util.f2_from_words(z["g2"][9][24:]))
+        assert o.f12_eq(o.f12_from_limbs32(got[i].tolist()), o.ark_pairing(P, Q)), i
+    # invalid arguments / non-canonical coefficients
+    assert lib.b381_g2_prepare(None, L.u32(co1)[1], 1, L.MODE_ARK) == -2
+    assert lib.b381_g2_prepare(L.u32(g2)[1], L.u32(co1)[1], 1, L.MODE_LITERAL) == -2
+    bad = np.full(W, 0xFFFFFFFF, dtype=np.uint32)
+    o1 = np.zeros(144, dtype=np.uint32)
+    assert lib.b381_miller_loop_prepared(L.u32(np.ascontiguousarray(z["g1"][0]))[1], L.u32(bad)[1], None, L.u32(o1)[1], 1, L.MODE_ARK) == -3

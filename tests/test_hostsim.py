@@ -161,3 +161,40 @@ def test_multi_miller_and_literal(hs):
     # Q at infinity (z = 0): f_den becomes 0 and the reference panics -> error bit 2
     qinf = ((0, 0), (1, 0), (0, 0))
     assert hs.hs_literal(A(g1p), A(sum((util.f2_words(x) for x in qinf), [])), out) == 2
+
+
+def _triples_words(co):
+    return sum((util.f2_words(c) for t in co for c in t), [])
+
+
+def test_g2_prepared_stage(hs):
+    """G2Prepared coefficients (68 triples) against the oracle's ark_g2_prepare / zk_g2_prepare, and the
+    prepared Miller loop / pairing against the golden fixture of the unprepared path."""
+    z = util.pairs_256()
+    for i in (0, 7):
+        g1, g2 = A(z["g1"][i]), A(z["g2"][i])
+        Q = (util.f2_from_words(z["g2"][i][:24]), util.f2_from_words(z["g2"][i][24:]))
+        for mode, prep in ((0, o.ark_g2_prepare), (1, o.zk_g2_prepare)):
+            co = u(68 * 72)
+            assert hs.hs_g2_prepare(g2, co, mode) == 0
+            want = prep(Q)
+            assert len(want) == 68
+            assert list(co) == _triples_words(want), (i, mode)
+            out = u(144)
+            assert hs.hs_miller_prepared(g1, co, 0, out, mode, 0) == 0
+            ref = u(144)
+            assert hs.hs_miller_loop(g1, g2, 0, ref, mode) == 0
+            assert list(out) == list(ref)
+            if mode == 0:
+                assert list(out) == list(z["miller_ark"][i])
+            assert hs.hs_miller_prepared(g1, co, 0, out, mode, 1) == 0 and list(out) == list(z["pairing"][i])
+            one = o.f12_to_limbs32(o.F12_ONE)
+            for inf in (1, 2, 3):
+                assert hs.hs_miller_prepared(g1, co, inf, out, mode, 0) == 0 and list(out) == one
+    # a coefficient that is not canonical is reported (bit 1), identity pairs ignore their coefficients
+    bad = u(68 * 72)
+    for k in range(68 * 72):
+        bad[k] = 0xFFFFFFFF
+    out = u(144)
+    assert hs.hs_miller_prepared(A(z["g1"][0]), bad, 0, out, 0, 0) == 1
+    assert hs.hs_miller_prepared(A(z["g1"][0]), bad, 2, out, 0, 0) == 0
