@@ -353,6 +353,26 @@ def main():
         extras["config2_fp_mul_stream_G_per_s"] = k / t / 1e6
         extras["config2_fp_mul_stream_GBps"] = k * 144 / t / 1e6
         L.check(lib.b381_check_dev(st))
+        # witness helpers, through the host-pointer API (H2D + kernel + D2H), 2^17 elements
+        import time as _t
+        kh = 1 << 17
+        ha = np.tile(g1[:12], kh).astype(np.uint32)
+        ho = np.zeros(kh * 12, dtype=np.uint32)
+        h2 = np.tile(g2[:24], kh).astype(np.uint32)
+        ho2 = np.zeros(kh * 24, dtype=np.uint32)
+        sq = np.tile(golden[0][:144], 1 << 13).astype(np.uint32)
+        so = np.zeros_like(sq)
+
+        def time_host(fn):
+            fn()
+            t0 = _t.perf_counter(); fn(); return _t.perf_counter() - t0
+        extras["helpers_fp_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_inv(L.u32(ha)[1], L.u32(ho)[1], kh)))
+        extras["helpers_fp2_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp2_inv(L.u32(h2)[1], L.u32(ho2)[1], kh)))
+        extras["helpers_fp12_inv_per_s"] = (1 << 13) / time_host(lambda: L.check(lib.b381_fp12_inv(L.u32(sq)[1], L.u32(so)[1], 1 << 13)))
+        L.check(lib.b381_fp_inv(L.u32(ha)[1], L.u32(ho)[1], kh))
+        hsq = np.zeros(kh * 12, dtype=np.uint32)
+        L.check(lib.b381_fp_mul(L.u32(ho)[1], L.u32(ho)[1], L.u32(hsq)[1], kh))          # squares: always have a root
+        extras["helpers_fp_sqrt_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_sqrt(L.u32(hsq)[1], None, L.u32(ho)[1], kh)))
 
     line = {"metric": "pairings/sec (Miller loop + final exp)", "value": value, "unit": "pairings/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -45,6 +45,7 @@ extern "C" {
 #define B381_E_NOT_CANONICAL (-3)   /* an input limb vector is >= p (reference: Fq::from_bigint(..).unwrap() panics) */
 #define B381_E_ZERO_DIVISION (-4)   /* final_exponentiation(0) / LITERAL f_den == 0 (reference panics) */
 #define B381_E_NOT_INIT (-5)
+#define B381_E_NOT_SQUARE (-6)      /* sqrt of a non-residue, or of zero with sgn0 = 1 (reference: x.sqrt().unwrap() / assert_eq! panic) */
 
 /* lifecycle ------------------------------------------------------------------------------------ */
 int b381_init(int device);                  /* bind this process to one GPU, allocate scratch */
@@ -100,6 +101,24 @@ int b381_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode);
 int b381_miller_loop_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode);
 /* out[i] = final_exp(miller_loop(P_i, prepared Q_i)) */
 int b381_pairing_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode);
+
+/* Batched witness-generation helpers: the native computations the reference's circuit generators run
+   per witness (src/fields/fq_target.rs:243-280, :316-343; fq2_target.rs:320-352, :373-410;
+   fq6_target.rs:384-418; fq12_target.rs:340-374; pow_fq src/fields/helpers.rs:176-195).  Element-wise. */
+int b381_fp_inv(const uint32_t* a, uint32_t* out, size_t n);                      /* a = 0 -> B381_E_ZERO_DIVISION */
+/* sqrt(a) with sgn0_fq(result) == sgn[i] (sgn = NULL: sgn0 = 0); FqSqrtGenerator, fq_target.rs:316-343 */
+int b381_fp_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n);
+/* out[i] = legendre(a) == 1 (fq_target.rs:269-280): zero is not a square by that definition */
+int b381_fp_is_square(const uint32_t* a, uint8_t* out, size_t n);
+/* pow_fq(a, exp) with one exponent (u64 limbs, little-endian) for the whole batch; as in the reference
+   an all-zero exponent returns a */
+int b381_fp_pow(const uint32_t* a, const uint64_t* exp, size_t exp_limbs, uint32_t* out, size_t n);
+int b381_fp2_inv(const uint32_t* a, uint32_t* out, size_t n);
+/* Fq2 sqrt with sgn0_fq2(result) == sgn[i] (src/fields/helpers.rs:169-174) */
+int b381_fp2_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n);
+int b381_fp2_is_square(const uint32_t* a, uint8_t* out, size_t n);
+int b381_fp6_inv(const uint32_t* a, uint32_t* out, size_t n);                     /* 72 words per element */
+int b381_fp12_inv(const uint32_t* a, uint32_t* out, size_t n);
 
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);

@@ -426,6 +426,62 @@ def sgn0_fq2(x):
     return sgn0_fq(x[0]) or (x[0] % P == 0 and sgn0_fq(x[1]))
 
 
+def fp_legendre_is_square(a):
+    """fq_target.rs:269-280: legendre(a) = a^((p-1)/2), is_square = (legendre == 1); zero is not a square."""
+    return pow(a % P, (P - 1) // 2, P) == 1
+
+
+def fp_sqrt_sgn(a, sgn):
+    """FqSqrtGenerator::run_once (fq_target.rs:316-343): sqrt(a), negated when its sgn0 differs from sgn.
+    None where the reference panics (non-residue; zero with sgn = True)."""
+    a %= P
+    s = pow(a, (P + 1) // 4, P)
+    if s * s % P != a:
+        return None
+    if sgn0_fq(s) != bool(sgn):
+        if s == 0:
+            return None
+        s = P - s
+    return s
+
+
+def f2_is_square(a):
+    """a^((p^2-1)/2) == 1 <=> the norm a0^2 + a1^2 is a non-zero square in Fq."""
+    return fp_legendre_is_square((a[0] * a[0] + a[1] * a[1]) % P)
+
+
+def f2_sqrt_sgn(a, sgn):
+    """Fq2 square root with sgn0_fq2(result) == sgn (fq2_target.rs:373-410); both roots +-s of a non-zero
+    element have opposite sgn0, so the result does not depend on the root-finding algorithm."""
+    a = (a[0] % P, a[1] % P)
+    if a == (0, 0):
+        return None if sgn else (0, 0)
+    if a[1] == 0:
+        s = pow(a[0], (P + 1) // 4, P)
+        if s * s % P == a[0]:
+            r = (s, 0)
+        else:
+            s = pow(P - a[0], (P + 1) // 4, P)
+            r = (0, s)
+    else:
+        n = (a[0] * a[0] + a[1] * a[1]) % P
+        s = pow(n, (P + 1) // 4, P)
+        if s * s % P != n:
+            return None
+        half = (P + 1) // 2
+        d = (a[0] + s) * half % P
+        t = pow(d, (P + 1) // 4, P)
+        if t * t % P != d:
+            d = (a[0] - s) * half % P
+            t = pow(d, (P + 1) // 4, P)
+        r = (t, a[1] * pow(2 * t, P - 2, P) % P)
+    if f2_sqr(r) != a:
+        return None
+    if sgn0_fq2(r) != bool(sgn):
+        r = ((P - r[0]) % P, (P - r[1]) % P)
+    return r
+
+
 def get_naf(exp_limbs):
     """helpers.rs:197-239 (u64 limbs, little-endian) -> NAF digits, LSB first."""
     exp = list(exp_limbs)

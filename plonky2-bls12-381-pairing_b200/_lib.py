@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("B381_LIB", os.path.join(_HERE, "libb381.so"))   # B38
 
 MODE_ARK, MODE_ZK, MODE_LITERAL = 0, 1, 2
 
-ERRORS = {-1: "B381_E_CUDA", -2: "B381_E_ARG", -3: "B381_E_NOT_CANONICAL", -4: "B381_E_ZERO_DIVISION", -5: "B381_E_NOT_INIT"}
+ERRORS = {-1: "B381_E_CUDA", -2: "B381_E_ARG", -3: "B381_E_NOT_CANONICAL", -4: "B381_E_ZERO_DIVISION", -5: "B381_E_NOT_INIT", -6: "B381_E_NOT_SQUARE"}
 
 
 class B381Error(RuntimeError):
@@ -53,6 +53,15 @@ SIGNATURES = {
     "b381_fp_mul_chain_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
     "b381_fp2_mul_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
     "b381_fp12_mul_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
+    "b381_fp_inv": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp_sqrt": [_u32p, _u8p, _u32p, ctypes.c_size_t],
+    "b381_fp_is_square": [_u32p, _u8p, ctypes.c_size_t],
+    "b381_fp_pow": [_u32p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t, _u32p, ctypes.c_size_t],
+    "b381_fp2_inv": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp2_sqrt": [_u32p, _u8p, _u32p, ctypes.c_size_t],
+    "b381_fp2_is_square": [_u32p, _u8p, ctypes.c_size_t],
+    "b381_fp6_inv": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp12_inv": [_u32p, _u32p, ctypes.c_size_t],
     "b381_g2_prepare": [_u32p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_miller_loop_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_pairing_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],

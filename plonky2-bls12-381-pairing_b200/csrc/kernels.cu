@@ -16,6 +16,7 @@
 
 #include "../../include/b381.h"
 #include "programs.cuh"
+#include "helpers.cuh"
 
 using namespace b381;
 
@@ -332,6 +333,43 @@ k_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* er
   }
 }
 
+// ---- witness helpers (helpers.cuh): one element per thread, registers only ---------------------------
+enum HelperOp { H_FP_INV = 0, H_FP_SQRT, H_FP_IS_SQUARE, H_FP_POW, H_FP2_INV, H_FP2_SQRT, H_FP2_IS_SQUARE };
+
+__global__ void __launch_bounds__(128)
+k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int nwords, uint32_t* out, uint8_t* out8, size_t n, int* err) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = 0;
+    const int s = sgn ? (sgn[i] & 1) : 0;
+    switch (op) {
+      case H_FP_INV: r = prog_fp_inv(a + 12 * i, out + 12 * i); break;
+      case H_FP_SQRT: r = prog_fp_sqrt(a + 12 * i, s, out + 12 * i); break;
+      case H_FP_IS_SQUARE: r = prog_fp_is_square(a + 12 * i, out8 + i); break;
+      case H_FP_POW: r = prog_fp_pow(a + 12 * i, e, nwords, out + 12 * i); break;
+      case H_FP2_INV: r = prog_fp2_inv(a + 24 * i, out + 24 * i); break;
+      case H_FP2_SQRT: r = prog_fp2_sqrt(a + 24 * i, s, out + 24 * i); break;
+      default: r = prog_fp2_is_square(a + 24 * i, out8 + i); break;
+    }
+    if (r) atomicOr(err, r);
+  }
+}
+
+// Fq12 (deg = 12) / Fq6 (deg = 6) inverse through the slot arena
+__global__ void __launch_bounds__(BLOCK, 1)
+k_tower_inv(const uint32_t* in, uint32_t* out, size_t n, int deg, u4* garena, int* err, uint32_t* dump) {
+  Ctx cx = make_ctx(garena, B381_LOCKSTEP);
+  const int w = deg == 12 ? 144 : 72;
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    uint32_t* o = active ? out + (size_t)w * i : dump + 144 * threadIdx.x;
+    int e = deg == 12 ? prog_f12_inv(cx, in + (size_t)w * i, o) : prog_f6_inv(cx, in + (size_t)w * i, o);
+    if (active) report(e, err);
+  }
+}
+
 // integer-pipe roofline probe: what the multiplier pipe sustains on 32 x 32 -> 64-bit multiply-accumulates.
 // Eight accumulator chains; the multiplicand of every multiply-accumulate is the low word of the
 // neighbouring chain's accumulator, so it changes with every instruction and ptxas cannot hoist or
@@ -414,7 +452,8 @@ int fail_arg(const char* what) {
 
 int map_err(int bits) {
   if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
-  if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0) or f_den == 0)"; return B381_E_ZERO_DIVISION; }
+  if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0), f_den == 0 or inverse of zero)"; return B381_E_ZERO_DIVISION; }
+  if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1)"; return B381_E_NOT_SQUARE; }
   return B381_OK;
 }
 
@@ -711,7 +750,7 @@ int b381_init(int device) {
   int rc;
   if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
       (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)))
+      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)))
     return rc;
   CU(cudaDeviceSynchronize());
   g.launches = 0;
@@ -1025,6 +1064,104 @@ int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, co
   if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_miller_loop_prepared_dev: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return launch_miller_prepared(g1, coeffs, inf, out, n, mode, final_exp ? 1 : 0, (cudaStream_t)stream, 0);
+}
+
+// ---- witness helpers -------------------------------------------------------------------
+// element-wise pipelines over host buffers; wi / wo = words per element in / out (wo = 0: byte output)
+static int helper_host(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e_words, int nwords, uint32_t* out, uint8_t* out8, size_t n, size_t w) {
+  // exponent (shared by the batch) to the device once
+  uint32_t* d_e = nullptr;
+  if (e_words) {
+    CU(cudaMalloc((void**)&d_e, (size_t)nwords * 4));
+    CU(cudaMemcpy(d_e, e_words, (size_t)nwords * 4, cudaMemcpyHostToDevice));
+  }
+  const bool bytes_out = out8 != nullptr;
+  std::vector<uint32_t> tmp;                         // byte results: each chunk writes its m bytes at the start of an m-word window
+  uint32_t* hout = out;
+  if (bytes_out) { tmp.resize(n); hout = tmp.data(); }
+  int rc = host_binary(a, (const uint32_t*)nullptr, hout, n, w, 0, bytes_out ? 1 : w, CHUNK,
+                       [op, d_e, nwords, bytes_out](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int) {
+                         k_helper<<<elem_grid(m, 128, 8), 128, 0, s>>>(op, x, g.cur_inf, d_e, nwords, bytes_out ? nullptr : o, bytes_out ? reinterpret_cast<uint8_t*>(o) : nullptr, m, g.d_err);
+                         g.launches++;
+                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_helper");
+                       }, sgn);
+  if (d_e) cudaFree(d_e);
+  if (rc) return rc;
+  if (bytes_out) {
+    // each chunk wrote m bytes at the start of its m-word window of hout
+    for (size_t off = 0; off < n; off += CHUNK) {
+      size_t m = n - off < CHUNK ? n - off : CHUNK;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(tmp.data() + off);
+      for (size_t i = 0; i < m; i++) out8[off + i] = src[i];
+    }
+  }
+  return 0;
+}
+
+int b381_fp_inv(const uint32_t* a, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp_inv: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP_INV, a, nullptr, nullptr, 0, out, nullptr, n, 12);
+}
+int b381_fp_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp_sqrt: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP_SQRT, a, sgn, nullptr, 0, out, nullptr, n, 12);
+}
+int b381_fp_is_square(const uint32_t* a, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp_is_square: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP_IS_SQUARE, a, nullptr, nullptr, 0, nullptr, out, n, 12);
+}
+int b381_fp_pow(const uint32_t* a, const uint64_t* exp, size_t exp_limbs, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !exp || exp_limbs == 0 || exp_limbs > 64 || !out || n == 0) return fail_arg("b381_fp_pow: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  std::vector<uint32_t> e(2 * exp_limbs);
+  for (size_t i = 0; i < exp_limbs; i++) { e[2 * i] = (uint32_t)exp[i]; e[2 * i + 1] = (uint32_t)(exp[i] >> 32); }
+  return helper_host(H_FP_POW, a, nullptr, e.data(), (int)(2 * exp_limbs), out, nullptr, n, 12);
+}
+int b381_fp2_inv(const uint32_t* a, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp2_inv: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP2_INV, a, nullptr, nullptr, 0, out, nullptr, n, 24);
+}
+int b381_fp2_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp2_sqrt: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP2_SQRT, a, sgn, nullptr, 0, out, nullptr, n, 24);
+}
+int b381_fp2_is_square(const uint32_t* a, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp2_is_square: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return helper_host(H_FP2_IS_SQUARE, a, nullptr, nullptr, 0, nullptr, out, n, 24);
+}
+static int tower_inv_host(const uint32_t* a, uint32_t* out, size_t n, int deg) {
+  const size_t w = deg == 12 ? 144 : 72;
+  return host_binary(a, (const uint32_t*)nullptr, out, n, w, 0, w, CHUNK,
+                     [deg](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                       k_tower_inv<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, o, m, deg, g.garena[lane], g.d_err, g.d_dump[lane]);
+                       g.launches++;
+                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_tower_inv");
+                     });
+}
+int b381_fp6_inv(const uint32_t* a, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp6_inv: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return tower_inv_host(a, out, n, 6);
+}
+int b381_fp12_inv(const uint32_t* a, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp12_inv: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return tower_inv_host(a, out, n, 12);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

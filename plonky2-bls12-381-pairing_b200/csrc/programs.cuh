@@ -204,6 +204,32 @@ B381_DEV B381_INL int prog_miller_prepared(const Ctx& cx, const uint32_t* g1, co
   return err;
 }
 
+// Fq12 / Fq6 inverse (witness helpers): /root/reference/src/fields/fq12_target.rs:340-374,
+// fq6_target.rs:384-418 run x.inverse() natively; formulas fq12_target_tree.rs:77-90, fq6_target_tree.rs:59-89
+B381_DEV B381_INL int prog_f12_inv(const Ctx& cx, const uint32_t* in, uint32_t* out) {
+  int err = 0;
+  if (!f12_load_ext(cx, 0, in)) err |= ERR_NOT_CANONICAL;
+  bool zero = true;
+  for (int i = 0; i < 6; i++) zero = f2_is_zero(S_(i)) && zero;
+  if (zero) err |= ERR_ZERO_DIVISION;
+  f12_inv(cx, 0, 6);
+  f12_store_ext(cx, out, 0);
+  return err;
+}
+
+B381_DEV B381_INL int prog_f6_inv(const Ctx& cx, const uint32_t* in, uint32_t* out) {
+  int err = 0;
+  bool zero = true;
+  for (int i = 0; i < 3; i++) {
+    if (!f2_load_ext(S_(i), in + 24 * i)) err |= ERR_NOT_CANONICAL;
+    zero = f2_is_zero(S_(i)) && zero;
+  }
+  if (zero) err |= ERR_ZERO_DIVISION;
+  f6_inv(cx, 3, 0, 6);
+  for (int i = 0; i < 3; i++) f2_store_ext(out + 24 * i, S_(3 + i));
+  return err;
+}
+
 B381_DEV B381_INL int prog_final_exp(const Ctx& cx, const uint32_t* in, uint32_t* out) {
   int err = 0;
   if (!f12_load_ext(cx, FE_F, in)) err |= ERR_NOT_CANONICAL;

@@ -122,3 +122,92 @@ def pow_fq(a: Fq, exp: List[int]) -> Fq:
                 assert z == 1
                 started = True
     return Fq(res)
+
+
+# ---- batched witness helpers on the GPU: the native computations of the reference's
+# ---- circuit generators (fq_target.rs:243-343, fq2_target.rs:320-410, fq6_target.rs:384-418, fq12_target.rs:340-374)
+def _flat(xs):
+    return np.array([w for x in xs for w in x.limbs()], dtype=np.uint32)
+
+
+def _u8p(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+def _unary(fn_name, xs, cls, words):
+    n = len(xs)
+    if n == 0:
+        raise ValueError("empty batch")
+    a = _flat(xs)
+    out = np.zeros(n * words, dtype=np.uint32)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.u32(a)[1], _lib.u32(out)[1], n))
+    return [cls.from_limbs(out[words * i:words * (i + 1)]) for i in range(n)]
+
+
+def inverse_fq_batch(xs: List[Fq]) -> List[Fq]:
+    return _unary("b381_fp_inv", xs, Fq, 12)
+
+
+def inverse_fq2_batch(xs: List[Fq2]) -> List[Fq2]:
+    return _unary("b381_fp2_inv", xs, Fq2, 24)
+
+
+def inverse_fq6_batch(xs: List[Fq6]) -> List[Fq6]:
+    return _unary("b381_fp6_inv", xs, Fq6, 72)
+
+
+def inverse_fq12_batch(xs: List[Fq12]) -> List[Fq12]:
+    return _unary("b381_fp12_inv", xs, Fq12, 144)
+
+
+def _sqrt(fn_name, xs, sgns, cls, words):
+    n = len(xs)
+    if n == 0:
+        raise ValueError("empty batch")
+    a = _flat(xs)
+    s = np.array([1 if b else 0 for b in sgns], dtype=np.uint8)
+    out = np.zeros(n * words, dtype=np.uint32)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.u32(a)[1], _u8p(s), _lib.u32(out)[1], n))
+    return [cls.from_limbs(out[words * i:words * (i + 1)]) for i in range(n)]
+
+
+def sqrt_with_sgn_fq_batch(xs: List[Fq], sgns: List[bool]) -> List[Fq]:
+    """FqSqrtGenerator::run_once, fq_target.rs:316-343 (B381_E_NOT_SQUARE where the reference panics)."""
+    return _sqrt("b381_fp_sqrt", xs, sgns, Fq, 12)
+
+
+def sqrt_with_sgn_fq2_batch(xs: List[Fq2], sgns: List[bool]) -> List[Fq2]:
+    return _sqrt("b381_fp2_sqrt", xs, sgns, Fq2, 24)
+
+
+def _is_square(fn_name, xs):
+    n = len(xs)
+    if n == 0:
+        raise ValueError("empty batch")
+    a = _flat(xs)
+    out = np.zeros(n, dtype=np.uint8)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.u32(a)[1], _u8p(out), n))
+    return [bool(b) for b in out]
+
+
+def is_square_fq_batch(xs: List[Fq]) -> List[bool]:
+    """fq_target.rs:269-280: legendre(x) == 1."""
+    return _is_square("b381_fp_is_square", xs)
+
+
+def is_square_fq2_batch(xs: List[Fq2]) -> List[bool]:
+    return _is_square("b381_fp2_is_square", xs)
+
+
+def pow_fq_batch(xs: List[Fq], exp: List[int]) -> List[Fq]:
+    """pow_fq (helpers.rs:176-195) of every element with one exponent (u64 limbs, little-endian)."""
+    import ctypes
+    n = len(xs)
+    if n == 0:
+        raise ValueError("empty batch")
+    a = _flat(xs)
+    e = (ctypes.c_uint64 * len(exp))(*[int(x) for x in exp])
+    out = np.zeros(n * 12, dtype=np.uint32)
+    _lib.check(_lib.lib().b381_fp_pow(_lib.u32(a)[1], e, len(exp), _lib.u32(out)[1], n))
+    return [Fq.from_limbs(out[12 * i:12 * i + 12]) for i in range(n)]

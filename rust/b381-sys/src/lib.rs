@@ -42,6 +42,15 @@ extern "C" {
     pub fn b381_fp_mul_chain_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, k: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_fp2_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
     pub fn b381_fp12_mul_dev(a: *const u32, b: *const u32, out: *mut u32, n: usize, stream: *mut c_void) -> c_int;
+    pub fn b381_fp_inv(a: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp_sqrt(a: *const u32, sgn: *const u8, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp_is_square(a: *const u32, out: *mut u8, n: usize) -> c_int;
+    pub fn b381_fp_pow(a: *const u32, exp: *const u64, exp_limbs: usize, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp2_inv(a: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp2_sqrt(a: *const u32, sgn: *const u8, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp2_is_square(a: *const u32, out: *mut u8, n: usize) -> c_int;
+    pub fn b381_fp6_inv(a: *const u32, out: *mut u32, n: usize) -> c_int;
+    pub fn b381_fp12_inv(a: *const u32, out: *mut u32, n: usize) -> c_int;
     pub fn b381_g2_prepare(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_miller_loop_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_pairing_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;

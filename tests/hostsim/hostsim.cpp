@@ -7,6 +7,7 @@
 // It is NOT part of the product: libb381.so never links or loads it.
 #include <cstring>
 #include "../../plonky2-bls12-381-pairing_b200/csrc/programs.cuh"
+#include "../../plonky2-bls12-381-pairing_b200/csrc/helpers.cuh"
 
 using namespace b381;
 
@@ -136,6 +137,18 @@ int hs_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, int inf, uint
   Ctx cx = make_ctx();
   return prog_miller_prepared(cx, g1, coeffs, inf, out, mode, do_fe);
 }
+
+#if B381_FMT == 32
+int hs_fp_inv(const uint32_t* a, uint32_t* out) { return prog_fp_inv(a, out); }
+int hs_fp_pow(const uint32_t* a, const uint32_t* e, int nwords, uint32_t* out) { return prog_fp_pow(a, e, nwords, out); }
+int hs_fp_is_square(const uint32_t* a, uint8_t* out) { return prog_fp_is_square(a, out); }
+int hs_fp_sqrt(const uint32_t* a, int sgn, uint32_t* out) { return prog_fp_sqrt(a, sgn, out); }
+int hs_fp2_inv_ext(const uint32_t* a, uint32_t* out) { return prog_fp2_inv(a, out); }
+int hs_fp2_sqrt(const uint32_t* a, int sgn, uint32_t* out) { return prog_fp2_sqrt(a, sgn, out); }
+int hs_fp2_is_square(const uint32_t* a, uint8_t* out) { return prog_fp2_is_square(a, out); }
+#endif
+int hs_fp12_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_inv(cx, a, out); }
+int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f6_inv(cx, a, out); }
 
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS

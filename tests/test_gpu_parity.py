@@ -353,6 +353,16 @@ def test_python_host_api(L):
     qp = G2Prepared.from_affine(Q)
     assert miller_loop_prepared_batch([(P, qp)])[0].f == res.f
     assert pairing_prepared_batch([(P, qp), (G1Affine.identity(), qp)]) == [res.final_exponentiation(), Fq12.one()]
+    from b381.fields import helpers as H
+    from b381.fields.types import Fq, Fq2
+    xs = [Fq(3), Fq(4), Fq(o.P - 1)]
+    assert [x.v for x in H.inverse_fq_batch(xs)] == [o.fp_inv(x.v) for x in xs]
+    assert H.is_square_fq_batch(xs) == [o.fp_legendre_is_square(x.v) for x in xs]
+    assert H.sqrt_with_sgn_fq_batch([Fq(4), Fq(4)], [False, True])[0].v == 2
+    assert H.pow_fq_batch(xs, [5])[0].v == 243
+    z2 = Fq2(Fq(5), Fq(7))
+    inv2 = H.inverse_fq2_batch([z2])[0]
+    assert (inv2.c0.v, inv2.c1.v) == o.f2_inv((5, 7))
     lit = b381.optimized_miller_loop(G1Projective.generator(), G2Projective.generator())
     assert [lit.c0.c0.c0.v, lit.c0.c0.c1.v] == [int(h, 16) for h in kv["literal_g1_g2_c00"]]
     r = util.rng(48)
@@ -414,3 +424,70 @@ def test_g2_prepared_stage(L, lib, z):
     bad = np.full(W, 0xFFFFFFFF, dtype=np.uint32)
     o1 = np.zeros(144, dtype=np.uint32)
     assert lib.b381_miller_loop_prepared(L.u32(np.ascontiguousarray(z["g1"][0]))[1], L.u32(bad)[1], None, L.u32(o1)[1], 1, L.MODE_ARK) == -3
+
+
+def test_witness_helpers_batched(L, lib):
+    """b381_fp_inv / sqrt / is_square / pow, b381_fp2_inv / sqrt / is_square, b381_fp6_inv, b381_fp12_inv on
+    ragged batches against the oracle, plus the error codes where the reference panics."""
+    r = util.rng(77)
+    n = 1000
+    vals = [1, 2, 3, 4, o.P - 1] + [util.rfp(r) for _ in range(n - 5)]
+    a = np.array(sum((o.fp_to_limbs32(v) for v in vals), []), dtype=np.uint32)
+    out = np.zeros(n * 12, dtype=np.uint32)
+    L.check(lib.b381_fp_inv(L.u32(a)[1], L.u32(out)[1], n))
+    for i in list(range(8)) + [999]:
+        assert o.fp_from_limbs32(out[12 * i:12 * i + 12].tolist()) == o.fp_inv(vals[i])
+    sq = np.zeros(n, dtype=np.uint8)
+    L.check(lib.b381_fp_is_square(L.u32(a)[1], sq.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), n))
+    assert sq.tolist() == [1 if o.fp_legendre_is_square(v) else 0 for v in vals]
+    # square roots of the squares among them, alternating sign request
+    sqv = [v for v, f in zip(vals, sq) if f]
+    m = len(sqv)
+    sgn = np.array([i & 1 for i in range(m)], dtype=np.uint8)
+    b = np.array(sum((o.fp_to_limbs32(v) for v in sqv), []), dtype=np.uint32)
+    ro = np.zeros(m * 12, dtype=np.uint32)
+    L.check(lib.b381_fp_sqrt(L.u32(b)[1], sgn.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), L.u32(ro)[1], m))
+    for i in range(m):
+        assert o.fp_from_limbs32(ro[12 * i:12 * i + 12].tolist()) == o.fp_sqrt_sgn(sqv[i], sgn[i]), i
+    nonsq = next(v for v, f in zip(vals, sq) if not f)
+    assert lib.b381_fp_sqrt(L.u32(np.array(o.fp_to_limbs32(nonsq), dtype=np.uint32))[1], None, L.u32(ro)[1], 1) == -6
+    assert lib.b381_fp_inv(L.u32(np.zeros(12, dtype=np.uint32))[1], L.u32(ro)[1], 1) == -4
+    exp = (ctypes.c_uint64 * 2)(0xFFFFFFFFFFFFFFFF, 3)
+    L.check(lib.b381_fp_pow(L.u32(a)[1], exp, 2, L.u32(out)[1], n))
+    for i in (0, 4, 500, 999):
+        assert o.fp_from_limbs32(out[12 * i:12 * i + 12].tolist()) == o.pow_fq(vals[i], [0xFFFFFFFFFFFFFFFF, 3])
+    # Fq2
+    n2 = 400
+    v2 = [(1, 0), (0, 1), (3, 0), (o.P - 1, 0)] + [util.rf2(r) for _ in range(n2 - 4 - 50)] + [o.f2_sqr(util.rf2(r)) for _ in range(50)]
+    a2 = np.array(sum((util.f2_words(v) for v in v2), []), dtype=np.uint32)
+    o2 = np.zeros(n2 * 24, dtype=np.uint32)
+    L.check(lib.b381_fp2_inv(L.u32(a2)[1], L.u32(o2)[1], n2))
+    for i in (0, 1, 2, 3, 100, 399):
+        assert util.f2_from_words(o2[24 * i:24 * i + 24].tolist()) == o.f2_inv(v2[i])
+    s2 = np.zeros(n2, dtype=np.uint8)
+    L.check(lib.b381_fp2_is_square(L.u32(a2)[1], s2.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), n2))
+    assert s2.tolist() == [1 if o.f2_is_square(v) else 0 for v in v2]
+    q2 = [v for v, f in zip(v2, s2) if f]
+    m2 = len(q2)
+    sg2 = np.array([(i >> 1) & 1 for i in range(m2)], dtype=np.uint8)
+    b2 = np.array(sum((util.f2_words(v) for v in q2), []), dtype=np.uint32)
+    r2 = np.zeros(m2 * 24, dtype=np.uint32)
+    L.check(lib.b381_fp2_sqrt(L.u32(b2)[1], sg2.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), L.u32(r2)[1], m2))
+    for i in range(m2):
+        assert util.f2_from_words(r2[24 * i:24 * i + 24].tolist()) == o.f2_sqrt_sgn(q2[i], sg2[i]), i
+    # Fq6 / Fq12 inverse, batch larger than one CTA
+    k = 300
+    v12 = [util.rf12(r) for _ in range(4)]
+    a12 = np.array(sum((o.f12_to_limbs32(v12[i % 4]) for i in range(k)), []), dtype=np.uint32)
+    o12 = np.zeros(k * 144, dtype=np.uint32)
+    L.check(lib.b381_fp12_inv(L.u32(a12)[1], L.u32(o12)[1], k))
+    for i in (0, 1, 2, 3, 299):
+        assert o.f12_eq(o.f12_from_limbs32(o12[144 * i:144 * i + 144].tolist()), o.f12_inv(v12[i % 4]))
+    v6 = [tuple(util.rf2(r) for _ in range(3)) for _ in range(3)]
+    a6 = np.array(sum((sum((util.f2_words(c) for c in v6[i % 3]), []) for i in range(k)), []), dtype=np.uint32)
+    o6 = np.zeros(k * 72, dtype=np.uint32)
+    L.check(lib.b381_fp6_inv(L.u32(a6)[1], L.u32(o6)[1], k))
+    for i in (0, 1, 2, 299):
+        got = tuple(util.f2_from_words(o6[72 * i + 24 * j:72 * i + 24 * j + 24].tolist()) for j in range(3))
+        assert got == o.f6_inv(v6[i % 3])
+    assert lib.b381_fp12_inv(L.u32(np.zeros(144, dtype=np.uint32))[1], L.u32(o12)[1], 1) == -4

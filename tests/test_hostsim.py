@@ -198,3 +198,60 @@ def test_g2_prepared_stage(hs):
     out = u(144)
     assert hs.hs_miller_prepared(A(z["g1"][0]), bad, 0, out, 0, 0) == 1
     assert hs.hs_miller_prepared(A(z["g1"][0]), bad, 2, out, 0, 0) == 0
+
+
+def test_witness_helpers(hs):
+    """Batched witness helpers (helpers.cuh) against the oracle: inverse, sqrt with prescribed sgn0,
+    Legendre / is_square, pow_fq, Fq2 / Fq6 / Fq12 inverse; edge cases the reference panics on."""
+    r = util.rng(31)
+    out, out2, b8 = u(12), u(24), (ctypes.c_uint8 * 1)()
+    vals = [1, 2, 3, 4, o.P - 1, o.P - 2, (o.P - 1) // 2] + [util.rfp(r) for _ in range(12)]
+    for a in vals:
+        wa = A(o.fp_to_limbs32(a))
+        assert hs.hs_fp_inv(wa, out) == 0 and o.fp_from_limbs32(list(out)) == o.fp_inv(a)
+        assert hs.hs_fp_is_square(wa, b8) == 0 and bool(b8[0]) == o.fp_legendre_is_square(a)
+        for sgn in (0, 1):
+            want = o.fp_sqrt_sgn(a, sgn)
+            rc = hs.hs_fp_sqrt(wa, sgn, out)
+            if want is None:
+                assert rc == 4
+            else:
+                got = o.fp_from_limbs32(list(out))
+                assert rc == 0 and got == want and got * got % o.P == a and o.sgn0_fq(got) == bool(sgn)
+        for exp in ([5], [0], [1], [0xFFFFFFFFFFFFFFFF, 3], [(o.P - 1) // 2 & (2**64 - 1), 7, 0]):
+            e32 = sum(([x & 0xFFFFFFFF, x >> 32] for x in exp), [])
+            assert hs.hs_fp_pow(wa, A(e32), len(e32), out) == 0
+            assert o.fp_from_limbs32(list(out)) == o.pow_fq(a, exp), exp
+    assert hs.hs_fp_inv(A([0] * 12), out) == 2                       # inverse of zero: the reference unwraps None
+    assert hs.hs_fp_sqrt(A([0] * 12), 0, out) == 0 and list(out) == [0] * 12
+    assert hs.hs_fp_sqrt(A([0] * 12), 1, out) == 4                   # sqrt(0) cannot have sgn0 = 1
+    assert hs.hs_fp_is_square(A([0] * 12), b8) == 0 and b8[0] == 0
+    assert hs.hs_fp_inv(A([0xFFFFFFFF] * 12), out) & 1              # not canonical
+    cases = [(1, 0), (0, 1), (4, 0), (3, 0), (o.P - 1, 0), (0, o.P - 4), (5, 7)] + [util.rf2(r) for _ in range(10)]
+    cases += [o.f2_sqr(util.rf2(r)) for _ in range(6)]
+    for a in cases:
+        wa = A(util.f2_words(a))
+        assert hs.hs_fp2_inv_ext(wa, out2) == 0 and util.f2_from_words(list(out2)) == o.f2_inv(a)
+        assert hs.hs_fp2_is_square(wa, b8) == 0 and bool(b8[0]) == o.f2_is_square(a)
+        for sgn in (0, 1):
+            want = o.f2_sqrt_sgn(a, sgn)
+            rc = hs.hs_fp2_sqrt(wa, sgn, out2)
+            if want is None:
+                assert rc == 4, (a, sgn)
+            else:
+                got = util.f2_from_words(list(out2))
+                assert rc == 0 and got == want and o.f2_sqr(got) == a and o.sgn0_fq2(got) == bool(sgn)
+    assert hs.hs_fp2_inv_ext(A([0] * 24), out2) == 2
+    assert hs.hs_fp2_sqrt(A([0] * 24), 0, out2) == 0 and list(out2) == [0] * 24
+    assert hs.hs_fp2_sqrt(A([0] * 24), 1, out2) == 4
+    o72, o144 = u(72), u(144)
+    for _ in range(3):
+        a6 = util.rf6(r) if hasattr(util, "rf6") else tuple(util.rf2(r) for _ in range(3))
+        assert hs.hs_fp6_inv_ext(A(sum((util.f2_words(c) for c in a6), [])), o72) == 0
+        got6 = tuple(util.f2_from_words(list(o72)[24 * i:24 * i + 24]) for i in range(3))
+        assert got6 == o.f6_inv(a6)
+        a12 = util.rf12(r)
+        assert hs.hs_fp12_inv_ext(A(o.f12_to_limbs32(a12)), o144) == 0
+        assert o.f12_eq(o.f12_from_limbs32(list(o144)), o.f12_inv(a12))
+    assert hs.hs_fp12_inv_ext(A([0] * 144), o144) == 2
+    assert hs.hs_fp6_inv_ext(A([0] * 72), o72) == 2
