@@ -45,6 +45,7 @@ extern "C" {
 #define B381_E_NOT_CANONICAL (-3)   /* an input limb vector is >= p (reference: Fq::from_bigint(..).unwrap() panics) */
 #define B381_E_ZERO_DIVISION (-4)   /* final_exponentiation(0) / LITERAL f_den == 0 (reference panics) */
 #define B381_E_NOT_INIT (-5)
+#define B381_E_BAD_ENCODING (-7)    /* point encoding with inconsistent flag bits */
 #define B381_E_NOT_SQUARE (-6)      /* sqrt of a non-residue, or of zero with sgn0 = 1 (reference: x.sqrt().unwrap() / assert_eq! panic) */
 
 /* lifecycle ------------------------------------------------------------------------------------ */
@@ -119,6 +120,23 @@ int b381_fp2_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n
 int b381_fp2_is_square(const uint32_t* a, uint8_t* out, size_t n);
 int b381_fp6_inv(const uint32_t* a, uint32_t* out, size_t n);                     /* 72 words per element */
 int b381_fp12_inv(const uint32_t* a, uint32_t* out, size_t n);
+
+/* Wire formats ----------------------------------------------------------------------------------------
+   (a) the reference's witness format: canonical (non-Montgomery) integers as 12 x 32-bit little-endian
+   digits -- `BigUint::from(fq).to_u32_digits()` padded to 12 (src/fields/fq_target.rs:300-313); the
+   inverse is from_biguint_to_fq (src/fields/helpers.rs:154-157); Fq12Target::set_witness
+   (src/fields/fq12_target.rs:408-416) writes the twelve MyFq12 coefficients (w-basis order,
+   src/fields/helpers.rs:39-41) that way: 144 digits per Fq12. */
+int b381_fp_to_u32_digits(const uint32_t* a, uint32_t* out, size_t n);
+int b381_fp_from_u32_digits(const uint32_t* digits, uint32_t* out, size_t n);   /* digits >= p -> B381_E_NOT_CANONICAL */
+int b381_fp12_to_witness_limbs(const uint32_t* f, uint32_t* out, size_t n);
+/* (b) ZCash / IETF point encodings as implemented by ark-bls12-381 0.4 (big-endian; byte 0: 0x80 compressed,
+   0x40 infinity, 0x20 y lexicographically largest): G1 48 / 96 bytes, G2 96 / 192 bytes (x.c1 first).
+   Deserialisation checks the flags, x < p and the curve equation; it does NOT check subgroup membership. */
+int b381_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* inf, size_t n);
+int b381_g1_serialize(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
+int b381_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n);
+int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
 
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);

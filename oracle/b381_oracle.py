@@ -482,6 +482,118 @@ def f2_sqrt_sgn(a, sgn):
     return r
 
 
+# ---- wire formats ----------------------------------------------------------------
+def fp_to_u32_digits(a):
+    """`BigUint::from(fq).to_u32_digits()` padded to 12 (src/fields/fq_target.rs:300-313): canonical integer."""
+    return [(a % P >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+
+
+def f12_to_witness_limbs(f):
+    """Fq12Target::set_witness (src/fields/fq12_target.rs:408-416): MyFq12 order (helpers.rs:39-41), 12 digits each."""
+    out = []
+    for k in range(2):
+        for j in range(3):
+            for i in range(2):
+                out += fp_to_u32_digits(f[i][j][k])
+    return out
+
+
+def _lex_largest_fp(y):
+    return y % P > (P - 1) // 2
+
+
+def _lex_largest_f2(y):
+    return _lex_largest_fp(y[1]) or (y[1] % P == 0 and _lex_largest_fp(y[0]))
+
+
+def g1_serialize(pt, compressed=True):
+    """ZCash / IETF encoding as implemented by ark-bls12-381 0.4: big-endian, flags in the top bits of byte 0."""
+    n = 48 if compressed else 96
+    if pt is None:
+        return bytes([(0x80 if compressed else 0) | 0x40]) + bytes(n - 1)
+    x, y = pt
+    b = bytearray(x.to_bytes(48, "big"))
+    if compressed:
+        b[0] |= 0x80 | (0x20 if _lex_largest_fp(y) else 0)
+        return bytes(b)
+    return bytes(b) + y.to_bytes(48, "big")
+
+
+def g1_deserialize(data, compressed=True):
+    """-> ("ok", point-or-None) or ("err", reason); no subgroup check."""
+    f = data[0]
+    fc, fi, fs = bool(f & 0x80), bool(f & 0x40), bool(f & 0x20)
+    if fc != compressed:
+        return ("err", "encoding")
+    x = int.from_bytes(bytes([f & 0x1F]) + data[1:48], "big")
+    if fi:
+        if fs or x != 0 or any(data[48:]):
+            return ("err", "encoding")
+        return ("ok", None)
+    if x >= P:
+        return ("err", "canonical")
+    rhs = (x * x * x + 4) % P
+    if compressed:
+        y = pow(rhs, (P + 1) // 4, P)
+        if y * y % P != rhs:
+            return ("err", "curve")
+        if _lex_largest_fp(y) != fs:
+            y = (P - y) % P
+        return ("ok", (x, y))
+    if fs:
+        return ("err", "encoding")
+    y = int.from_bytes(data[48:96], "big")
+    if y >= P:
+        return ("err", "canonical")
+    if y * y % P != rhs:
+        return ("err", "curve")
+    return ("ok", (x, y))
+
+
+def g2_serialize(pt, compressed=True):
+    n = 96 if compressed else 192
+    if pt is None:
+        return bytes([(0x80 if compressed else 0) | 0x40]) + bytes(n - 1)
+    x, y = pt
+    b = bytearray(x[1].to_bytes(48, "big") + x[0].to_bytes(48, "big"))
+    if compressed:
+        b[0] |= 0x80 | (0x20 if _lex_largest_f2(y) else 0)
+        return bytes(b)
+    return bytes(b) + y[1].to_bytes(48, "big") + y[0].to_bytes(48, "big")
+
+
+def g2_deserialize(data, compressed=True):
+    f = data[0]
+    fc, fi, fs = bool(f & 0x80), bool(f & 0x40), bool(f & 0x20)
+    if fc != compressed:
+        return ("err", "encoding")
+    x1 = int.from_bytes(bytes([f & 0x1F]) + data[1:48], "big")
+    x0 = int.from_bytes(data[48:96], "big")
+    if fi:
+        if fs or x1 != 0 or any(data[48:]):
+            return ("err", "encoding")
+        return ("ok", None)
+    if x0 >= P or x1 >= P:
+        return ("err", "canonical")
+    x = (x0, x1)
+    rhs = f2_add(f2_mul(f2_sqr(x), x), (4, 4))
+    if compressed:
+        y = f2_sqrt_sgn(rhs, False)
+        if y is None:
+            return ("err", "curve")
+        if _lex_largest_f2(y) != fs:
+            y = f2_neg(y)
+        return ("ok", (x, y))
+    if fs:
+        return ("err", "encoding")
+    y = (int.from_bytes(data[144:192], "big"), int.from_bytes(data[96:144], "big"))
+    if y[0] >= P or y[1] >= P:
+        return ("err", "canonical")
+    if f2_sqr(y) != rhs:
+        return ("err", "curve")
+    return ("ok", (x, y))
+
+
 def get_naf(exp_limbs):
     """helpers.rs:197-239 (u64 limbs, little-endian) -> NAF digits, LSB first."""
     exp = list(exp_limbs)

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("B381_LIB", os.path.join(_HERE, "libb381.so"))   # B38
 
 MODE_ARK, MODE_ZK, MODE_LITERAL = 0, 1, 2
 
-ERRORS = {-1: "B381_E_CUDA", -2: "B381_E_ARG", -3: "B381_E_NOT_CANONICAL", -4: "B381_E_ZERO_DIVISION", -5: "B381_E_NOT_INIT", -6: "B381_E_NOT_SQUARE"}
+ERRORS = {-1: "B381_E_CUDA", -2: "B381_E_ARG", -3: "B381_E_NOT_CANONICAL", -4: "B381_E_ZERO_DIVISION", -5: "B381_E_NOT_INIT", -6: "B381_E_NOT_SQUARE", -7: "B381_E_BAD_ENCODING"}
 
 
 class B381Error(RuntimeError):
@@ -62,6 +62,13 @@ SIGNATURES = {
     "b381_fp2_is_square": [_u32p, _u8p, ctypes.c_size_t],
     "b381_fp6_inv": [_u32p, _u32p, ctypes.c_size_t],
     "b381_fp12_inv": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp_to_u32_digits": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp_from_u32_digits": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_fp12_to_witness_limbs": [_u32p, _u32p, ctypes.c_size_t],
+    "b381_g1_deserialize": [_u8p, ctypes.c_int, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g1_serialize": [_u32p, _u8p, ctypes.c_int, _u8p, ctypes.c_size_t],
+    "b381_g2_deserialize": [_u8p, ctypes.c_int, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g2_serialize": [_u32p, _u8p, ctypes.c_int, _u8p, ctypes.c_size_t],
     "b381_g2_prepare": [_u32p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_miller_loop_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_pairing_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],

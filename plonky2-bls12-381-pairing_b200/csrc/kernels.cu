@@ -354,6 +354,36 @@ k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int n
   }
 }
 
+// wire formats (helpers.cuh): one element per thread
+enum WireOp { W_FP_TO_DIGITS = 0, W_FP_FROM_DIGITS, W_FP12_TO_WITNESS, W_G1_DESER, W_G1_SER, W_G2_DESER, W_G2_SER };
+
+__global__ void __launch_bounds__(128)
+k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, int* err) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = 0;
+    const uint8_t* inb = reinterpret_cast<const uint8_t*>(in);
+    uint8_t* outb = reinterpret_cast<uint8_t*>(out);
+    switch (op) {
+      case W_FP_TO_DIGITS: r = prog_fp_to_digits(in + 12 * i, out + 12 * i); break;
+      case W_FP_FROM_DIGITS: r = prog_fp_from_digits(in + 12 * i, out + 12 * i); break;
+      case W_FP12_TO_WITNESS: r = prog_fp12_to_witness(in + 144 * i, out + 144 * i); break;
+      case W_G1_DESER: {
+        uint8_t f = 0;
+        r = prog_g1_deserialize(inb + (compressed ? 48 : 96) * i, compressed, out + 25 * i, &f);
+        out[25 * i + 24] = f;
+      } break;
+      case W_G1_SER: r = prog_g1_serialize(in + 24 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 48 : 96) * i); break;
+      case W_G2_DESER: {
+        uint8_t f = 0;
+        r = prog_g2_deserialize(inb + (compressed ? 96 : 192) * i, compressed, out + 49 * i, &f);
+        out[49 * i + 48] = f;
+      } break;
+      default: r = prog_g2_serialize(in + 48 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 96 : 192) * i); break;
+    }
+    if (r) atomicOr(err, r);
+  }
+}
+
 // Fq12 (deg = 12) / Fq6 (deg = 6) inverse through the slot arena
 __global__ void __launch_bounds__(BLOCK, 1)
 k_tower_inv(const uint32_t* in, uint32_t* out, size_t n, int deg, u4* garena, int* err, uint32_t* dump) {
@@ -453,7 +483,8 @@ int fail_arg(const char* what) {
 int map_err(int bits) {
   if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
   if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0), f_den == 0 or inverse of zero)"; return B381_E_ZERO_DIVISION; }
-  if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1)"; return B381_E_NOT_SQUARE; }
+  if (bits & 8) { g.last_error = "invalid point encoding (flag bits)"; return B381_E_BAD_ENCODING; }
+  if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1; point not on the curve)"; return B381_E_NOT_SQUARE; }
   return B381_OK;
 }
 
@@ -1162,6 +1193,67 @@ int b381_fp12_inv(const uint32_t* a, uint32_t* out, size_t n) {
   if (!a || !out || n == 0) return fail_arg("b381_fp12_inv: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return tower_inv_host(a, out, n, 12);
+}
+
+// ---- wire formats -------------------------------------------------------------------------
+static int wire_host(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, size_t wi, size_t wo) {
+  return host_binary(in, (const uint32_t*)nullptr, out, n, wi, 0, wo, CHUNK,
+                     [op, compressed](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int) {
+                       k_wire<<<elem_grid(m, 128, 8), 128, 0, s>>>(op, x, g.cur_inf, compressed, o, m, g.d_err);
+                       g.launches++;
+                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_wire");
+                     }, inf);
+}
+int b381_fp_to_u32_digits(const uint32_t* a, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!a || !out || n == 0) return fail_arg("b381_fp_to_u32_digits: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return wire_host(W_FP_TO_DIGITS, a, nullptr, 0, out, n, 12, 12);
+}
+int b381_fp_from_u32_digits(const uint32_t* digits, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!digits || !out || n == 0) return fail_arg("b381_fp_from_u32_digits: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return wire_host(W_FP_FROM_DIGITS, digits, nullptr, 0, out, n, 12, 12);
+}
+int b381_fp12_to_witness_limbs(const uint32_t* f, uint32_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!f || !out || n == 0) return fail_arg("b381_fp12_to_witness_limbs: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return wire_host(W_FP12_TO_WITNESS, f, nullptr, 0, out, n, 144, 144);
+}
+static int deser_host(int op, const uint8_t* in, int compressed, uint32_t* pts, uint8_t* inf, size_t n, size_t in_bytes, size_t pt_words) {
+  std::vector<uint32_t> tmp(n * (pt_words + 1));
+  int rc = wire_host(op, reinterpret_cast<const uint32_t*>(in), nullptr, compressed, tmp.data(), n, in_bytes / 4, pt_words + 1);
+  for (size_t i = 0; i < n; i++) {                  // results are written even when an error is reported
+    memcpy(pts + pt_words * i, tmp.data() + (pt_words + 1) * i, pt_words * 4);
+    if (inf) inf[i] = (uint8_t)tmp[(pt_words + 1) * i + pt_words];
+  }
+  return rc;
+}
+int b381_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* inf, size_t n) {
+  REQUIRE_INIT();
+  if (!in || !g1 || !inf || n == 0) return fail_arg("b381_g1_deserialize: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return deser_host(W_G1_DESER, in, compressed ? 1 : 0, g1, inf, n, compressed ? 48 : 96, 24);
+}
+int b381_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n) {
+  REQUIRE_INIT();
+  if (!in || !g2 || !inf || n == 0) return fail_arg("b381_g2_deserialize: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return deser_host(W_G2_DESER, in, compressed ? 1 : 0, g2, inf, n, compressed ? 96 : 192, 48);
+}
+int b381_g1_serialize(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!g1 || !out || n == 0) return fail_arg("b381_g1_serialize: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return wire_host(W_G1_SER, g1, inf, compressed ? 1 : 0, reinterpret_cast<uint32_t*>(out), n, 24, compressed ? 12 : 24);
+}
+int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!g2 || !out || n == 0) return fail_arg("b381_g2_serialize: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return wire_host(W_G2_SER, g2, inf, compressed ? 1 : 0, reinterpret_cast<uint32_t*>(out), n, 48, compressed ? 24 : 48);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

@@ -146,6 +146,13 @@ int hs_fp_sqrt(const uint32_t* a, int sgn, uint32_t* out) { return prog_fp_sqrt(
 int hs_fp2_inv_ext(const uint32_t* a, uint32_t* out) { return prog_fp2_inv(a, out); }
 int hs_fp2_sqrt(const uint32_t* a, int sgn, uint32_t* out) { return prog_fp2_sqrt(a, sgn, out); }
 int hs_fp2_is_square(const uint32_t* a, uint8_t* out) { return prog_fp2_is_square(a, out); }
+int hs_fp_to_digits(const uint32_t* a, uint32_t* out) { return prog_fp_to_digits(a, out); }
+int hs_fp_from_digits(const uint32_t* d, uint32_t* out) { return prog_fp_from_digits(d, out); }
+int hs_fp12_to_witness(const uint32_t* f, uint32_t* out) { return prog_fp12_to_witness(f, out); }
+int hs_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* inf) { return prog_g1_deserialize(in, compressed, g1, inf); }
+int hs_g1_serialize(const uint32_t* g1, int inf, int compressed, uint8_t* out) { return prog_g1_serialize(g1, inf, compressed, out); }
+int hs_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf) { return prog_g2_deserialize(in, compressed, g2, inf); }
+int hs_g2_serialize(const uint32_t* g2, int inf, int compressed, uint8_t* out) { return prog_g2_serialize(g2, inf, compressed, out); }
 #endif
 int hs_fp12_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_inv(cx, a, out); }
 int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f6_inv(cx, a, out); }

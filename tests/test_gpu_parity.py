@@ -491,3 +491,60 @@ def test_witness_helpers_batched(L, lib):
         got = tuple(util.f2_from_words(o6[72 * i + 24 * j:72 * i + 24 * j + 24].tolist()) for j in range(3))
         assert got == o.f6_inv(v6[i % 3])
     assert lib.b381_fp12_inv(L.u32(np.zeros(144, dtype=np.uint32))[1], L.u32(o12)[1], 1) == -4
+
+
+def test_wire_formats_batched(L, lib, z):
+    """b381_fp_to_u32_digits / from / b381_fp12_to_witness_limbs and the point (de)serialisers on ragged
+    batches against the oracle; invalid encodings give the documented error codes."""
+    r = util.rng(55)
+    n = 700
+    vals = [0, 1, o.P - 1] + [util.rfp(r) for _ in range(n - 3)]
+    a = np.array(sum((o.fp_to_limbs32(v) for v in vals), []), dtype=np.uint32)
+    d = np.zeros(n * 12, dtype=np.uint32)
+    L.check(lib.b381_fp_to_u32_digits(L.u32(a)[1], L.u32(d)[1], n))
+    assert d.tolist() == sum((o.fp_to_u32_digits(v) for v in vals), [])
+    back = np.zeros(n * 12, dtype=np.uint32)
+    L.check(lib.b381_fp_from_u32_digits(L.u32(d)[1], L.u32(back)[1], n))
+    assert np.array_equal(back, a)
+    assert lib.b381_fp_from_u32_digits(L.u32(np.array([(o.P >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32))[1], L.u32(back)[1], 1) == -3
+    k = 40
+    f12 = np.ascontiguousarray(z["pairing"][:k]).reshape(-1)
+    w = np.zeros(k * 144, dtype=np.uint32)
+    L.check(lib.b381_fp12_to_witness_limbs(L.u32(f12)[1], L.u32(w)[1], k))
+    for i in (0, 7, 39):
+        assert w[144 * i:144 * i + 144].tolist() == o.f12_to_witness_limbs(o.f12_from_limbs32(z["pairing"][i].tolist()))
+    u8 = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    m = 256
+    g1 = np.ascontiguousarray(z["g1"][:m]).reshape(-1)
+    g2 = np.ascontiguousarray(z["g2"][:m]).reshape(-1)
+    inf = np.zeros(m, dtype=np.uint8); inf[5] = 1
+    for c, b1, b2 in ((1, 48, 96), (0, 96, 192)):
+        e1 = np.zeros(m * b1, dtype=np.uint8)
+        e2 = np.zeros(m * b2, dtype=np.uint8)
+        L.check(lib.b381_g1_serialize(L.u32(g1)[1], u8(inf), c, u8(e1), m))
+        L.check(lib.b381_g2_serialize(L.u32(g2)[1], u8(inf), c, u8(e2), m))
+        for i in (0, 5, 100, 255):
+            P1 = None if inf[i] else (o.fp_from_limbs32(z["g1"][i][:12].tolist()), o.fp_from_limbs32(z["g1"][i][12:].tolist()))
+            Q = None if inf[i] else (util.f2_from_words(z["g2"][i][:24].tolist()), util.f2_from_words(z["g2"][i][24:].tolist()))
+            assert bytes(e1[b1 * i:b1 * (i + 1)]) == o.g1_serialize(P1, bool(c))
+            assert bytes(e2[b2 * i:b2 * (i + 1)]) == o.g2_serialize(Q, bool(c))
+        d1 = np.zeros(m * 24, dtype=np.uint32); d2 = np.zeros(m * 48, dtype=np.uint32)
+        i1 = np.zeros(m, dtype=np.uint8); i2 = np.zeros(m, dtype=np.uint8)
+        L.check(lib.b381_g1_deserialize(u8(e1), c, L.u32(d1)[1], u8(i1), m))
+        L.check(lib.b381_g2_deserialize(u8(e2), c, L.u32(d2)[1], u8(i2), m))
+        assert np.array_equal(i1, inf) and np.array_equal(i2, inf)
+        keep = np.repeat(inf == 0, 24); keep2 = np.repeat(inf == 0, 48)
+        assert np.array_equal(d1[keep], g1[keep]) and np.array_equal(d2[keep2], g2[keep2])
+    # decompressed points feed the pairing directly
+    out = np.zeros(m * 144, dtype=np.uint32)
+    L.check(lib.b381_pairing(L.u32(d1)[1], L.u32(d2)[1], u8(inf), L.u32(out)[1], m, L.MODE_ARK))
+    got = out.reshape(m, 144)
+    assert np.array_equal(got[0], z["pairing"][0]) and np.array_equal(got[255], z["pairing"][255])
+    bad = bytearray(o.g1_serialize(o.G1_GEN, True)); bad[0] &= 0x7F
+    bb = np.frombuffer(bytes(bad), dtype=np.uint8).copy()
+    assert lib.b381_g1_deserialize(u8(bb), 1, L.u32(d1)[1], u8(i1), 1) == -7
+    x = 1
+    while o.g1_deserialize(bytes([0x80]) + x.to_bytes(47, "big"), True)[0] == "ok":
+        x += 1
+    bb = np.frombuffer(bytes([0x80]) + x.to_bytes(47, "big"), dtype=np.uint8).copy()
+    assert lib.b381_g1_deserialize(u8(bb), 1, L.u32(d1)[1], u8(i1), 1) == -6

@@ -255,3 +255,66 @@ def test_witness_helpers(hs):
         assert o.f12_eq(o.f12_from_limbs32(list(o144)), o.f12_inv(a12))
     assert hs.hs_fp12_inv_ext(A([0] * 144), o144) == 2
     assert hs.hs_fp6_inv_ext(A([0] * 72), o72) == 2
+
+
+def test_wire_formats(hs):
+    """Witness digits (fq_target.rs:300-313, fq12_target.rs:408-416) and the ZCash / IETF point encodings
+    against the oracle: round trips, both y signs, infinity, uncompressed, and every rejection path."""
+    r = util.rng(33)
+    out = u(12)
+    for v in [0, 1, o.P - 1, (1 << 380) + 12345] + [util.rfp(r) for _ in range(6)]:
+        assert hs.hs_fp_to_digits(A(o.fp_to_limbs32(v)), out) == 0 and list(out) == o.fp_to_u32_digits(v)
+        assert hs.hs_fp_from_digits(A(o.fp_to_u32_digits(v)), out) == 0 and list(out) == o.fp_to_limbs32(v)
+    assert hs.hs_fp_from_digits(A([(o.P >> (32 * i)) & 0xFFFFFFFF for i in range(12)]), out) == 1
+    f = util.rf12(r)
+    o144 = u(144)
+    assert hs.hs_fp12_to_witness(A(o.f12_to_limbs32(f)), o144) == 0 and list(o144) == o.f12_to_witness_limbs(f)
+    B = lambda b: (ctypes.c_uint8 * len(b))(*b)
+    inf = (ctypes.c_uint8 * 1)()
+    pts1 = [o.G1_GEN] + [o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER)) for _ in range(3)]
+    pts1 += [(p[0], (o.P - p[1]) % o.P) for p in pts1]
+    for pt in pts1:
+        for c in (1, 0):
+            enc = o.g1_serialize(pt, bool(c))
+            g1 = u(24)
+            assert hs.hs_g1_deserialize(B(enc), c, g1, inf) == 0 and inf[0] == 0
+            assert list(g1) == o.g1_to_limbs32(pt)
+            ob = (ctypes.c_uint8 * len(enc))()
+            assert hs.hs_g1_serialize(g1, 0, c, ob) == 0 and bytes(ob) == enc
+    pts2 = [o.G2_GEN] + [o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER)) for _ in range(3)]
+    pts2 += [(p[0], o.f2_neg(p[1])) for p in pts2]
+    for pt in pts2:
+        for c in (1, 0):
+            enc = o.g2_serialize(pt, bool(c))
+            g2 = u(48)
+            assert hs.hs_g2_deserialize(B(enc), c, g2, inf) == 0 and inf[0] == 0
+            assert list(g2) == o.g2_to_limbs32(pt)
+            ob = (ctypes.c_uint8 * len(enc))()
+            assert hs.hs_g2_serialize(g2, 0, c, ob) == 0 and bytes(ob) == enc
+    # infinity
+    for c, n1, n2 in ((1, 48, 96), (0, 96, 192)):
+        g1, g2 = u(24), u(48)
+        assert hs.hs_g1_deserialize(B(o.g1_serialize(None, bool(c))), c, g1, inf) == 0 and inf[0] == 1
+        assert hs.hs_g2_deserialize(B(o.g2_serialize(None, bool(c))), c, g2, inf) == 0 and inf[0] == 1
+        ob = (ctypes.c_uint8 * n1)()
+        assert hs.hs_g1_serialize(g1, 1, c, ob) == 0 and bytes(ob) == o.g1_serialize(None, bool(c))
+        ob = (ctypes.c_uint8 * n2)()
+        assert hs.hs_g2_serialize(g2, 1, c, ob) == 0 and bytes(ob) == o.g2_serialize(None, bool(c))
+    # rejections: wrong compression flag, infinity with stray bits, x >= p, x not on the curve, y off the curve
+    g1 = u(24)
+    good = bytearray(o.g1_serialize(o.G1_GEN, True))
+    bad = bytearray(good); bad[0] &= 0x7F
+    assert hs.hs_g1_deserialize(B(bytes(bad)), 1, g1, inf) & 8
+    bad = bytearray(o.g1_serialize(None, True)); bad[47] = 1
+    assert hs.hs_g1_deserialize(B(bytes(bad)), 1, g1, inf) & 8
+    bad = bytearray(o.P.to_bytes(48, "big")); bad[0] |= 0x80
+    assert hs.hs_g1_deserialize(B(bytes(bad)), 1, g1, inf) & 1
+    x = 1
+    while o.g1_deserialize(bytes([0x80]) + x.to_bytes(47, "big"), True)[0] == "ok":
+        x += 1
+    assert hs.hs_g1_deserialize(B(bytes([0x80]) + x.to_bytes(47, "big")), 1, g1, inf) & 4
+    unc = bytearray(o.g1_serialize(o.G1_GEN, False)); unc[95] ^= 1
+    assert hs.hs_g1_deserialize(B(bytes(unc)), 0, g1, inf) & 4
+    g2 = u(48)
+    unc = bytearray(o.g2_serialize(o.G2_GEN, False)); unc[191] ^= 1
+    assert hs.hs_g2_deserialize(B(bytes(unc)), 0, g2, inf) & 4

@@ -185,3 +185,31 @@ def test_c_port_matches_fixture_and_python():
     x, y = util.arr(o.f12_to_limbs32(X)), util.arr(o.f12_to_limbs32(Y))
     lib.ref_fp12_mul(util.p32(x), util.p32(y), util.p32(o144), 1, 1)
     assert o.f12_eq(o.f12_from_limbs32(o144), o.f12_mul(X, Y))
+
+
+def test_point_encodings_known_answers():
+    """The standard compressed encodings of the BLS12-381 generators (IETF / ZCash serialisation, the
+    format ark-bls12-381 0.4 implements) pin the oracle's serialiser; round trips pin the parser."""
+    g1c = o.g1_serialize(o.G1_GEN, True)
+    assert g1c.hex() == ("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
+                         "6c55e83ff97a1aeffb3af00adb22c6bb")
+    g2c = o.g2_serialize(o.G2_GEN, True)
+    assert g2c.hex() == ("93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049"
+                         "334cf11213945d57e5ac7d055d042b7e024aa2b2f08f0a91260805272dc51051"
+                         "c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8")
+    assert o.g1_serialize(None, True).hex() == "c0" + "00" * 47
+    assert o.g2_serialize(None, False).hex() == "40" + "00" * 191
+    r = util.rng(91)
+    for _ in range(4):
+        p1 = o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER))
+        p2 = o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER))
+        for c in (True, False):
+            assert o.g1_deserialize(o.g1_serialize(p1, c), c) == ("ok", p1)
+            assert o.g2_deserialize(o.g2_serialize(p2, c), c) == ("ok", p2)
+            neg1 = (p1[0], (o.P - p1[1]) % o.P)
+            assert o.g1_deserialize(o.g1_serialize(neg1, c), c) == ("ok", neg1)
+    assert o.g1_deserialize(o.g1_serialize(None, True), True) == ("ok", None)
+    assert o.g1_deserialize(bytes([0x80]) + bytes(47), True)[0] in ("ok", "err")
+    f = o.f12_mul(util.rf12(r), util.rf12(r))
+    w = o.f12_to_witness_limbs(f)
+    assert len(w) == 144 and w[12:24] == o.fp_to_u32_digits(f[1][0][0]) and w[72:84] == o.fp_to_u32_digits(f[0][0][1])
