@@ -41,6 +41,12 @@
 #define B381_CHECK(cond, msg)
 #endif
 
+#ifdef B381_TRACK_BOUNDS
+#define B381_SETRANGE(r, lo, hi) do { (r).mag = ((lo) < 0 ? -(lo) : (lo)) > ((hi) < 0 ? -(hi) : (hi)) ? ((lo) < 0 ? -(lo) : (lo)) : ((hi) < 0 ? -(hi) : (hi)); (r).lb = 1.0; (r).nonneg = (lo) >= 0; } while (0)
+#else
+#define B381_SETRANGE(r, lo, hi)
+#endif
+
 namespace b381 {
 
 typedef int32_t limb_t;

@@ -40,8 +40,9 @@
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
+#include <execinfo.h>
 #define B381_TB(x) x
-#define B381_CHECK(cond, msg) do { if (!(cond)) { fprintf(stderr, "bound violation: %s (%s:%d)\n", msg, __FILE__, __LINE__); abort(); } } while (0)
+#define B381_CHECK(cond, msg) do { if (!(cond)) { fprintf(stderr, "bound violation: %s (%s:%d)\n", msg, __FILE__, __LINE__); void* bt_[24]; int n_ = backtrace(bt_, 24); backtrace_symbols_fd(bt_, n_, 2); abort(); } } while (0)
 #else
 #define B381_TB(x)
 #define B381_CHECK(cond, msg)
@@ -88,6 +89,7 @@ struct Fp {
 #ifdef B381_TRACK_BOUNDS
   double mag;   // bound on |value| / p
   double lb;    // LOWER bound on value / p (>= 0: provably non-negative)
+  double ub;    // UPPER bound on value / p (mag = max(|lb|, |ub|))
   bool nonneg;  // unused in this format
 #endif
 };
@@ -100,6 +102,12 @@ struct Acc {
 #endif
 };
 
+#ifdef B381_TRACK_BOUNDS
+inline void tb_range(Fp& r, double lo, double hi) { r.lb = lo; r.ub = hi; r.mag = (lo < 0 ? -lo : lo) > (hi < 0 ? -hi : hi) ? (lo < 0 ? -lo : lo) : (hi < 0 ? -hi : hi); r.nonneg = true; }
+#define B381_SETRANGE(r, lo, hi) tb_range(r, lo, hi)
+#else
+#define B381_SETRANGE(r, lo, hi)
+#endif
 constexpr double FP_MAG_MAX = 1048576.0;        // 2^20 p < 2^401: far inside the 2^415 word range
 constexpr double MUL_MAG_MAX = 131072.0;        // operands of a multiplication: |v| < 2^17 p
 constexpr double ACC_MAG_MAX = 1.0e9;           // reduction input: result < (1 + 1e9 / 4.2e10) p
@@ -119,7 +127,7 @@ B381_HD B381_INL constexpr uint32_t pword(int j) {
 B381_HD B381_INL void fp_zero(Fp& r) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = 0;
-  B381_TB(r.mag = 0; r.lb = 0; r.nonneg = true;)
+  B381_SETRANGE(r, 0, 0);
 }
 
 // r = a + 128 p: makes a difference of two stored values (each below 128 p) non-negative
@@ -130,7 +138,19 @@ B381_HD B381_INL void fp_add_p128(Fp& r, const Fp& a) {
 #pragma unroll
   for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], k[i]);
   ADDC(r.l[NL - 1], a.l[NL - 1], k[NL - 1]);
-  B381_TB(r.mag = a.mag + 128; r.lb = a.lb + 128; r.nonneg = true;)
+  B381_SETRANGE(r, a.lb + 128, a.ub + 128);
+}
+
+// r = a + 5 p: a difference a0 - a1 of stored values (each at most 5 p) made non-negative while staying
+// below 2^384 = 9.84 p, so that it still fits the 12-word multiplication
+B381_HD B381_INL void fp_add_p5(Fp& r, const Fp& a) {
+  const uint32_t k[NL] = B381_P5;
+  B381_CC_DECL;
+  ADD_CC(r.l[0], a.l[0], k[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], k[i]);
+  ADDC(r.l[NL - 1], a.l[NL - 1], k[NL - 1]);
+  B381_SETRANGE(r, a.lb + 5, a.ub + 5);
 }
 
 // r = a + p
@@ -140,7 +160,7 @@ B381_HD B381_INL void fp_add_p(Fp& r, const Fp& a) {
 #pragma unroll
   for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], pword(i));
   ADDC(r.l[NL - 1], a.l[NL - 1], 0u);
-  B381_TB(r.mag = a.mag + 1; r.lb = a.lb + 1; r.nonneg = true;)
+  B381_SETRANGE(r, a.lb + 1, a.ub + 1);
 }
 
 B381_HD B381_INL void fp_add(Fp& r, const Fp& a, const Fp& b) {
@@ -149,7 +169,7 @@ B381_HD B381_INL void fp_add(Fp& r, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) ADDC_CC(r.l[k], a.l[k], b.l[k]);
   ADDC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
-  B381_TB(r.mag = a.mag + b.mag; r.lb = a.lb + b.lb; r.nonneg = true;)
+  B381_SETRANGE(r, a.lb + b.lb, a.ub + b.ub);
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_add: magnitude");
 }
 
@@ -159,7 +179,7 @@ B381_HD B381_INL void fp_sub(Fp& r, const Fp& a, const Fp& b) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], a.l[k], b.l[k]);
   SUBC(r.l[NL - 1], a.l[NL - 1], b.l[NL - 1]);
-  B381_TB(r.lb = a.lb - b.mag; r.mag = a.mag + b.mag; r.nonneg = true;)
+  B381_SETRANGE(r, a.lb - b.ub, a.ub - b.lb);
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_sub: magnitude");
 }
 
@@ -169,7 +189,7 @@ B381_HD B381_INL void fp_neg(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(r.l[k], 0u, a.l[k]);
   SUBC(r.l[NL - 1], 0u, a.l[NL - 1]);
-  B381_TB(r.lb = -a.mag; r.mag = a.mag; r.nonneg = true;)
+  B381_SETRANGE(r, -a.ub, -a.lb);
 }
 
 B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
@@ -177,7 +197,7 @@ B381_HD B381_INL void fp_dbl(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = NL - 1; k > 0; k--) r.l[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
   r.l[0] = a.l[0] << 1;
-  B381_TB(r.mag = 2 * a.mag; r.lb = 2 * a.lb; r.nonneg = true;)
+  B381_SETRANGE(r, 2 * a.lb, 2 * a.ub);
   B381_CHECK(r.mag < FP_MAG_MAX, "fp_dbl: magnitude");
 }
 
@@ -188,7 +208,7 @@ B381_HD B381_INL void fp_carry_exact(Fp&) {}
 B381_HD B381_INL void fp_set(Fp& r, const uint32_t (&v)[NL]) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
-  B381_TB(r.mag = 1.0; r.lb = 0.0; r.nonneg = true;)
+  B381_SETRANGE(r, 0.0, 1.0);
 }
 
 // exact halving mod p: (v + (v odd ? p : 0)) >> 1 (arithmetic).  Equals multiplication by 2^-1
@@ -204,7 +224,7 @@ B381_HD B381_INL void fp_half(Fp& r, const Fp& a) {
 #pragma unroll
   for (int k = 0; k < NL - 1; k++) r.l[k] = (t.l[k] >> 1) | (t.l[k + 1] << 31);
   r.l[NL - 1] = (uint32_t)((int32_t)t.l[NL - 1] >> 1);
-  B381_TB(r.mag = (a.mag + 1) / 2; r.lb = a.lb >= 0 ? 0 : a.lb; r.nonneg = true;)
+  B381_SETRANGE(r, a.lb >= 0 ? 0 : a.lb, (a.ub + 1) / 2 > 0 ? (a.ub + 1) / 2 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -253,30 +273,52 @@ B381_HD B381_INL void acc_sub(Acc& r, const Acc& a, const Acc& b) {
     if (tail) { ADDC_CC(X[(s) + 2 * (cnt)], X[(s) + 2 * (cnt)], 0u); }                                  \
   }
 
-template <bool SIGNED>
+// N = 13: any operands;  N = 12: both operands below 2^384 (top word zero, asserted by the tracker):
+// 144 multiplies instead of 169.
+template <bool SIGNED, int N>
 B381_HD B381_INL void acc_mul_t(Acc& t, const Fp& a, const Fp& b) {
   B381_CC_DECL;
+  constexpr int NE = (N + 1) / 2, NO = N / 2;       // even / odd words of a
   uint32_t E[30], O[30];
 #pragma unroll
   for (int k = 0; k < 30; k++) { E[k] = 0; O[k] = 0; }
-  // Chain ends.  The 7-product chains end in a word nothing has written yet (no carry out); the
-  // 6-product chains end inside the previous chain's range and push their carry into the next word,
-  // which is fresh.  All chains of one array are LINKED through the carry flag (the flag handed on
-  // is always zero): the link is semantically void but makes each array one serial dependency chain,
-  // so ptxas interleaves exactly two chains (E and O) instead of a wavefront of thirteen, whose live
-  // carries exceed the seven predicate registers and get spilled through LOP3 bit twiddling.
+  // Chain ends.  A chain whose last word nothing has written yet cannot carry out; otherwise it
+  // pushes its carry into the next word, which is fresh (hi = highest word written so far; the
+  // loops are fully unrolled, so all of this folds at compile time).  All chains of one array are
+  // LINKED through the carry flag (the flag handed on is always zero): the link is semantically void
+  // but makes each array one serial dependency chain, so ptxas interleaves exactly two chains (E
+  // and O) instead of a wavefront of thirteen, whose live carries exceed the seven predicate
+  // registers and get spilled through LOP3 bit twiddling.
+  int hi = -1;
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
+  for (int i = 0; i < N; i++) {
     const uint32_t bi = b.l[i];
-    if ((i & 1) == 0) { B381_MUL_CHAIN(E, i, a, 0, 7, bi, i != 0, 0); }     // a0, a2, .., a12 at words (i + 2k, i + 2k + 1)
-    else { B381_MUL_CHAIN(E, i + 1, a, 1, 6, bi, 1, 1); }                    // a1, a3, .., a11 at words (i + 2k + 1, i + 2k + 2)
+    if ((i & 1) == 0) {                              // even words of a at words (i + 2k, i + 2k + 1)
+      const int last = i + 2 * NE - 1; const bool tail = last <= hi;
+      B381_MUL_CHAIN(E, i, a, 0, NE, bi, i != 0, tail);
+      hi = tail ? last + 1 : last;
+    } else {                                         // odd words of a at words (i + 2k + 1, i + 2k + 2)
+      const int last = i + 1 + 2 * NO - 1; const bool tail = last <= hi;
+      B381_MUL_CHAIN(E, i + 1, a, 1, NO, bi, 1, tail);
+      hi = tail ? last + 1 : (last > hi ? last : hi);
+    }
   }
+  hi = -1;
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
+  for (int i = 0; i < N; i++) {
     const uint32_t bi = b.l[i];
-    if ((i & 1) == 0) { B381_MUL_CHAIN(O, i, a, 1, 6, bi, i != 0, 1); }
-    else { B381_MUL_CHAIN(O, i - 1, a, 0, 7, bi, 1, 0); }
+    if ((i & 1) == 0) {
+      const int last = i + 2 * NO - 1; const bool tail = last <= hi;
+      B381_MUL_CHAIN(O, i, a, 1, NO, bi, i != 0, tail);
+      hi = tail ? last + 1 : (last > hi ? last : hi);
+    } else {
+      const int last = i - 1 + 2 * NE - 1; const bool tail = last <= hi;
+      B381_MUL_CHAIN(O, i - 1, a, 0, NE, bi, 1, tail);
+      hi = tail ? last + 1 : (last > hi ? last : hi);
+    }
   }
+  B381_TB(if (N != NL && !(a.ub < 9.8 && b.ub < 9.8 && a.lb >= 0 && b.lb >= 0)) fprintf(stderr, "acc_mul<12>: a in [%g, %g] b in [%g, %g]\n", a.lb, a.ub, b.lb, b.ub);)
+  B381_CHECK(N == NL || (a.ub < 9.8 && b.ub < 9.8 && a.lb >= 0 && b.lb >= 0), "acc_mul<12>: operand does not fit 12 words");
   uint32_t (&T)[NW] = t.c;
   T[0] = E[0];
   ADD_CC(T[1], E[1], O[0]);
@@ -304,36 +346,40 @@ B381_HD B381_INL void acc_mul_t(Acc& t, const Fp& a, const Fp& b) {
 // Stored values are kept NON-NEGATIVE (products are made so by adding p where the double-width value
 // can be negative, differences by the weak reduction or a 128 p offset), so the hot path multiplies
 // unsigned words and needs no sign correction; acc_mul_signed is for the rare canonicalisation paths.
-B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<false>(t, a, b); }
-B381_HD B381_INL void acc_mul_signed(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<true>(t, a, b); }
+B381_HD B381_INL void acc_mul(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<false, NL>(t, a, b); }
+B381_HD B381_INL void acc_mul12(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<false, 12>(t, a, b); }
+B381_HD B381_INL void acc_mul_signed(Acc& t, const Fp& a, const Fp& b) { acc_mul_t<true, NL>(t, a, b); }
 
 // t = a0 b0 + a1 b1 + a2 b2 (non-negative operands) accumulated in ONE pair of even / odd arrays:
 // all three products of a row are chained before the next row starts, so the words above the row
 // only ever hold small carry counts and each chain still ends with a single carry add.  Compared
 // with three separate products this saves two 26-word merges and two 26-word additions.
-B381_HD B381_INL void acc_mul3(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2) {
+template <int N>
+B381_HD B381_INL void acc_mul3_t(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2) {
   B381_CC_DECL;
+  constexpr int NE = (N + 1) / 2, NO = N / 2;
   uint32_t E[30], O[30];
 #pragma unroll
   for (int k = 0; k < 30; k++) { E[k] = 0; O[k] = 0; }
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
+  for (int i = 0; i < N; i++) {
     const uint32_t x0 = b0.l[i], x1 = b1.l[i], x2 = b2.l[i];
     if ((i & 1) == 0) {
-      B381_MUL_CHAIN(E, i, a0, 0, 7, x0, i != 0, 1); B381_MUL_CHAIN(E, i, a1, 0, 7, x1, 1, 1); B381_MUL_CHAIN(E, i, a2, 0, 7, x2, 1, 1);
+      B381_MUL_CHAIN(E, i, a0, 0, NE, x0, i != 0, 1); B381_MUL_CHAIN(E, i, a1, 0, NE, x1, 1, 1); B381_MUL_CHAIN(E, i, a2, 0, NE, x2, 1, 1);
     } else {
-      B381_MUL_CHAIN(E, i + 1, a0, 1, 6, x0, 1, 1); B381_MUL_CHAIN(E, i + 1, a1, 1, 6, x1, 1, 1); B381_MUL_CHAIN(E, i + 1, a2, 1, 6, x2, 1, 1);
+      B381_MUL_CHAIN(E, i + 1, a0, 1, NO, x0, 1, 1); B381_MUL_CHAIN(E, i + 1, a1, 1, NO, x1, 1, 1); B381_MUL_CHAIN(E, i + 1, a2, 1, NO, x2, 1, 1);
     }
   }
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
+  for (int i = 0; i < N; i++) {
     const uint32_t x0 = b0.l[i], x1 = b1.l[i], x2 = b2.l[i];
     if ((i & 1) == 0) {
-      B381_MUL_CHAIN(O, i, a0, 1, 6, x0, i != 0, 1); B381_MUL_CHAIN(O, i, a1, 1, 6, x1, 1, 1); B381_MUL_CHAIN(O, i, a2, 1, 6, x2, 1, 1);
+      B381_MUL_CHAIN(O, i, a0, 1, NO, x0, i != 0, 1); B381_MUL_CHAIN(O, i, a1, 1, NO, x1, 1, 1); B381_MUL_CHAIN(O, i, a2, 1, NO, x2, 1, 1);
     } else {
-      B381_MUL_CHAIN(O, i - 1, a0, 0, 7, x0, 1, 1); B381_MUL_CHAIN(O, i - 1, a1, 0, 7, x1, 1, 1); B381_MUL_CHAIN(O, i - 1, a2, 0, 7, x2, 1, 1);
+      B381_MUL_CHAIN(O, i - 1, a0, 0, NE, x0, 1, 1); B381_MUL_CHAIN(O, i - 1, a1, 0, NE, x1, 1, 1); B381_MUL_CHAIN(O, i - 1, a2, 0, NE, x2, 1, 1);
     }
   }
+  B381_CHECK(N == NL || (a0.ub < 9.8 && b0.ub < 9.8 && a1.ub < 9.8 && b1.ub < 9.8 && a2.ub < 9.8 && b2.ub < 9.8), "acc_mul3<12>: operand does not fit 12 words");
   uint32_t (&T)[NW] = t.c;
   T[0] = E[0];
   ADD_CC(T[1], E[1], O[0]);
@@ -344,6 +390,8 @@ B381_HD B381_INL void acc_mul3(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1,
   B381_CHECK(a0.mag < MUL_MAG_MAX && b0.mag < MUL_MAG_MAX && a1.mag < MUL_MAG_MAX && b1.mag < MUL_MAG_MAX && a2.mag < MUL_MAG_MAX && b2.mag < MUL_MAG_MAX, "acc_mul3: operand magnitude");
   B381_TB(t.cb = 0; t.mag = a0.mag * b0.mag + a1.mag * b1.mag + a2.mag * b2.mag;)
 }
+B381_HD B381_INL void acc_mul3(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2) { acc_mul3_t<NL>(t, a0, b0, a1, b1, a2, b2); }
+B381_HD B381_INL void acc_mul3_12(Acc& t, const Fp& a0, const Fp& b0, const Fp& a1, const Fp& b1, const Fp& a2, const Fp& b2) { acc_mul3_t<12>(t, a0, b0, a1, b1, a2, b2); }
 
 // t += a * b
 B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
@@ -353,6 +401,12 @@ B381_HD B381_INL void acc_mac(Acc& t, const Fp& a, const Fp& b) {
   acc_add(t, t, u);
 }
 B381_HD B381_INL void acc_mac_cross(Acc& t, const Fp& a, const Fp& b) { acc_mac(t, a, b); }
+B381_HD B381_INL void acc_mac12(Acc& t, const Fp& a, const Fp& b) {
+  Acc u;
+  B381_TB(u.mag = 0; u.cb = 0;)
+  acc_mul12(u, a, b);
+  acc_add(t, t, u);
+}
 
 B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
   B381_CC_DECL;
@@ -425,7 +479,7 @@ B381_HD B381_INL void acc_redc_rows(Fp& r, Acc& t) {
 B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
   B381_CHECK(t.mag < ACC_MAG_MAX, "acc_redc: input too large");
   acc_redc_rows<NL>(r, t);
-  B381_TB(r.mag = 1.0 + t.mag / 4.2e10 + 1e-9; r.lb = t.cb < 0 ? t.cb / 4.2e10 : 0.0; r.nonneg = true;)
+  B381_SETRANGE(r, t.cb < 0 ? t.cb / 4.2e10 : 0.0, 1.0 + t.mag / 4.2e10 + 1e-9);
 }
 
 // two independent reductions with their rows interleaved in source order (the latency of one row's
@@ -475,7 +529,8 @@ B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) ADDC_CC(r1.l[k], h[k], t1.c[ROWS + k]);
   ADDC(r1.l[NL - 1], h[NL - 1], t1.c[NW - 1]);
-  B381_TB(r0.mag = 1.0 + t0.mag / 4.2e10 + 1e-9; r0.lb = t0.cb < 0 ? t0.cb / 4.2e10 : 0.0; r1.mag = 1.0 + t1.mag / 4.2e10 + 1e-9; r1.lb = t1.cb < 0 ? t1.cb / 4.2e10 : 0.0; r0.nonneg = r1.nonneg = true;)
+  B381_SETRANGE(r0, t0.cb < 0 ? t0.cb / 4.2e10 : 0.0, 1.0 + t0.mag / 4.2e10 + 1e-9);
+  B381_SETRANGE(r1, t1.cb < 0 ? t1.cb / 4.2e10 : 0.0, 1.0 + t1.mag / 4.2e10 + 1e-9);
 }
 
 // r = t / 2^384 mod p: reduction in the EXTERNAL domain (12 rows), for the element-wise Fp / Fp2
@@ -483,7 +538,7 @@ B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
 B381_HD B381_INL void acc_redc384(Fp& r, Acc& t) {
   B381_CHECK(t.mag < 4.0, "acc_redc384: operands must be canonical");
   acc_redc_rows<12>(r, t);
-  B381_TB(r.mag = 1.0 + t.mag / 9.8; r.lb = t.cb < 0 ? t.cb / 9.8 : 0.0; r.nonneg = true;)
+  B381_SETRANGE(r, t.cb < 0 ? t.cb / 9.8 : 0.0, 1.0 + t.mag / 9.8);
 }
 
 B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
@@ -493,9 +548,19 @@ B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
   acc_redc(r, t);
 }
 
-// weak reduction: any |v| < 2^20 p comes out in [0, 11 p).  v' = v + 2^21 p >= 0; q = floor-estimate
-// of v' / p from the top word; r = v' - q p.  12 IMAD.WIDE.  Needed wherever a value feeds back
-// LINEARLY into itself (the -2z term of the cyclotomic squaring).
+// weak reduction: any |v| < 2^20 p comes out in [0, 1.02 p).  v' = v + 2^21 p >= 0; q = floor(h / D) with
+// h = v' >> 352 (top two words, below 2^51) and D = (p >> 352) + 1, by a 64-bit reciprocal and one
+// correction step; q p <= v', and v' - q p < 2^352 (1 + h / D) + p < 1.012 p.  12 IMAD.WIDE + a handful
+// of 64-bit operations.  Needed wherever a value feeds back LINEARLY into itself (the -2z term of the
+// cyclotomic squaring) and to bring differences back to small non-negative values.
+B381_HD B381_INL uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
 B381_HD B381_INL void fp_wreduce(Fp& a) {
   B381_CHECK(a.mag < FP_MAG_MAX, "fp_wreduce: value out of range");
   const uint32_t off[NL] = B381_WRED_OFF;       // 2^21 p
@@ -505,8 +570,10 @@ B381_HD B381_INL void fp_wreduce(Fp& a) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) ADDC_CC(v[k], a.l[k], off[k]);
   ADDC(v[NL - 1], a.l[NL - 1], off[NL - 1]);
-  // q <= floor(h 2^384 / p), h = top word (v' < 2^22 p < 2^404: h < 2^20)
-  const uint32_t q = (uint32_t)(((uint64_t)v[NL - 1] * (uint64_t)B381_WRED_C) >> 20);
+  const uint64_t h = ((uint64_t)v[NL - 1] << 32) | v[NL - 2];
+  uint64_t q64 = mulhi64(h, (uint64_t)B381_WRED_M) >> 28;
+  if (h - q64 * (uint64_t)B381_WRED_D >= (uint64_t)B381_WRED_D) q64 += 1;
+  const uint32_t q = (uint32_t)q64;
   uint32_t Q[NL];
 #pragma unroll
   for (int k = 0; k < 6; k++) MUL_WIDE(Q[2 * k], Q[2 * k + 1], q, pword(2 * k));
@@ -518,7 +585,7 @@ B381_HD B381_INL void fp_wreduce(Fp& a) {
 #pragma unroll
   for (int k = 1; k < NL - 1; k++) SUBC_CC(a.l[k], v[k], Q[k]);
   SUBC(a.l[NL - 1], v[NL - 1], Q[NL - 1]);
-  B381_TB(a.mag = 11.0; a.lb = 0.0; a.nonneg = true;)
+  B381_SETRANGE(a, 0.0, 1.02);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,7 +608,7 @@ B381_HD B381_INL void fp_canon_small(Fp& a) {
   const uint32_t ge = ~(uint32_t)((int32_t)t.l[NL - 1] >> 31);       // all ones if a >= p
 #pragma unroll
   for (int k = 0; k < NL; k++) a.l[k] = (t.l[k] & ge) | (a.l[k] & ~ge);
-  B381_TB(a.mag = 1.0; a.lb = 0.0; a.nonneg = true;)
+  B381_SETRANGE(a, 0.0, 1.0);
 }
 
 // full reduction of any stored value to canonical [0,p): one Montgomery multiplication by R' mod p
@@ -575,7 +642,7 @@ B381_HD B381_INL void fp_unpack32(Fp& r, const uint32_t (&w)[12]) {
 #pragma unroll
   for (int k = 0; k < 12; k++) r.l[k] = w[k];
   r.l[12] = 0;
-  B381_TB(r.mag = 9.9; r.lb = 0.0; r.nonneg = true;)     // any 384-bit integer
+  B381_SETRANGE(r, 0.0, 9.9);     // any 384-bit integer
 }
 
 // canonical words -> 12 x u32

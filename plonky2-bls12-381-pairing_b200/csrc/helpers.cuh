@@ -51,7 +51,7 @@ B381_DEV B381_INL void fp_plain(Fp& r, const Fp& a) {
   Fp one;
   fp_zero(one);
   one.l[0] = 1;
-  B381_TB(one.mag = 1e-30; one.lb = 0;)
+  B381_SETRANGE(one, 0.0, 1e-30);
   fp_mul(r, a, one);
   fp_canon_small(r);
 }
@@ -333,7 +333,7 @@ B381_DEV B381_INL void fp_four(Fp& r) {
   Fp x;
   fp_zero(x);
   x.l[0] = 4;
-  B381_TB(x.mag = 1e-30; x.lb = 0;)
+  B381_SETRANGE(x, 0.0, 1e-30);
   fp_from_plain(r, x);
 }
 

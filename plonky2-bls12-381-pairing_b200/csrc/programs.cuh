@@ -48,7 +48,7 @@ B381_DEV B381_INL void f12_load_raw(const Ctx& cx, int f, const uint32_t* src) {
   for (int i = 0; i < 6; i++) {
     Fp c0, c1;
     for (int k = 0; k < NL; k++) { c0.l[k] = (limb_t)src[28 * i + k]; c1.l[k] = (limb_t)src[28 * i + NL + k]; }
-    B381_TB(c0.mag = c1.mag = 40.0; c0.lb = c1.lb = 1.0; c0.nonneg = c1.nonneg = true;)
+    B381_SETRANGE(c0, 0.0, 5.0); B381_SETRANGE(c1, 0.0, 5.0);     // raw values are stored values
     st_f2(S_(f + i), c0, c1);
   }
 }

@@ -147,7 +147,7 @@ inline std::unordered_map<const void*, TrackEnt>& track_tab() { static std::unor
 inline void track_ld(const u4* p, int h, Fp& a) {
   auto it = track_tab().find(p);
 #if B381_FMT == 32
-  if (it == track_tab().end()) { a.mag = 1.0; a.lb = 0.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
+  if (it == track_tab().end()) tb_range(a, 0.0, 1.0); else tb_range(a, it->second.lb[h], it->second.mag[h]);
 #else
   if (it == track_tab().end()) { a.mag = 1.0; a.lb = 1.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
 #endif
@@ -161,7 +161,11 @@ inline void track_st(const u4* p, int h, const Fp& a) {
 #endif
   B381_CHECK(a.mag < 1000.0, "store of oversized value");
   auto& e = track_tab()[p];
+#if B381_FMT == 32
+  e.mag[h] = a.ub; e.lb[h] = a.lb;
+#else
   e.mag[h] = a.mag; e.lb[h] = a.lb;
+#endif
 }
 #endif
 
@@ -271,23 +275,40 @@ static const ConstTab g_ct = B381_CONST_INIT;
 B381_DEV B381_INL void fp_const(Fp& r, const limb_t* v) {
 #pragma unroll
   for (int k = 0; k < NL; k++) r.l[k] = v[k];
-  B381_TB(r.mag = 1.0; r.lb = 1.0; r.nonneg = true;)
+  B381_SETRANGE(r, 0.0, 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------
 // register-level Fp2 helpers
 // ---------------------------------------------------------------------------------------------
 #if B381_FMT == 32
+// B381_W12 (default): the hot primitives multiply 12-word operands (144 instead of 169 IMAD.WIDE per
+// product).  Every value they load is a stored value below 5 p and every in-register sum / offset
+// difference stays below 2^384 = 9.84 p; the bound tracker asserts it at each multiplication.
+#ifndef B381_W12
+#define B381_W12 1
+#endif
+#if B381_W12
+#define HOT_MUL acc_mul12
+#define HOT_MAC acc_mac12
+#define HOT_MUL3 acc_mul3_12
+#define HOT_OFF fp_add_p5
+#else
+#define HOT_MUL acc_mul
+#define HOT_MAC acc_mac
+#define HOT_MUL3 acc_mul3
+#define HOT_OFF fp_add_p128
+#endif
 // (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba in the double-width domain, one reduction per
 // coefficient: 3 x 169 + 2 x 156 IMAD.WIDE.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
 B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
   Acc A, B, X;
   Fp sa, sb;
-  acc_mul(A, a0, b0);
-  acc_mul(B, a1, b1);
+  HOT_MUL(A, a0, b0);
+  HOT_MUL(B, a1, b1);
   fp_add(sa, a0, a1);
   fp_add(sb, b0, b1);
-  acc_mul(X, sa, sb);
+  HOT_MUL(X, sa, sb);
   acc_sub(X, X, A);
   acc_sub(X, X, B);                                 // im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
   B381_TB(X.cb = 0;)                                // = a0 b1 + a1 b0 >= 0 for non-negative operands
@@ -301,19 +322,19 @@ B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
   Fp s, d, t;
   fp_add(s, a0, a1);
   fp_sub(d, a0, a1);
-  fp_add_p128(d, d);                                // a0 - a1 + 128 p >= 0 (same residue)
+  HOT_OFF(d, d);                                // a0 - a1 + 128 p >= 0 (same residue)
   fp_dbl(t, a0);
   Acc T, U;
-  acc_mul(T, s, d);
-  acc_mul(U, t, a1);
+  HOT_MUL(T, s, d);
+  HOT_MUL(U, t, a1);
   acc_redc2(r0, T, r1, U);
 }
 
 // (a0 s, a1 s) for an Fp scalar s
 B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& s) {
   Acc T, U;
-  acc_mul(T, a0, s);
-  acc_mul(U, a1, s);
+  HOT_MUL(T, a0, s);
+  HOT_MUL(U, a1, s);
   acc_redc2(r0, T, r1, U);
 }
 #else
@@ -413,6 +434,9 @@ B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u
     ld_f2(t0, t1, a2);
     fp_add(a0, a0, t0); fp_add(a1, a1, t1);
     f2_norm(a0, a1);
+#if B381_FMT == 32 && B381_W12
+    fp_wreduce(a0); fp_wreduce(a1);
+#endif
   }
   ld_f2(b0, b1, b);
   if (b2) {
@@ -420,6 +444,9 @@ B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u
     ld_f2(t0, t1, b2);
     fp_add(b0, b0, t0); fp_add(b1, b1, t1);
     f2_norm(b0, b1);
+#if B381_FMT == 32 && B381_W12
+    fp_wreduce(b0); fp_wreduce(b1);
+#endif
   }
   f2_mul_reg(r0, r1, a0, a1, b0, b1);
   st_f2(r, r0, r1);
@@ -445,12 +472,12 @@ B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p
   ld_f2(y0, y1, a1p); ld_f2(v0, v1, b1p);
   ld_f2(z0, z1, a2p); ld_f2(w0, w1, b2p);
   Acc P, Q, X;
-  acc_mul3(P, x0, u0, y0, v0, z0, w0);
-  acc_mul3(Q, x1, u1, y1, v1, z1, w1);
+  HOT_MUL3(P, x0, u0, y0, v0, z0, w0);
+  HOT_MUL3(Q, x1, u1, y1, v1, z1, w1);
   fp_add(x0, x0, x1); fp_add(u0, u0, u1);
   fp_add(y0, y0, y1); fp_add(v0, v0, v1);
   fp_add(z0, z0, z1); fp_add(w0, w0, w1);
-  acc_mul3(X, x0, u0, y0, v0, z0, w0);
+  HOT_MUL3(X, x0, u0, y0, v0, z0, w0);
   acc_sub(X, X, P);
   acc_sub(X, X, Q);                                 // im = sum (a_i0 b_i1 + a_i1 b_i0) >= 0
   B381_TB(X.cb = 0;)
@@ -510,6 +537,9 @@ B381_NOINL void f2_sqr(u4* r, const u4* a, const u4* a2) {
     ld_f2(t0, t1, a2);
     fp_add(a0, a0, t0); fp_add(a1, a1, t1);
     f2_norm(a0, a1);
+#if B381_FMT == 32 && B381_W12
+    fp_wreduce(a0); fp_wreduce(a1);                 // a sum of two stored values may exceed what the 12-word squaring takes
+#endif
   }
   f2_sqr_reg(r0, r1, a0, a1);
   st_f2(r, r0, r1);
@@ -531,7 +561,7 @@ B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
   if (conj) {
     fp_neg(a1, a1); fp_norm(a1);
 #if B381_FMT == 32
-    fp_add_p128(a1, a1);
+    HOT_OFF(a1, a1);                                // -a1 + 5 p (or 128 p): non-negative, same residue
 #endif
   }
   fp_const(g0, g_ct.frob[k - 1][j - 1][0]);
@@ -639,8 +669,10 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
   }
 #if B381_FMT == 32
   // stored values must be non-negative: the weak reduction (output in [0, 11 p)) where a difference occurs
-  const bool n0 = op == L_SUB || op == L_NEG || op == L_MULXI || op == L_XIADD || op == L_3A_M2B || op == L_3A_P2B || op == L_MUL12XI || op == L_2A_MB;
-  const bool n1 = op == L_SUB || op == L_NEG || op == L_CONJ || op == L_3A_M2B || op == L_3A_P2B || op == L_2A_MB;
+  // ... and (B381_W12) wherever the result could exceed 5 p, so that it fits the 12-word multiplications
+  const bool grow = B381_W12 && (op == L_TRIPLE || op == L_MUL4 || op == L_MUL8 || op == L_MUL12XI || op == L_XIADD);
+  const bool n0 = grow || op == L_SUB || op == L_NEG || op == L_MULXI || op == L_XIADD || op == L_3A_M2B || op == L_3A_P2B || op == L_MUL12XI || op == L_2A_MB;
+  const bool n1 = grow || op == L_SUB || op == L_NEG || op == L_CONJ || op == L_3A_M2B || op == L_3A_P2B || op == L_2A_MB;
   if (n0) fp_wreduce(r0);
   if (n1) fp_wreduce(r1);
 #else
@@ -698,16 +730,16 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
     // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
     Fp s, d, e;
     Acc X, Y, U;
-    fp_add(s, b0, b1); fp_sub(d, b0, b1); fp_add_p128(d, d);
-    acc_mul(X, s, d);                               // PB
+    fp_add(s, b0, b1); fp_sub(d, b0, b1); HOT_OFF(d, d);
+    HOT_MUL(X, s, d);                               // PB
     fp_dbl(e, b0);
-    acc_mul(U, e, b1);                              // QB
+    HOT_MUL(U, e, b1);                              // QB
     acc_add(Y, X, U);                               // PB + QB
     acc_sub(X, X, U);                               // PB - QB
-    fp_add(s, a0, a1); fp_sub(d, a0, a1); fp_add_p128(d, d);
-    acc_mac(X, s, d);                               // + PA
+    fp_add(s, a0, a1); fp_sub(d, a0, a1); HOT_OFF(d, d);
+    HOT_MAC(X, s, d);                               // + PA
     fp_dbl(e, a0);
-    acc_mac(Y, e, a1);                              // + QA
+    HOT_MAC(Y, e, a1);                              // + QA
     acc_redc2(t00, X, t01, Y);
   }
   // In this format every output goes through the weak reduction (it also makes the value
@@ -793,7 +825,7 @@ B381_NOINL void f2_set_small(u4* r, int one) {
   Fp c0, c1;
   fp_zero(c0); fp_zero(c1);
   if (one) fp_const(c0, g_ct.one);
-  B381_TB(c0.lb = 1; c1.lb = 1; c0.mag = 1; c1.mag = 1; c0.nonneg = c1.nonneg = true;)
+  B381_SETRANGE(c0, 0.0, 1.0); B381_SETRANGE(c1, 0.0, 1.0);
   st_f2(r, c0, c1);
 }
 
@@ -810,7 +842,7 @@ B381_NOINL void f2_override_if(u4* r, int cond, int one) {
     c0.l[i] = cond ? k0.l[i] : c0.l[i];
     c1.l[i] = cond ? k1.l[i] : c1.l[i];
   }
-  B381_TB(if (cond) { c0.mag = c1.mag = 1; c0.lb = c1.lb = 1; c0.nonneg = c1.nonneg = true; })
+  if (cond) { B381_SETRANGE(c0, 0.0, 1.0); B381_SETRANGE(c1, 0.0, 1.0); }
   st_f2(r, c0, c1);
 }
 
