@@ -303,8 +303,9 @@ def main():
                 "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
                         "peak = fused IMAD.WIDE.U32 rate measured live by b381_imad_peak (faster of two register allocations of the same "
                         "128-multiply loop body, SASS-checked; 32 IMAD.WIDE/clk/SM at %.0f MHz -- bench lines up to commit 357fec7 divided by a probe "
-                        "that ptxas had strength-reduced to IADD3 chains, i.e. by twice the real multiplier peak); the kernel executes 325 "
-                        "IMAD.WIDE per Fp mul (13 x 13 words + 13 x 12 reduction), i.e. multiplier-pipe busy fraction = frac x 1.08; "
+                        "that ptxas had strength-reduced to IADD3 chains, i.e. by twice the real multiplier peak); the hot primitives execute 300 "
+                        "IMAD.WIDE per Fp mul (12 x 12 words + 13 x 12 reduction) = the algorithmic count; weak reductions and the 13-word "
+                        "generic paths come on top; "
                         "HBM traffic is 864 B per pairing" % (FP_MULS_PAIRING, MACS_PER_FP_MUL, mhz.value)}
 
     cpu = None

@@ -137,6 +137,10 @@ int b381_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t
 int b381_g1_serialize(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
 int b381_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n);
 int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
+/* out[i] = 1 iff [r] P_i is the identity (r = x^4 - x^2 + 1, decimal at src/miller_loop_native_optimized.rs:110):
+   the check untrusted, deserialised points need before they are paired.  Points must be on the curve. */
+int b381_g1_in_subgroup(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n);
+int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n);
 
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);

@@ -244,6 +244,21 @@ k_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out, size_t n, u4*
   }
 }
 
+// subgroup membership [r] P == infinity: uniform ladder, data-dependent cases inside the group law -> no lock step
+__global__ void __launch_bounds__(BLOCK, 1)
+k_subgroup(const uint32_t* pts, const uint8_t* inf, int is_g2, uint32_t* out_words, size_t n, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena, 0);
+  const int w = is_g2 ? 48 : 24;
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) {
+      uint8_t r = 0;
+      report(prog_subgroup_check(cx, pts + (size_t)w * i, is_g2, inf ? inf[i] : 0, &r), err);
+      out_words[i] = r;
+    }
+  }
+}
+
 __global__ void k_fill_one_ext(uint32_t* out144) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const uint32_t one[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
@@ -781,7 +796,7 @@ int b381_init(int device) {
   int rc;
   if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
       (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)))
+      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)))
     return rc;
   CU(cudaDeviceSynchronize());
   g.launches = 0;
@@ -1254,6 +1269,30 @@ int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, ui
   if (!g2 || !out || n == 0) return fail_arg("b381_g2_serialize: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return wire_host(W_G2_SER, g2, inf, compressed ? 1 : 0, reinterpret_cast<uint32_t*>(out), n, 48, compressed ? 24 : 48);
+}
+
+static int subgroup_host(const uint32_t* pts, const uint8_t* inf, int is_g2, uint8_t* out, size_t n) {
+  std::vector<uint32_t> tmp(n);
+  int rc = host_binary(pts, (const uint32_t*)nullptr, tmp.data(), n, is_g2 ? 48 : 24, 0, 1, CHUNK,
+                       [is_g2](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                         k_subgroup<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, g.cur_inf, is_g2, o, m, g.garena[lane], g.d_err);
+                         g.launches++;
+                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_subgroup");
+                       }, inf);
+  for (size_t i = 0; i < n; i++) out[i] = (uint8_t)tmp[i];
+  return rc;
+}
+int b381_g1_in_subgroup(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!g1 || !out || n == 0) return fail_arg("b381_g1_in_subgroup: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return subgroup_host(g1, inf, 0, out, n);
+}
+int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n) {
+  REQUIRE_INIT();
+  if (!g2 || !out || n == 0) return fail_arg("b381_g2_in_subgroup: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return subgroup_host(g2, inf, 1, out, n);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

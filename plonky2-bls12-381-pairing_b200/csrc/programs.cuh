@@ -318,6 +318,37 @@ B381_DEV B381_INL int prog_literal(const Ctx& cx, const uint32_t* g1p, const uin
   return err;
 }
 
+// ---- subgroup membership: [r] P == infinity, r the 255-bit group order -----------
+// The scalar is public and shared by the whole batch, so the double-and-add ladder has uniform
+// control flow apart from the identity / equal-point cases inside the Jacobian formulas (ark-ec
+// short-Weierstrass Jacobian add / double, tower.cuh jac_add / jac_double).  G1 points are embedded in
+// Fq2 (imaginary parts zero): the curve y^2 = x^3 + 4 and the formulas are the same over the subfield.
+// pt: affine x, y in the C-ABI layout (G1: 24 words, G2: 48 words).  out: 1 = in the subgroup.
+B381_DEV B381_INL int prog_subgroup_check(const Ctx& cx, const uint32_t* pt, int is_g2, int inf, uint8_t* out) {
+  int err = 0;
+  if (inf & 1) { *out = 1; return 0; }              // the identity is in every subgroup
+  const int Q = 0, R = 3, T = 6;                    // Q (affine, Z = 1), accumulator R, 9 scratch slots
+  if (is_g2) {
+    if (!f2_load_ext(S_(Q), pt)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
+  } else {
+    uint32_t w[24];
+    for (int c = 0; c < 2; c++) {
+      for (int k = 0; k < 12; k++) { w[k] = pt[12 * c + k]; w[12 + k] = 0; }
+      if (!f2_load_ext(S_(Q + c), w)) err |= ERR_NOT_CANONICAL;
+    }
+  }
+  f2_set_small(S_(Q + 2), 1);
+  for (int k = 0; k < 3; k++) lin(cx, R + k, Q + k, -1, L_COPY);
+  const uint64_t rw[4] = B381_R_ORDER_U64;          // little-endian limbs of r; bit 254 is the leading one
+  for (int b = 253; b >= 0; b--) {
+    jac_double(cx, R, T);
+    if ((rw[b >> 6] >> (b & 63)) & 1) jac_add(cx, R, Q, T);
+  }
+  *out = f2_is_zero(S_(R + 2)) ? 1 : 0;
+  return err;
+}
+
 #undef S_
 
 }  // namespace b381

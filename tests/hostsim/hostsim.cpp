@@ -157,6 +157,8 @@ int hs_g2_serialize(const uint32_t* g2, int inf, int compressed, uint8_t* out) {
 int hs_fp12_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_inv(cx, a, out); }
 int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f6_inv(cx, a, out); }
 
+int hs_subgroup_check(const uint32_t* pt, int is_g2, int inf, uint8_t* out) { Ctx cx = make_ctx(); return prog_subgroup_check(cx, pt, is_g2, inf, out); }
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

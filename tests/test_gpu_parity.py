@@ -548,3 +548,36 @@ def test_wire_formats_batched(L, lib, z):
         x += 1
     bb = np.frombuffer(bytes([0x80]) + x.to_bytes(47, "big"), dtype=np.uint8).copy()
     assert lib.b381_g1_deserialize(u8(bb), 1, L.u32(d1)[1], u8(i1), 1) == -6
+
+
+def test_subgroup_check_batched(L, lib, z):
+    """b381_g1_in_subgroup / b381_g2_in_subgroup: the fixture points are in the subgroups, curve points
+    decompressed from small x are (almost surely) not -- expectation from the oracle's scalar multiplication."""
+    u8 = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    m = 300
+    idx = np.arange(m) % 256
+    g1 = np.ascontiguousarray(z["g1"][idx]).reshape(-1).copy()
+    g2 = np.ascontiguousarray(z["g2"][idx]).reshape(-1).copy()
+    want1 = np.ones(m, dtype=np.uint8); want2 = np.ones(m, dtype=np.uint8)
+    x, put = 1, 0
+    while put < 3:
+        res = o.g1_deserialize(bytes([0x80]) + x.to_bytes(47, "big"), True)
+        if res[0] == "ok":
+            g1[24 * (10 + put):24 * (11 + put)] = o.g1_to_limbs32(res[1])
+            want1[10 + put] = 1 if o.g1_mul(res[1], o.R_ORDER) is None else 0
+            put += 1
+        x += 1
+    x, put = 1, 0
+    while put < 2:
+        res = o.g2_deserialize(bytes([0x80]) + bytes(47) + x.to_bytes(48, "big"), True)
+        if res[0] == "ok":
+            g2[48 * (20 + put):48 * (21 + put)] = o.g2_to_limbs32(res[1])
+            want2[20 + put] = 1 if o.g2_mul(res[1], o.R_ORDER) is None else 0
+            put += 1
+        x += 1
+    inf = np.zeros(m, dtype=np.uint8); inf[299] = 1
+    o1 = np.zeros(m, dtype=np.uint8); o2 = np.zeros(m, dtype=np.uint8)
+    L.check(lib.b381_g1_in_subgroup(L.u32(g1)[1], u8(inf), u8(o1), m))
+    L.check(lib.b381_g2_in_subgroup(L.u32(g2)[1], u8(inf), u8(o2), m))
+    assert np.array_equal(o1, want1) and np.array_equal(o2, want2)
+    assert want1[10:13].min() == 0 and want2[20:22].min() == 0

@@ -318,3 +318,34 @@ def test_wire_formats(hs):
     g2 = u(48)
     unc = bytearray(o.g2_serialize(o.G2_GEN, False)); unc[191] ^= 1
     assert hs.hs_g2_deserialize(B(bytes(unc)), 0, g2, inf) & 4
+
+
+def test_subgroup_check(hs):
+    """[r] P == infinity on the host simulation: subgroup points, curve points outside the subgroup
+    (found by decompressing small x), the identity flag; G1 (embedded in Fq2) and G2."""
+    b = (ctypes.c_uint8 * 1)()
+    r = util.rng(35)
+    for _ in range(2):
+        P1 = o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER))
+        Q = o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER))
+        assert hs.hs_subgroup_check(A(o.g1_to_limbs32(P1)), 0, 0, b) == 0 and b[0] == 1
+        assert hs.hs_subgroup_check(A(o.g2_to_limbs32(Q)), 1, 0, b) == 0 and b[0] == 1
+    x = 1
+    found = 0
+    while found < 2:
+        res = o.g1_deserialize(bytes([0x80]) + x.to_bytes(47, "big"), True)
+        if res[0] == "ok":
+            want = o.g1_mul(res[1], o.R_ORDER) is None
+            assert hs.hs_subgroup_check(A(o.g1_to_limbs32(res[1])), 0, 0, b) == 0 and bool(b[0]) == want
+            found += 0 if want else 1
+        x += 1
+    x = 1
+    while True:
+        res = o.g2_deserialize(bytes([0x80]) + bytes(47) + x.to_bytes(48, "big"), True)
+        if res[0] == "ok":
+            want = o.g2_mul(res[1], o.R_ORDER) is None
+            assert hs.hs_subgroup_check(A(o.g2_to_limbs32(res[1])), 1, 0, b) == 0 and bool(b[0]) == want
+            if not want:
+                break
+        x += 1
+    assert hs.hs_subgroup_check(A([0] * 24), 0, 1, b) == 0 and b[0] == 1
