@@ -141,6 +141,12 @@ int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, ui
    the check untrusted, deserialised points need before they are paired.  Points must be on the curve. */
 int b381_g1_in_subgroup(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n);
 int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n);
+/* out[i] = [k_i] P_i (affine, + identity flag), k_i = 256-bit scalar as 8 little-endian u32 words; the group
+   law is the ark-ec Jacobian add / double the reference's native loop uses (`R + R`, `R + Q`,
+   src/miller_loop_native_optimized.rs:93,98).  Generates (a_i G1, b_i G2) test points and aggregates keys
+   on the device.  Not constant time. */
+int b381_g1_scalar_mul(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
+int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
 
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);

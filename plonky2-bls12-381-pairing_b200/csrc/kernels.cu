@@ -259,6 +259,21 @@ k_subgroup(const uint32_t* pts, const uint8_t* inf, int is_g2, uint32_t* out_wor
   }
 }
 
+// [k_i] P_i with per-element 256-bit scalars: divergent control flow -> no lock step
+__global__ void __launch_bounds__(BLOCK, 1)
+k_scalar_mul(const uint32_t* pts, const uint32_t* scalars, const uint8_t* inf, int is_g2, uint32_t* out, size_t n, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena, 0);
+  const int w = is_g2 ? 48 : 24;
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+    size_t i = base + threadIdx.x;
+    if (i < n) {
+      uint8_t f = 0;
+      report(prog_scalar_mul(cx, pts + (size_t)w * i, is_g2, inf ? inf[i] : 0, scalars + 8 * i, out + (size_t)(w + 1) * i, &f), err);
+      out[(size_t)(w + 1) * i + w] = f;
+    }
+  }
+}
+
 __global__ void k_fill_one_ext(uint32_t* out144) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const uint32_t one[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
@@ -796,7 +811,7 @@ int b381_init(int device) {
   int rc;
   if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
       (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)))
+      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)) || (rc = set_smem(k_scalar_mul)))
     return rc;
   CU(cudaDeviceSynchronize());
   g.launches = 0;
@@ -1293,6 +1308,34 @@ int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, si
   if (!g2 || !out || n == 0) return fail_arg("b381_g2_in_subgroup: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return subgroup_host(g2, inf, 1, out, n);
+}
+
+static int scalar_mul_host(const uint32_t* pts, const uint32_t* scalars, const uint8_t* inf, int is_g2, uint32_t* out, uint8_t* out_inf, size_t n) {
+  const size_t w = is_g2 ? 48 : 24;
+  std::vector<uint32_t> tmp(n * (w + 1));
+  int rc = host_binary(pts, scalars, tmp.data(), n, w, 8, w + 1, CHUNK,
+                       [is_g2](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
+                         k_scalar_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, g.cur_inf, is_g2, o, m, g.garena[lane], g.d_err);
+                         g.launches++;
+                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_scalar_mul");
+                       }, inf);
+  for (size_t i = 0; i < n; i++) {
+    memcpy(out + w * i, tmp.data() + (w + 1) * i, w * 4);
+    if (out_inf) out_inf[i] = (uint8_t)tmp[(w + 1) * i + w];
+  }
+  return rc;
+}
+int b381_g1_scalar_mul(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g1 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g1_scalar_mul: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return scalar_mul_host(g1, scalars, inf, 0, out, out_inf, n);
+}
+int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g2 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g2_scalar_mul: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return scalar_mul_host(g2, scalars, inf, 1, out, out_inf, n);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

@@ -349,6 +349,67 @@ B381_DEV B381_INL int prog_subgroup_check(const Ctx& cx, const uint32_t* pt, int
   return err;
 }
 
+// ---- scalar multiplication (first half): out = [k] P, k = 256-bit scalar (8 LE words) ----
+// Left-to-right double-and-add over the Jacobian group law the reference's native loop already uses
+// (`R + R`, `R + Q` at /root/reference/src/miller_loop_native_optimized.rs:93,98 = ark-ec Projective add /
+// double, tower.cuh jac_add / jac_double), then one inversion back to affine.  Per-thread scalars:
+// control flow diverges, so the kernel runs without the lock-step barriers.  Not constant time.
+B381_DEV B381_INL int prog_scalar_mul(const Ctx& cx, const uint32_t* pt, int is_g2, int inf, const uint32_t* k, uint32_t* out, uint8_t* out_inf) {
+  int err = 0;
+  const int Q = 0, R = 3, T = 6, ZI = 15, ZI2 = 16;
+  const int w = is_g2 ? 48 : 24;
+  uint32_t kk[8], nz = 0;
+  for (int i = 0; i < 8; i++) { kk[i] = k[i]; nz |= kk[i]; }
+  if ((inf & 1) || nz == 0) {
+    for (int i = 0; i < w; i++) out[i] = 0;
+    *out_inf = 1;
+    return 0;
+  }
+  if (is_g2) {
+    if (!f2_load_ext(S_(Q), pt)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
+  } else {
+    uint32_t wd[24];
+    for (int c = 0; c < 2; c++) {
+      for (int j = 0; j < 12; j++) { wd[j] = pt[12 * c + j]; wd[12 + j] = 0; }
+      if (!f2_load_ext(S_(Q + c), wd)) err |= ERR_NOT_CANONICAL;
+    }
+  }
+  f2_set_small(S_(Q + 2), 1);
+  f2_set_small(S_(R), 0); f2_set_small(S_(R + 1), 1); f2_set_small(S_(R + 2), 0);     // identity (Z = 0)
+  bool started = false;
+  for (int b = 255; b >= 0; b--) {
+    const bool bit = (kk[b >> 5] >> (b & 31)) & 1u;
+    if (started) jac_double(cx, R, T);
+    if (bit) {
+      if (started) jac_add(cx, R, Q, T);
+      else { for (int c = 0; c < 3; c++) lin(cx, R + c, Q + c, -1, L_COPY); started = true; }
+    }
+  }
+  if (f2_is_zero(S_(R + 2))) {
+    for (int i = 0; i < w; i++) out[i] = 0;
+    *out_inf = 1;
+    return err;
+  }
+  *out_inf = 0;
+  f2_inv(S_(ZI), S_(R + 2));                                       // affine: (X / Z^2, Y / Z^3)
+  sqr(cx, ZI2, ZI);
+  mul(cx, R, R, ZI2);
+  mul(cx, ZI2, ZI2, ZI);
+  mul(cx, R + 1, R + 1, ZI2);
+  if (is_g2) {
+    f2_store_ext(out, S_(R));
+    f2_store_ext(out + 24, S_(R + 1));
+  } else {
+    uint32_t wd[24];
+    f2_store_ext(wd, S_(R));
+    for (int j = 0; j < 12; j++) out[j] = wd[j];
+    f2_store_ext(wd, S_(R + 1));
+    for (int j = 0; j < 12; j++) out[12 + j] = wd[j];
+  }
+  return err;
+}
+
 #undef S_
 
 }  // namespace b381

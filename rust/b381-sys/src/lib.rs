@@ -60,6 +60,8 @@ extern "C" {
     pub fn b381_g2_serialize(g2: *const u32, inf: *const u8, compressed: c_int, out: *mut u8, n: usize) -> c_int;
     pub fn b381_g1_in_subgroup(g1: *const u32, inf: *const u8, out: *mut u8, n: usize) -> c_int;
     pub fn b381_g2_in_subgroup(g2: *const u32, inf: *const u8, out: *mut u8, n: usize) -> c_int;
+    pub fn b381_g1_scalar_mul(g1: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
+    pub fn b381_g2_scalar_mul(g2: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
     pub fn b381_g2_prepare(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_miller_loop_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_pairing_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;

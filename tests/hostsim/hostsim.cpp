@@ -159,6 +159,11 @@ int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); retu
 
 int hs_subgroup_check(const uint32_t* pt, int is_g2, int inf, uint8_t* out) { Ctx cx = make_ctx(); return prog_subgroup_check(cx, pt, is_g2, inf, out); }
 
+int hs_scalar_mul(const uint32_t* pt, int is_g2, int inf, const uint32_t* k, uint32_t* out, uint8_t* out_inf) {
+  Ctx cx = make_ctx();
+  return prog_scalar_mul(cx, pt, is_g2, inf, k, out, out_inf);
+}
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

@@ -581,3 +581,33 @@ def test_subgroup_check_batched(L, lib, z):
     L.check(lib.b381_g2_in_subgroup(L.u32(g2)[1], u8(inf), u8(o2), m))
     assert np.array_equal(o1, want1) and np.array_equal(o2, want2)
     assert want1[10:13].min() == 0 and want2[20:22].min() == 0
+
+
+def test_scalar_mul_batched(L, lib, z):
+    """b381_g1_scalar_mul / b381_g2_scalar_mul with per-element scalars against the oracle; the products
+    feed the pairing: e([a] P, [b] Q) computed on the device equals e(P, Q)^(ab) (bilinearity)."""
+    u8 = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    r = util.rng(99)
+    m = 300
+    ks = [1, 2, o.R_ORDER - 1, o.R_ORDER] + [r.randrange(1, 1 << 256) for _ in range(m - 4)]
+    sc = np.array([[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for k in ks], dtype=np.uint32).reshape(-1)
+    g1 = np.tile(np.array(o.g1_to_limbs32(o.G1_GEN), dtype=np.uint32), m)
+    g2 = np.tile(np.array(o.g2_to_limbs32(o.G2_GEN), dtype=np.uint32), m)
+    o1 = np.zeros(m * 24, dtype=np.uint32); o2 = np.zeros(m * 48, dtype=np.uint32)
+    i1 = np.zeros(m, dtype=np.uint8); i2 = np.zeros(m, dtype=np.uint8)
+    L.check(lib.b381_g1_scalar_mul(L.u32(g1)[1], None, L.u32(sc)[1], L.u32(o1)[1], u8(i1), m))
+    L.check(lib.b381_g2_scalar_mul(L.u32(g2)[1], None, L.u32(sc)[1], L.u32(o2)[1], u8(i2), m))
+    for i in (0, 1, 2, 3, 4, 150, 299):
+        w1, w2 = o.g1_mul(o.G1_GEN, ks[i]), o.g2_mul(o.G2_GEN, ks[i])
+        assert (i1[i] == 1 and w1 is None) or (i1[i] == 0 and o1[24 * i:24 * i + 24].tolist() == o.g1_to_limbs32(w1)), i
+        assert (i2[i] == 1 and w2 is None) or (i2[i] == 0 and o2[48 * i:48 * i + 48].tolist() == o.g2_to_limbs32(w2)), i
+    assert i1[3] == 1 and i2[3] == 1 and i1.sum() == 1
+    # bilinearity through the device: e([a]G1, [b]G2) == e([ab]G1, G2)
+    a, b = ks[10] % o.R_ORDER, ks[11] % o.R_ORDER
+    ab = np.array([(a * b % o.R_ORDER >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+    pab = np.zeros(24, dtype=np.uint32); iab = np.zeros(1, dtype=np.uint8)
+    L.check(lib.b381_g1_scalar_mul(L.u32(g1[:24])[1], None, L.u32(ab)[1], L.u32(pab)[1], u8(iab), 1))
+    e1 = np.zeros(144, dtype=np.uint32); e2 = np.zeros(144, dtype=np.uint32)
+    L.check(lib.b381_pairing(L.u32(o1[240:264])[1], L.u32(o2[48 * 11:48 * 12])[1], None, L.u32(e1)[1], 1, L.MODE_ARK))
+    L.check(lib.b381_pairing(L.u32(pab)[1], L.u32(g2[:48])[1], None, L.u32(e2)[1], 1, L.MODE_ARK))
+    assert np.array_equal(e1, e2)

@@ -349,3 +349,22 @@ def test_subgroup_check(hs):
                 break
         x += 1
     assert hs.hs_subgroup_check(A([0] * 24), 0, 1, b) == 0 and b[0] == 1
+
+
+def test_scalar_mul(hs):
+    """[k] P on the host simulation against the oracle: small, order-related and random 256-bit scalars."""
+    b = (ctypes.c_uint8 * 1)()
+    r = util.rng(36)
+    base1 = o.g1_mul(o.G1_GEN, 7)
+    base2 = o.g2_mul(o.G2_GEN, 11)
+    for k in [1, 2, 3, o.R_ORDER - 1, o.R_ORDER, o.R_ORDER + 5, r.randrange(1, 1 << 255), (1 << 256) - 1]:
+        kw = A([(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+        o1, o2 = u(24), u(48)
+        assert hs.hs_scalar_mul(A(o.g1_to_limbs32(base1)), 0, 0, kw, o1, b) == 0
+        w = o.g1_mul(base1, k)
+        assert (b[0] == 1 and w is None) or (b[0] == 0 and list(o1) == o.g1_to_limbs32(w)), k
+        assert hs.hs_scalar_mul(A(o.g2_to_limbs32(base2)), 1, 0, kw, o2, b) == 0
+        w = o.g2_mul(base2, k)
+        assert (b[0] == 1 and w is None) or (b[0] == 0 and list(o2) == o.g2_to_limbs32(w)), k
+    assert hs.hs_scalar_mul(A(o.g1_to_limbs32(base1)), 0, 0, A([0] * 8), u(24), b) == 0 and b[0] == 1
+    assert hs.hs_scalar_mul(A(o.g1_to_limbs32(base1)), 0, 1, A([5] + [0] * 7), u(24), b) == 0 and b[0] == 1
