@@ -502,6 +502,13 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
 
 B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
   B381_CHECK(t0.mag < ACC_MAG_MAX && t1.mag < ACC_MAG_MAX, "acc_redc2: input too large");
+#ifdef B381_REDC2_SEQ
+  acc_redc_rows<NL>(r0, t0);
+  acc_redc_rows<NL>(r1, t1);
+  B381_SETRANGE(r0, t0.cb < 0 ? t0.cb / 4.2e10 : 0.0, 1.0 + t0.mag / 4.2e10 + 1e-9);
+  B381_SETRANGE(r1, t1.cb < 0 ? t1.cb / 4.2e10 : 0.0, 1.0 + t1.mag / 4.2e10 + 1e-9);
+  return;
+#endif
   B381_CC_DECL;
   constexpr int ROWS = NL;
   uint32_t A0[14], B0[14], A1[14], B1[14], c0 = 0, c1 = 0;
@@ -545,6 +552,13 @@ B381_HD B381_INL void fp_mul(Fp& r, const Fp& a, const Fp& b) {
   Acc t;
   B381_TB(t.mag = 0; t.cb = 0;)
   acc_mul(t, a, b);
+  acc_redc(r, t);
+}
+// both operands below 2^384 (tracker-asserted): 144 + 156 IMAD.WIDE
+B381_HD B381_INL void fp_mul12(Fp& r, const Fp& a, const Fp& b) {
+  Acc t;
+  B381_TB(t.mag = 0; t.cb = 0;)
+  acc_mul12(t, a, b);
   acc_redc(r, t);
 }
 

@@ -396,6 +396,11 @@ B381_DEV B381_INL void f2_mulxi_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) 
 
 // Fermat inversion a^(p-2), 4-bit fixed windows, table in registers is too large -> binary
 // square-and-multiply driven by the nibble table (uniform control flow across the warp).
+#if B381_FMT == 32 && B381_W12
+#define FP_MUL_SMALL fp_mul12      // x and a are reduction outputs (at most 1.03 p): 12-word products
+#else
+#define FP_MUL_SMALL fp_mul
+#endif
 B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
   Fp x;
   fp_const(x, g_ct.one);
@@ -403,10 +408,10 @@ B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
     int nib = g_ct.pm2_nib[i];
     for (int b = 3; b >= 0; b--) {
       Fp t;
-      fp_mul(t, x, x);
+      FP_MUL_SMALL(t, x, x);
       x = t;
       if ((nib >> b) & 1) {
-        fp_mul(t, x, a);
+        FP_MUL_SMALL(t, x, a);
         x = t;
       }
     }
