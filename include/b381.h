@@ -147,6 +147,13 @@ int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, si
    on the device.  Not constant time. */
 int b381_g1_scalar_mul(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
 int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
+/* ONE point out: the sum of the n points (public-key aggregation), and sum_i [k_i] P_i (multi-scalar
+   multiplication; this version is n independent scalar multiplications + a 16-ary reduction tree on the
+   device, not yet the bucket method). */
+int b381_g1_sum(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
+int b381_g2_sum(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
+int b381_g1_msm(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
+int b381_g2_msm(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
 
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only throughput) ---- */
 int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream);

@@ -73,6 +73,10 @@ SIGNATURES = {
     "b381_g2_in_subgroup": [_u32p, _u8p, _u8p, ctypes.c_size_t],
     "b381_g1_scalar_mul": [_u32p, _u8p, _u32p, _u32p, _u8p, ctypes.c_size_t],
     "b381_g2_scalar_mul": [_u32p, _u8p, _u32p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g1_sum": [_u32p, _u8p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g2_sum": [_u32p, _u8p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g1_msm": [_u32p, _u8p, _u32p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g2_msm": [_u32p, _u8p, _u32p, _u32p, _u8p, ctypes.c_size_t],
     "b381_g2_prepare": [_u32p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_miller_loop_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_pairing_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],

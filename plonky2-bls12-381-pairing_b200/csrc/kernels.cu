@@ -274,6 +274,20 @@ k_scalar_mul(const uint32_t* pts, const uint32_t* scalars, const uint8_t* inf, i
   }
 }
 
+// out[j] = sum of in[j*K .. min((j+1)K, n_in)) in the packed point layout (trip counts differ -> no lock step)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_point_sum(const uint32_t* in, size_t n_in, uint32_t* out, size_t n_out, int K, int is_g2, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena, 0);
+  const size_t w1 = (is_g2 ? 48 : 24) + 1;
+  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n_out; base += (size_t)gridDim.x * BLOCK) {
+    size_t j = base + threadIdx.x;
+    if (j < n_out) {
+      size_t lo = j * (size_t)K, hi = lo + K < n_in ? lo + K : n_in;
+      report(prog_point_sum(cx, in + lo * w1, hi - lo, is_g2, out + j * w1), err);
+    }
+  }
+}
+
 __global__ void k_fill_one_ext(uint32_t* out144) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const uint32_t one[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
@@ -811,7 +825,7 @@ int b381_init(int device) {
   int rc;
   if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
       (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)) || (rc = set_smem(k_scalar_mul)))
+      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)) || (rc = set_smem(k_scalar_mul)) || (rc = set_smem(k_point_sum)))
     return rc;
   CU(cudaDeviceSynchronize());
   g.launches = 0;
@@ -1336,6 +1350,85 @@ int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* s
   if (!g2 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g2_scalar_mul: bad argument");
   std::lock_guard<std::mutex> lk(g.mu);
   return scalar_mul_host(g2, scalars, inf, 1, out, out_inf, n);
+}
+
+// ---- point sums and the (naive) multi-scalar multiplication ---------------------------------------------
+// tree-reduce n packed points on the device (16-ary), result -> host
+static int point_tree(uint32_t* d_a, uint32_t* d_b, size_t n, int is_g2, uint32_t* out, uint8_t* out_inf) {
+  const size_t w = is_g2 ? 48 : 24;
+  cudaStream_t s = g.stream[0];
+  const int K = 16;
+  size_t cnt = n;
+  do {                                              // at least one level: it also normalises a single point
+    size_t n_out = (cnt + K - 1) / K;
+    k_point_sum<<<grid_for(n_out), BLOCK, SMEM_BYTES, s>>>(d_a, cnt, d_b, n_out, K, is_g2, g.garena[0], g.d_err);
+    g.launches++;
+    CU(cudaGetLastError());
+    uint32_t* t = d_a; d_a = d_b; d_b = t;
+    cnt = n_out;
+  } while (cnt > 1);
+  std::vector<uint32_t> res(w + 1);
+  CU(cudaMemcpyAsync(res.data(), d_a, (w + 1) * 4, cudaMemcpyDeviceToHost, s));
+  int rc = read_err(s);
+  memcpy(out, res.data(), w * 4);
+  *out_inf = (uint8_t)res[w];
+  return rc;
+}
+
+static int point_sum_host(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, int is_g2, uint32_t* out, uint8_t* out_inf, size_t n) {
+  const size_t w = is_g2 ? 48 : 24;
+  uint32_t *d_a = nullptr, *d_b = nullptr, *d_p = nullptr, *d_s = nullptr;
+  uint8_t* d_i = nullptr;
+  cudaStream_t s = g.stream[0];
+  int rc = 0;
+  CU(cudaMalloc((void**)&d_a, n * (w + 1) * 4));
+  CU(cudaMalloc((void**)&d_b, ((n + 15) / 16 + 1) * (w + 1) * 4));
+  if (scalars) {                                    // MSM: [k_i] P_i on the device, straight into the packed layout
+    CU(cudaMalloc((void**)&d_p, n * w * 4));
+    CU(cudaMalloc((void**)&d_s, n * 8 * 4));
+    CU(cudaMemcpyAsync(d_p, pts, n * w * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_s, scalars, n * 8 * 4, cudaMemcpyHostToDevice, s));
+    if (inf) { CU(cudaMalloc((void**)&d_i, n)); CU(cudaMemcpyAsync(d_i, inf, n, cudaMemcpyHostToDevice, s)); }
+    k_scalar_mul<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(d_p, d_s, d_i, is_g2, d_a, n, g.garena[0], g.d_err);
+    g.launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "k_scalar_mul");
+  } else {
+    std::vector<uint32_t> packed(n * (w + 1));
+    for (size_t i = 0; i < n; i++) {
+      memcpy(packed.data() + (w + 1) * i, pts + w * i, w * 4);
+      packed[(w + 1) * i + w] = inf ? (inf[i] & 1) : 0;
+    }
+    CU(cudaMemcpyAsync(d_a, packed.data(), n * (w + 1) * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if (!rc) rc = point_tree(d_a, d_b, n, is_g2, out, out_inf);
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_p); cudaFree(d_s); cudaFree(d_i);
+  return rc;
+}
+
+int b381_g1_sum(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g1 || !out || !out_inf || n == 0) return fail_arg("b381_g1_sum: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return point_sum_host(g1, inf, nullptr, 0, out, out_inf, n);
+}
+int b381_g2_sum(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g2 || !out || !out_inf || n == 0) return fail_arg("b381_g2_sum: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return point_sum_host(g2, inf, nullptr, 1, out, out_inf, n);
+}
+int b381_g1_msm(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g1 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g1_msm: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return point_sum_host(g1, inf, scalars, 0, out, out_inf, n);
+}
+int b381_g2_msm(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
+  REQUIRE_INIT();
+  if (!g2 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g2_msm: bad argument");
+  std::lock_guard<std::mutex> lk(g.mu);
+  return point_sum_host(g2, inf, scalars, 1, out, out_inf, n);
 }
 
 int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {

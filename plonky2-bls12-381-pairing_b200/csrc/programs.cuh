@@ -349,6 +349,69 @@ B381_DEV B381_INL int prog_subgroup_check(const Ctx& cx, const uint32_t* pt, int
   return err;
 }
 
+// Jacobian (X, Y, Z) in slots R..R+2 -> affine (X / Z^2, Y / Z^3) in the C-ABI layout + identity flag;
+// t = 2 scratch slots
+B381_DEV B381_INL void jac_store_affine(const Ctx& cx, int R, int t, int is_g2, uint32_t* out, uint8_t* out_inf) {
+  const int w = is_g2 ? 48 : 24, ZI = t, ZI2 = t + 1;
+  if (f2_is_zero(S_(R + 2))) {
+    for (int i = 0; i < w; i++) out[i] = 0;
+    *out_inf = 1;
+    return;
+  }
+  *out_inf = 0;
+  f2_inv(S_(ZI), S_(R + 2));
+  sqr(cx, ZI2, ZI);
+  mul(cx, R, R, ZI2);
+  mul(cx, ZI2, ZI2, ZI);
+  mul(cx, R + 1, R + 1, ZI2);
+  if (is_g2) {
+    f2_store_ext(out, S_(R));
+    f2_store_ext(out + 24, S_(R + 1));
+  } else {
+    uint32_t wd[24];
+    f2_store_ext(wd, S_(R));
+    for (int j = 0; j < 12; j++) out[j] = wd[j];
+    f2_store_ext(wd, S_(R + 1));
+    for (int j = 0; j < 12; j++) out[12 + j] = wd[j];
+  }
+}
+
+// affine point (C-ABI layout) -> slots Q, Q+1 with Z = 1 in Q+2; G1 coordinates are embedded in Fq2
+B381_DEV B381_INL int load_affine_point(const Ctx& cx, int Q, const uint32_t* pt, int is_g2) {
+  int err = 0;
+  if (is_g2) {
+    if (!f2_load_ext(S_(Q), pt)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
+  } else {
+    uint32_t wd[24];
+    for (int c = 0; c < 2; c++) {
+      for (int j = 0; j < 12; j++) { wd[j] = pt[12 * c + j]; wd[12 + j] = 0; }
+      if (!f2_load_ext(S_(Q + c), wd)) err |= ERR_NOT_CANONICAL;
+    }
+  }
+  f2_set_small(S_(Q + 2), 1);
+  return err;
+}
+
+// sum of cnt points in the PACKED layout (w + 1 words per point: affine coordinates, then the identity
+// flag) -> one packed point.  One level of the reduction tree behind b381_g1/g2_sum and the MSM.
+B381_DEV B381_INL int prog_point_sum(const Ctx& cx, const uint32_t* in, size_t cnt, int is_g2, uint32_t* out) {
+  int err = 0;
+  const int Q = 0, R = 3, T = 6, ZI = 15;
+  const int w = is_g2 ? 48 : 24;
+  f2_set_small(S_(R), 0); f2_set_small(S_(R + 1), 1); f2_set_small(S_(R + 2), 0);     // identity
+  for (size_t i = 0; i < cnt; i++) {
+    const uint32_t* p = in + (size_t)(w + 1) * i;
+    if (p[w] & 1) continue;
+    err |= load_affine_point(cx, Q, p, is_g2);
+    jac_add(cx, R, Q, T);
+  }
+  uint8_t f = 0;
+  jac_store_affine(cx, R, ZI, is_g2, out, &f);
+  out[w] = f;
+  return err;
+}
+
 // ---- scalar multiplication (first half): out = [k] P, k = 256-bit scalar (8 LE words) ----
 // Left-to-right double-and-add over the Jacobian group law the reference's native loop already uses
 // (`R + R`, `R + Q` at /root/reference/src/miller_loop_native_optimized.rs:93,98 = ark-ec Projective add /
@@ -386,27 +449,7 @@ B381_DEV B381_INL int prog_scalar_mul(const Ctx& cx, const uint32_t* pt, int is_
       else { for (int c = 0; c < 3; c++) lin(cx, R + c, Q + c, -1, L_COPY); started = true; }
     }
   }
-  if (f2_is_zero(S_(R + 2))) {
-    for (int i = 0; i < w; i++) out[i] = 0;
-    *out_inf = 1;
-    return err;
-  }
-  *out_inf = 0;
-  f2_inv(S_(ZI), S_(R + 2));                                       // affine: (X / Z^2, Y / Z^3)
-  sqr(cx, ZI2, ZI);
-  mul(cx, R, R, ZI2);
-  mul(cx, ZI2, ZI2, ZI);
-  mul(cx, R + 1, R + 1, ZI2);
-  if (is_g2) {
-    f2_store_ext(out, S_(R));
-    f2_store_ext(out + 24, S_(R + 1));
-  } else {
-    uint32_t wd[24];
-    f2_store_ext(wd, S_(R));
-    for (int j = 0; j < 12; j++) out[j] = wd[j];
-    f2_store_ext(wd, S_(R + 1));
-    for (int j = 0; j < 12; j++) out[12 + j] = wd[j];
-  }
+  jac_store_affine(cx, R, ZI, is_g2, out, out_inf);
   return err;
 }
 

@@ -62,6 +62,10 @@ extern "C" {
     pub fn b381_g2_in_subgroup(g2: *const u32, inf: *const u8, out: *mut u8, n: usize) -> c_int;
     pub fn b381_g1_scalar_mul(g1: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
     pub fn b381_g2_scalar_mul(g2: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
+    pub fn b381_g1_sum(g1: *const u32, inf: *const u8, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
+    pub fn b381_g2_sum(g2: *const u32, inf: *const u8, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
+    pub fn b381_g1_msm(g1: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
+    pub fn b381_g2_msm(g2: *const u32, inf: *const u8, scalars: *const u32, out: *mut u32, out_inf: *mut u8, n: usize) -> c_int;
     pub fn b381_g2_prepare(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_miller_loop_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;
     pub fn b381_pairing_prepared(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int) -> c_int;

@@ -164,6 +164,8 @@ int hs_scalar_mul(const uint32_t* pt, int is_g2, int inf, const uint32_t* k, uin
   return prog_scalar_mul(cx, pt, is_g2, inf, k, out, out_inf);
 }
 
+int hs_point_sum(const uint32_t* packed, size_t cnt, int is_g2, uint32_t* out) { Ctx cx = make_ctx(); return prog_point_sum(cx, packed, cnt, is_g2, out); }
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

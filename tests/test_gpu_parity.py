@@ -611,3 +611,47 @@ def test_scalar_mul_batched(L, lib, z):
     L.check(lib.b381_pairing(L.u32(o1[240:264])[1], L.u32(o2[48 * 11:48 * 12])[1], None, L.u32(e1)[1], 1, L.MODE_ARK))
     L.check(lib.b381_pairing(L.u32(pab)[1], L.u32(g2[:48])[1], None, L.u32(e2)[1], 1, L.MODE_ARK))
     assert np.array_equal(e1, e2)
+
+
+def test_point_sum_and_msm(L, lib, z):
+    """b381_g1/g2_sum and b381_g1/g2_msm (scalar multiplications + 16-ary reduction tree on the device)
+    against the oracle; sizes that exercise one, two and three tree levels; identity handling."""
+    u8 = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    r = util.rng(111)
+    for m in (1, 5, 17, 300):
+        idx = np.arange(m) % 256
+        g1 = np.ascontiguousarray(z["g1"][idx]).reshape(-1)
+        g2 = np.ascontiguousarray(z["g2"][idx]).reshape(-1)
+        inf = np.zeros(m, dtype=np.uint8)
+        if m > 3:
+            inf[3] = 1
+        o1 = np.zeros(24, dtype=np.uint32); o2 = np.zeros(48, dtype=np.uint32); f = np.zeros(1, dtype=np.uint8)
+        L.check(lib.b381_g1_sum(L.u32(g1)[1], u8(inf), L.u32(o1)[1], u8(f), m))
+        acc = None
+        for i in range(m):
+            if not inf[i]:
+                acc = o.g1_add(acc, (o.fp_from_limbs32(z["g1"][idx[i]][:12].tolist()), o.fp_from_limbs32(z["g1"][idx[i]][12:].tolist())))
+        assert f[0] == 0 and o1.tolist() == o.g1_to_limbs32(acc), m
+        if m <= 17:
+            L.check(lib.b381_g2_sum(L.u32(g2)[1], u8(inf), L.u32(o2)[1], u8(f), m))
+            acc2 = None
+            for i in range(m):
+                if not inf[i]:
+                    acc2 = o.g2_add(acc2, (util.f2_from_words(z["g2"][idx[i]][:24].tolist()), util.f2_from_words(z["g2"][idx[i]][24:].tolist())))
+            assert f[0] == 0 and o2.tolist() == o.g2_to_limbs32(acc2), m
+    # MSM: sum [k_i] G = [sum k_i] G
+    m = 100
+    ks = [r.randrange(1, 1 << 256) for _ in range(m)]
+    sc = np.array([[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for k in ks], dtype=np.uint32).reshape(-1)
+    g1 = np.tile(np.array(o.g1_to_limbs32(o.G1_GEN), dtype=np.uint32), m)
+    g2 = np.tile(np.array(o.g2_to_limbs32(o.G2_GEN), dtype=np.uint32), m)
+    o1 = np.zeros(24, dtype=np.uint32); o2 = np.zeros(48, dtype=np.uint32); f = np.zeros(1, dtype=np.uint8)
+    L.check(lib.b381_g1_msm(L.u32(g1)[1], None, L.u32(sc)[1], L.u32(o1)[1], u8(f), m))
+    assert f[0] == 0 and o1.tolist() == o.g1_to_limbs32(o.g1_mul(o.G1_GEN, sum(ks) % o.R_ORDER))
+    L.check(lib.b381_g2_msm(L.u32(g2)[1], None, L.u32(sc)[1], L.u32(o2)[1], u8(f), m))
+    assert f[0] == 0 and o2.tolist() == o.g2_to_limbs32(o.g2_mul(o.G2_GEN, sum(ks) % o.R_ORDER))
+    # the scalars r - k and k cancel: the sum is the identity
+    k = ks[0] % o.R_ORDER
+    sc2 = np.array([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for v in (k, o.R_ORDER - k)], dtype=np.uint32).reshape(-1)
+    L.check(lib.b381_g1_msm(L.u32(g1[:48])[1], None, L.u32(sc2)[1], L.u32(o1)[1], u8(f), 2))
+    assert f[0] == 1

@@ -368,3 +368,25 @@ def test_scalar_mul(hs):
         assert (b[0] == 1 and w is None) or (b[0] == 0 and list(o2) == o.g2_to_limbs32(w)), k
     assert hs.hs_scalar_mul(A(o.g1_to_limbs32(base1)), 0, 0, A([0] * 8), u(24), b) == 0 and b[0] == 1
     assert hs.hs_scalar_mul(A(o.g1_to_limbs32(base1)), 0, 1, A([5] + [0] * 7), u(24), b) == 0 and b[0] == 1
+
+
+def test_point_sum(hs):
+    """One level of the point-reduction tree (packed layout) against the oracle's group law: distinct
+    points, a repeated point (doubling case), P + (-P), identity flags."""
+    r = util.rng(37)
+    pts = [o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER)) for _ in range(5)]
+    pts += [pts[0], (pts[1][0], (o.P - pts[1][1]) % o.P)]
+    packed = []
+    for i, p in enumerate(pts):
+        packed += o.g1_to_limbs32(p) + [1 if i == 2 else 0]
+    out = u(25)
+    assert hs.hs_point_sum(A(packed), ctypes.c_size_t(len(pts)), 0, out) == 0
+    acc = None
+    for i, p in enumerate(pts):
+        if i != 2:
+            acc = o.g1_add(acc, p)
+    assert out[24] == 0 and list(out)[:24] == o.g1_to_limbs32(acc)
+    q = o.g2_mul(o.G2_GEN, 5)
+    packed2 = o.g2_to_limbs32(q) + [0] + o.g2_to_limbs32((q[0], o.f2_neg(q[1]))) + [0]
+    out2 = u(49)
+    assert hs.hs_point_sum(A(packed2), ctypes.c_size_t(2), 1, out2) == 0 and out2[48] == 1
