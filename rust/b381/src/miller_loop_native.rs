@@ -64,3 +64,33 @@ impl MillerLoopResult {
         Ok(read_fq12(&out))
     }
 }
+
+/// `G2Prepared` as a cached stage (ark-ec `G2Prepared`; the shape of `G2PreparedTarget`,
+/// src/miller_loop_target.rs:23-76): 68 coefficient triples per point in the C-ABI layout.
+pub struct G2Prepared { pub coeffs: Vec<u32>, pub infinity: bool, pub mode: Mode }
+
+impl G2Prepared {
+    pub fn from_affine(q: &G2Affine, mode: Mode) -> Result<Self, B381Error> {
+        let mut g2 = Vec::with_capacity(48);
+        push_g2(&mut g2, q);
+        let mut coeffs = vec![0u32; 68 * 72];
+        if !q.infinity {
+            check(unsafe { b381_sys::b381_g2_prepare(g2.as_ptr(), coeffs.as_mut_ptr(), 1, mode as i32) })?;
+        }
+        Ok(G2Prepared { coeffs, infinity: q.infinity, mode })
+    }
+}
+
+/// one Miller value per (P, prepared Q); identical values to `miller_loop_batch` on (P, Q)
+pub fn miller_loop_prepared_batch(terms: &[(&G1Affine, &G2Prepared)]) -> Result<Vec<MillerLoopResult>, B381Error> {
+    let mode = terms.first().map(|t| t.1.mode).unwrap_or(Mode::Ark);
+    let (mut g1, mut co, mut inf) = (Vec::new(), Vec::new(), Vec::new());
+    for (p, q) in terms {
+        push_g1(&mut g1, p);
+        co.extend_from_slice(&q.coeffs);
+        inf.push(p.infinity as u8 | ((q.infinity as u8) << 1));
+    }
+    let mut out = vec![0u32; 144 * terms.len()];
+    check(unsafe { b381_sys::b381_miller_loop_prepared(g1.as_ptr(), co.as_ptr(), inf.as_ptr(), out.as_mut_ptr(), terms.len(), mode as i32) })?;
+    Ok(out.chunks_exact(144).map(|w| MillerLoopResult(read_fq12(w))).collect())
+}
