@@ -374,6 +374,27 @@ def main():
         hsq = np.zeros(kh * 12, dtype=np.uint32)
         L.check(lib.b381_fp_mul(L.u32(ho)[1], L.u32(ho)[1], L.u32(hsq)[1], kh))          # squares: always have a root
         extras["helpers_fp_sqrt_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_sqrt(L.u32(hsq)[1], None, L.u32(ho)[1], kh)))
+        # wire formats, subgroup checks, scalar multiplication, MSM, host-pointer API, 2^15 points
+        import ctypes as _c
+        kp = 1 << 15
+        u8p = lambda arr: arr.ctypes.data_as(_c.POINTER(_c.c_uint8))
+        p1 = np.ascontiguousarray(g1[:kp * 24]); p2 = np.ascontiguousarray(g2[:kp * 48])
+        enc1 = np.zeros(kp * 48, dtype=np.uint8); enc2 = np.zeros(kp * 96, dtype=np.uint8)
+        extras["g1_compress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_serialize(L.u32(p1)[1], None, 1, u8p(enc1), kp)))
+        L.check(lib.b381_g2_serialize(L.u32(p2)[1], None, 1, u8p(enc2), kp))
+        d1_ = np.zeros(kp * 24, dtype=np.uint32); d2_ = np.zeros(kp * 48, dtype=np.uint32); fi = np.zeros(kp, dtype=np.uint8)
+        extras["g1_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_deserialize(u8p(enc1), 1, L.u32(d1_)[1], u8p(fi), kp)))
+        extras["g2_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_deserialize(u8p(enc2), 1, L.u32(d2_)[1], u8p(fi), kp)))
+        extras["wire_roundtrip_ok"] = bool(np.array_equal(d1_, p1) and np.array_equal(d2_, p2))
+        sg = np.zeros(kp, dtype=np.uint8)
+        extras["g1_subgroup_checks_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_in_subgroup(L.u32(p1)[1], None, u8p(sg), kp)))
+        extras["g2_subgroup_checks_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_in_subgroup(L.u32(p2)[1], None, u8p(sg), kp)))
+        extras["subgroup_all_in"] = bool(sg.all())
+        sc_ = np.random.default_rng(7).integers(0, 1 << 32, size=kp * 8, dtype=np.uint64).astype(np.uint32)
+        extras["g1_scalar_muls_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_scalar_mul(L.u32(p1)[1], None, L.u32(sc_)[1], L.u32(d1_)[1], u8p(fi), kp)))
+        extras["g2_scalar_muls_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_scalar_mul(L.u32(p2)[1], None, L.u32(sc_)[1], L.u32(d2_)[1], u8p(fi), kp)))
+        m1 = np.zeros(24, dtype=np.uint32); f1 = np.zeros(1, dtype=np.uint8)
+        extras["g1_msm_points_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_msm(L.u32(p1)[1], None, L.u32(sc_)[1], L.u32(m1)[1], u8p(f1), kp)))
 
     line = {"metric": "pairings/sec (Miller loop + final exp)", "value": value, "unit": "pairings/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

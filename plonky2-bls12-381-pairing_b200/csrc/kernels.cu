@@ -1377,21 +1377,21 @@ static int point_tree(uint32_t* d_a, uint32_t* d_b, size_t n, int is_g2, uint32_
 
 static int point_sum_host(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, int is_g2, uint32_t* out, uint8_t* out_inf, size_t n) {
   const size_t w = is_g2 ? 48 : 24;
-  uint32_t *d_a = nullptr, *d_b = nullptr, *d_p = nullptr, *d_s = nullptr;
-  uint8_t* d_i = nullptr;
   cudaStream_t s = g.stream[0];
-  int rc = 0;
-  CU(cudaMalloc((void**)&d_a, n * (w + 1) * 4));
-  CU(cudaMalloc((void**)&d_b, ((n + 15) / 16 + 1) * (w + 1) * 4));
+  int rc;
+  // the library's persistent staging buffers (no allocation per call): d_out[0] / d_out[1] ping-pong the packed points
+  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, n * (w + 1) * 4))) return rc;
+  uint32_t *d_a = g.d_out[0], *d_b = g.d_out[1];
   if (scalars) {                                    // MSM: [k_i] P_i on the device, straight into the packed layout
-    CU(cudaMalloc((void**)&d_p, n * w * 4));
-    CU(cudaMalloc((void**)&d_s, n * 8 * 4));
-    CU(cudaMemcpyAsync(d_p, pts, n * w * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_s, scalars, n * 8 * 4, cudaMemcpyHostToDevice, s));
-    if (inf) { CU(cudaMalloc((void**)&d_i, n)); CU(cudaMemcpyAsync(d_i, inf, n, cudaMemcpyHostToDevice, s)); }
-    k_scalar_mul<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(d_p, d_s, d_i, is_g2, d_a, n, g.garena[0], g.d_err);
+    if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * w * 4))) return rc;
+    if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, n * 8 * 4))) return rc;
+    if (inf && (rc = ensure_inf_staging(n))) return rc;
+    CU(cudaMemcpyAsync(g.d_in1[0], pts, n * w * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(g.d_in2[0], scalars, n * 8 * 4, cudaMemcpyHostToDevice, s));
+    if (inf) CU(cudaMemcpyAsync(g.d_inf[0], inf, n, cudaMemcpyHostToDevice, s));
+    k_scalar_mul<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g.d_in1[0], g.d_in2[0], inf ? g.d_inf[0] : nullptr, is_g2, d_a, n, g.garena[0], g.d_err);
     g.launches++;
-    if (cudaGetLastError() != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "k_scalar_mul");
+    CU(cudaGetLastError());
   } else {
     std::vector<uint32_t> packed(n * (w + 1));
     for (size_t i = 0; i < n; i++) {
@@ -1401,9 +1401,7 @@ static int point_sum_host(const uint32_t* pts, const uint8_t* inf, const uint32_
     CU(cudaMemcpyAsync(d_a, packed.data(), n * (w + 1) * 4, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
   }
-  if (!rc) rc = point_tree(d_a, d_b, n, is_g2, out, out_inf);
-  cudaFree(d_a); cudaFree(d_b); cudaFree(d_p); cudaFree(d_s); cudaFree(d_i);
-  return rc;
+  return point_tree(d_a, d_b, n, is_g2, out, out_inf);
 }
 
 int b381_g1_sum(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n) {
