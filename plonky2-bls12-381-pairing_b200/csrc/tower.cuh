@@ -618,6 +618,7 @@ enum LinOp {
   L_MUL8,         // 8a
   L_2A_MB,        // 2a - b
   L_MUL4,         // 4a
+  L_ADD_R,        // a + b, weak-reduced (results that feed the cyclotomic squarings must be below 1.1 p)
 };
 
 B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
@@ -625,7 +626,7 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
   ld_f2(a0, a1, a);
   if (b) ld_f2(b0, b1, b); else { fp_zero(b0); fp_zero(b1); }
   switch (op) {
-    case L_ADD: fp_add(r0, a0, b0); fp_add(r1, a1, b1); break;
+    case L_ADD: case L_ADD_R: fp_add(r0, a0, b0); fp_add(r1, a1, b1); break;
     case L_SUB: fp_sub(r0, a0, b0); fp_sub(r1, a1, b1); break;
     case L_NEG: fp_neg(r0, a0); fp_neg(r1, a1); break;
     case L_DBL: fp_dbl(r0, a0); fp_dbl(r1, a1); break;
@@ -675,7 +676,7 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
 #if B381_FMT == 32
   // stored values must be non-negative: the weak reduction (output in [0, 11 p)) where a difference occurs
   // ... and (B381_W12) wherever the result could exceed 5 p, so that it fits the 12-word multiplications
-  const bool grow = B381_W12 && (op == L_TRIPLE || op == L_MUL4 || op == L_MUL8 || op == L_MUL12XI || op == L_XIADD);
+  const bool grow = (B381_W12 && (op == L_TRIPLE || op == L_MUL4 || op == L_MUL8 || op == L_MUL12XI || op == L_XIADD)) || op == L_ADD_R;
   const bool n0 = grow || op == L_SUB || op == L_NEG || op == L_MULXI || op == L_XIADD || op == L_3A_M2B || op == L_3A_P2B || op == L_MUL12XI || op == L_2A_MB;
   const bool n1 = grow || op == L_SUB || op == L_NEG || op == L_CONJ || op == L_3A_M2B || op == L_3A_P2B || op == L_2A_MB;
   if (n0) fp_wreduce(r0);
@@ -725,7 +726,73 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
 // squarings (6 x 196 + 6 x 225) plus seven memory-to-memory linear operations.  The linear feedback
 // of z (magnitude M -> 9 + 2M) is absorbed by the weak reduction when `reduce` is set; callers set it
 // at least every sixth squaring (2 -> 13 -> 35 -> 79 -> 167 -> 343 stays far below the 14-limb range).
-#if B381_FMT == 32
+#if B381_FMT == 32 && B381_W12 && !defined(B381_CYC7)
+// Six-product form: with A = a^2 = (PA, QA), B = b^2 = (PB, QB), C = (a + b)^2 = (PC, QC), where
+// P = (x0 + x1)(x0 - x1 + 5p) and Q = 2 x0 x1 for x = (x0, x1):
+//   t0 = a^2 + xi b^2 = (PA + PB - QB, QA + PB + QB);   t1 = 2ab = (PC - PA - PB, QC - QA - QB)
+// 6 x 144 + 4 x 156 IMAD.WIDE instead of 7 x 144 + 4 x 156 (the a b product of the seven-product form is
+// replaced by one squaring), and only four double-width values are ever live.  Operands must be
+// below 1.1 p each (weak-reduced), which every caller guarantees (tracker-asserted through the
+// 12-word multiplications).
+B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
+  (void)reduce;
+  Fp a0, a1, b0, b1, t00, t01, t10, t11;
+  ld_f2(a0, a1, a);
+  ld_f2(b0, b1, b);
+  Acc SP, SQ;
+  {
+    Fp s, d, e;
+    Acc PB, QB;
+    fp_add(s, a0, a1); fp_sub(d, a0, a1); HOT_OFF(d, d);
+    HOT_MUL(SP, s, d);                              // PA
+    fp_dbl(e, a0);
+    HOT_MUL(SQ, e, a1);                             // QA
+    fp_add(s, b0, b1); fp_sub(d, b0, b1); HOT_OFF(d, d);
+    HOT_MUL(PB, s, d);                              // PB
+    fp_dbl(e, b0);
+    HOT_MUL(QB, e, b1);                             // QB
+    acc_add(SP, SP, PB);                            // PA + PB
+    acc_add(SQ, SQ, QB);                            // QA + QB
+    acc_sub(QB, SP, QB);                            // X = PA + PB - QB
+    acc_add(PB, SQ, PB);                            // Y = QA + QB + PB
+    acc_redc2(t00, QB, t01, PB);
+    fp_add_p(t00, t00);                             // X may be negative
+  }
+  Fp z0, z1;
+  {
+    const u4* zt0 = mode == 0 ? za : zb;
+    if (zt0 == a) { z0 = a0; z1 = a1; } else ld_f2(z0, z1, zt0);
+    Fp w0, w1;
+    fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
+    fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
+    fp_wreduce(w0); fp_wreduce(w1);
+    st_f2(mode == 0 ? ra : rb, w0, w1);
+  }
+  const u4* zt1 = mode == 0 ? zb : za;
+  if (zt1 == b) { z0 = b0; z1 = b1; } else ld_f2(z0, z1, zt1);
+  {
+    Fp c0, c1, s, d, e;
+    Acc PC, QC;
+    fp_add(c0, a0, b0); fp_add(c1, a1, b1);
+    fp_add(s, c0, c1); fp_sub(d, c0, c1); HOT_OFF(d, d);
+    HOT_MUL(PC, s, d);
+    fp_dbl(e, c0);
+    HOT_MUL(QC, e, c1);
+    acc_sub(PC, PC, SP);                            // re(2ab) = PC - PA - PB
+    acc_sub(QC, QC, SQ);                            // im(2ab) = QC - QA - QB = 2 (a0 b1 + a1 b0) >= 0
+    B381_TB(QC.cb = 0;)
+    acc_redc2(t10, PC, t11, QC);
+    fp_add_p(t10, t10);
+  }
+  if (mode == 1) f2_mulxi_reg(t10, t11, t10, t11);
+  // 3 t1 + 2 z
+  Fp x0, x1;
+  fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0); fp_add(x0, x0, z0);
+  fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1); fp_add(x1, x1, z1);
+  fp_wreduce(x0); fp_wreduce(x1);
+  st_f2(mode == 0 ? rb : ra, x0, x1);
+}
+#elif B381_FMT == 32
 B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
   Fp a0, a1, b0, b1, t00, t01, t10, t11;
   ld_f2(a0, a1, a);
@@ -953,8 +1020,8 @@ B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
   f6_mul(cx, r + 3, sa, sb, w);                   // (a0+a1)(b0+b1)   (a, b dead from here on)
   for (int i = 0; i < 3; i++) kcomb(cx, r + 3 + i, r + 3 + i, aa + i, bb + i, -1, K_PLAIN);
   lin(cx, r, aa, bb + 2, L_XIADD);                // c0 = aa + v bb ; v bb = (xi bb2, bb0, bb1)
-  lin(cx, r + 1, aa + 1, bb, L_ADD);
-  lin(cx, r + 2, aa + 2, bb + 1, L_ADD);
+  lin(cx, r + 1, aa + 1, bb, L_ADD_R);
+  lin(cx, r + 2, aa + 2, bb + 1, L_ADD_R);
 }
 
 // Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  Scratch: t = 5 slots, s3 = 3 more
