@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(128)
 k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int nwords, uint32_t* out, uint8_t* out8, size_t n, int* err) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0;
+#if B381_FMT == 32
     const int s = sgn ? (sgn[i] & 1) : 0;
     switch (op) {
       case H_FP_INV: r = prog_fp_inv(a + 12 * i, out + 12 * i); break;
@@ -394,6 +395,9 @@ k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int n
       case H_FP2_SQRT: r = prog_fp2_sqrt(a + 24 * i, s, out + 24 * i); break;
       default: r = prog_fp2_is_square(a + 24 * i, out8 + i); break;
     }
+#else
+    r = 16;                                          // helpers.cuh needs the 13 x 32-bit format
+#endif
     if (r) atomicOr(err, r);
   }
 }
@@ -405,6 +409,7 @@ __global__ void __launch_bounds__(128)
 k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, int* err) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0;
+#if B381_FMT == 32
     const uint8_t* inb = reinterpret_cast<const uint8_t*>(in);
     uint8_t* outb = reinterpret_cast<uint8_t*>(out);
     switch (op) {
@@ -424,6 +429,9 @@ k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t*
       } break;
       default: r = prog_g2_serialize(in + 48 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 96 : 192) * i); break;
     }
+#else
+    r = 16;
+#endif
     if (r) atomicOr(err, r);
   }
 }
@@ -527,6 +535,7 @@ int fail_arg(const char* what) {
 int map_err(int bits) {
   if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
   if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0), f_den == 0 or inverse of zero)"; return B381_E_ZERO_DIVISION; }
+  if (bits & 16) { g.last_error = "entry point not available in this build (witness helpers / wire formats need B381_FMT=32)"; return B381_E_ARG; }
   if (bits & 8) { g.last_error = "invalid point encoding (flag bits)"; return B381_E_BAD_ENCODING; }
   if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1; point not on the curve)"; return B381_E_NOT_SQUARE; }
   return B381_OK;
