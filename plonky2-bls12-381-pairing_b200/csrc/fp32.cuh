@@ -8,11 +8,15 @@
 // pipe 75 % busy.  What is left is the NUMBER of wide multiplies per field multiplication:
 //   14 x 28-bit limbs, carry-free columns (fp28.cuh):  196 + 15*14+15 = 421 per Fp multiplication
 //   13 x 32-bit words, carry chains (this file):       169 + 13*12    = 325 (+13 narrow IMAD)
+//   ... with operands provably below 2^384 (acc_mul12): 144 + 13*12    = 300 = the algorithmic count
 // and the accumulators shrink from 29 x 64-bit columns (58 registers) to 26 words.
 //
 //   value   = two's-complement integer of 13 x 32-bit words (sign in bit 415), |v| < 2^20 p by the
 //             bound tracker; additions / subtractions / negations are plain carry chains (no modular
 //             correction: "lazy"), products of two such values are 26-word two's-complement integers.
+//             STORED values are kept non-negative and below 5 p (weak reduction / + p / + 5 p offsets),
+//             so the hot path multiplies unsigned 12-word operands; the tracker (lower and upper
+//             bound per value) asserts it at every multiplication and store.
 //   radix   R' = 2^416: 13 Montgomery rows over the 12 words of p.  (T + M p) / 2^416 lies in
 //             (T / 2^416, T / 2^416 + p]: any product of operands below 2^17 p reduces to (-eps, p + eps).
 //
