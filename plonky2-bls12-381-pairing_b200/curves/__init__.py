@@ -57,7 +57,8 @@ class G1Projective:
 
     @staticmethod
     def from_affine(p: G1Affine):
-        return G1Projective(Fq(0), Fq(1), Fq(0)) if p.infinity else G1Projective(p.x, p.y, Fq(1))
+        # ark-ec 0.4 Projective::zero() and From<Affine> give (1, 1, 0) for the identity
+        return G1Projective(Fq(1), Fq(1), Fq(0)) if p.infinity else G1Projective(p.x, p.y, Fq(1))
 
     @staticmethod
     def generator():
@@ -75,7 +76,7 @@ class G2Projective:
 
     @staticmethod
     def from_affine(q: G2Affine):
-        return G2Projective(Fq2.zero(), Fq2.one(), Fq2.zero()) if q.infinity else G2Projective(q.x, q.y, Fq2.one())
+        return G2Projective(Fq2.one(), Fq2.one(), Fq2.zero()) if q.infinity else G2Projective(q.x, q.y, Fq2.one())
 
     @staticmethod
     def generator():

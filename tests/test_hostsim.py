@@ -390,3 +390,51 @@ def test_point_sum(hs):
     packed2 = o.g2_to_limbs32(q) + [0] + o.g2_to_limbs32((q[0], o.f2_neg(q[1]))) + [0]
     out2 = u(49)
     assert hs.hs_point_sum(A(packed2), ctypes.c_size_t(2), 1, out2) == 0 and out2[48] == 1
+
+
+def test_literal_vertical_line_branch(hs):
+    """x = 0 gives 2 (0, y) = (0, -y) under the a = 0 doubling formula: at bit 16 the running point is -Q and
+    optimized_line_function takes its vertical-line branch (src/miller_loop_native_optimized.rs:62-77); the sum is
+    the identity, the next tangent has den = 0, f_den = 0: reference panics, oracle raises, error bit 2 here.
+    The identity of ark-ec 0.4, (1, 1, 0), as P gives zp = 0 and the same outcome."""
+    out = u(144)
+    pp = (o.G1_X, o.G1_Y, 1)
+    qq = ((0, 0), (5, 7), (1, 0))
+    with pytest.raises(ZeroDivisionError):
+        o.literal_optimized_miller_loop(pp, qq)
+    assert hs.hs_literal(A(sum((o.fp_to_limbs32(x) for x in pp), [])), A(sum((util.f2_words(x) for x in qq), [])), out) == 2
+    ident = (1, 1, 0)
+    g2p = util.f2_words(o.G2_X) + util.f2_words(o.G2_Y) + util.f2_words((1, 0))
+    with pytest.raises(ZeroDivisionError):
+        o.literal_optimized_miller_loop(ident, (o.G2_X, o.G2_Y, (1, 0)))
+    assert hs.hs_literal(A(sum((o.fp_to_limbs32(x) for x in ident), [])), A(g2p), out) == 2
+
+
+def test_adversarial_operands(hs):
+    """carry-stressing canonical values (all-ones words, 2^k - 1, p - 1, Montgomery pre-images of such patterns)
+    through the Fp / Fp2 / Fp12 products, the cyclotomic chain and a Miller loop of the host simulation."""
+    P = o.P
+    rinv = o.MONT_RINV
+    S = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (1 << 380) - 1, (1 << 380) + 1, (1 << 352) - 1, (1 << 256) - 1, (1 << 32) - 1, 1 << 32,
+         int("aaaaaaaa" * 12, 16) % P, int("7fffffff" * 12, 16) % P]
+    S += [rep * rinv % P for rep in ((1 << 352) - 1, (1 << 380) - 1, P - 1, (1 << 96) - 1, 0xFFFFFFFF, (P >> 1) + 1)]
+    out = u(12)
+    for a in S:
+        for b in S:
+            hs.hs_fp_mul(A(o.fp_to_limbs32(a)), A(o.fp_to_limbs32(b)), out)
+            assert o.fp_from_limbs32(list(out)) == a * b % P
+    r = util.rng(31)
+    o2 = u(24)
+    for _ in range(200):
+        a, b = (r.choice(S), r.choice(S)), (r.choice(S), r.choice(S))
+        hs.hs_fp2_mul(A(util.f2_words(a)), A(util.f2_words(b)), o2)
+        assert util.f2_from_words(list(o2)) == o.f2_mul(a, b)
+    o12 = u(144)
+    for k in range(12):
+        x = o.f12_unflat([r.choice(S) for _ in range(12)]) if k else o.f12_unflat([P - 1] * 12)
+        y = o.f12_unflat([r.choice(S) for _ in range(12)]) if k else o.f12_unflat([P - 1] * 12)
+        hs.hs_fp12_mul(A(o.f12_to_limbs32(x)), A(o.f12_to_limbs32(y)), o12)
+        assert o.f12_eq(o.f12_from_limbs32(list(o12)), o.f12_mul(x, y))
+        if k < 3:
+            assert hs.hs_final_exp(A(o.f12_to_limbs32(x)), o12) == 0
+            assert o.f12_eq(o.f12_from_limbs32(list(o12)), o.ark_final_exponentiation(x))
