@@ -157,6 +157,18 @@ B381_HD B381_INL void fp_add_p5(Fp& r, const Fp& a) {
   B381_SETRANGE(r, a.lb + 5, a.ub + 5);
 }
 
+// r = a + 3 p: offset of the in-register differences b0 - b1 (xi b) and b - f of the fused primitives, whose
+// subtrahend is at most 3 p
+B381_HD B381_INL void fp_add_p3(Fp& r, const Fp& a) {
+  const uint32_t k[NL] = B381_P3;
+  B381_CC_DECL;
+  ADD_CC(r.l[0], a.l[0], k[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) ADDC_CC(r.l[i], a.l[i], k[i]);
+  ADDC(r.l[NL - 1], a.l[NL - 1], k[NL - 1]);
+  B381_SETRANGE(r, a.lb + 3, a.ub + 3);
+}
+
 // r = a + p
 B381_HD B381_INL void fp_add_p(Fp& r, const Fp& a) {
   B381_CC_DECL;
@@ -256,6 +268,14 @@ B381_HD B381_INL void acc_sub(Acc& r, const Acc& a, const Acc& b) {
   for (int k = 1; k < NW - 1; k++) SUBC_CC(r.c[k], a.c[k], b.c[k]);
   SUBC(r.c[NW - 1], a.c[NW - 1], b.c[NW - 1]);
   B381_TB(r.cb = a.cb - b.mag; r.mag = a.mag + b.mag;)
+}
+
+// t = 2 t (two's complement: the bit pattern shifts the same way for either sign)
+B381_HD B381_INL void acc_dbl(Acc& t) {
+#pragma unroll
+  for (int k = NW - 1; k > 0; k--) t.c[k] = (t.c[k] << 1) | (t.c[k - 1] >> 31);
+  t.c[0] <<= 1;
+  B381_TB(t.cb *= 2; t.mag *= 2;)
 }
 
 // t = a * b as a 26-word two's-complement integer: 169 IMAD.WIDE.  Row i multiplies a by word i of
@@ -506,13 +526,6 @@ B381_HD B381_INL void acc_redc(Fp& r, Acc& t) {
 
 B381_HD B381_INL void acc_redc2(Fp& r0, Acc& t0, Fp& r1, Acc& t1) {
   B381_CHECK(t0.mag < ACC_MAG_MAX && t1.mag < ACC_MAG_MAX, "acc_redc2: input too large");
-#ifdef B381_REDC2_SEQ
-  acc_redc_rows<NL>(r0, t0);
-  acc_redc_rows<NL>(r1, t1);
-  B381_SETRANGE(r0, t0.cb < 0 ? t0.cb / 4.2e10 : 0.0, 1.0 + t0.mag / 4.2e10 + 1e-9);
-  B381_SETRANGE(r1, t1.cb < 0 ? t1.cb / 4.2e10 : 0.0, 1.0 + t1.mag / 4.2e10 + 1e-9);
-  return;
-#endif
   B381_CC_DECL;
   constexpr int ROWS = NL;
   uint32_t A0[14], B0[14], A1[14], B1[14], c0 = 0, c1 = 0;

@@ -12,7 +12,6 @@
 #pragma once
 #include "tower.cuh"
 
-#if B381_FMT == 32
 namespace b381 {
 
 enum HelperErr { HERR_NOT_CANONICAL = 1, HERR_ZERO_DIVISION = 2, HERR_NOT_SQUARE = 4 };
@@ -234,12 +233,10 @@ B381_DEV B381_INL int prog_fp2_is_square(const uint32_t* a, uint8_t* out) {
 }
 
 }  // namespace b381
-#endif  // B381_FMT == 32
 
 // ---------------------------------------------------------------------------------------------------
 // Wire formats
 // ---------------------------------------------------------------------------------------------------
-#if B381_FMT == 32
 namespace b381 {
 
 // (a) the reference's own witness format: the canonical (non-Montgomery) integer as 12 x 32-bit
@@ -517,4 +514,3 @@ B381_DEV B381_INL int prog_g2_serialize(const uint32_t* g2, int inf, int compres
 }
 
 }  // namespace b381
-#endif

@@ -2,11 +2,11 @@
 //
 // Execution model.  One pairing per thread.  The tower kernels are PERSISTENT: one CTA of
 // B381_BLOCK threads per SM (grid = min(batches, #SM)), each CTA loops over batches of
-// B381_BLOCK pairings.  Per-thread state is an arena of Fp2 slots: the hot 16 slots in shared
-// memory (224 KB per CTA, word-interleaved so every LDS.128/STS.128 is conflict-free), the cold
-// slots in a per-CTA global scratch region that stays L2-resident because only #SM CTAs exist.
-// The arithmetic is fp32.cuh (13 x 32-bit words, IMAD.WIDE.U32.X carry chains; default) or fp28.cuh
-// (14 x 28-bit limbs, carry-free IMAD.WIDE column accumulation; -DB381_FMT=28); see DESIGN.md section 2.
+// B381_BLOCK pairings.  Per-thread state is an arena of Fp2 slots (24 words): the hot 9 slots in shared
+// memory (216 KB per CTA, word-interleaved so every LDS.128/STS.128 is conflict-free), 10 more in
+// tensor memory, the cold slots in a per-CTA global scratch region that stays L2-resident because
+// only #SM CTAs exist.  The arithmetic is fp32.cuh (13 x 32-bit words, IMAD.WIDE.U32.X carry chains);
+// see DESIGN.md section 2.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -24,7 +24,7 @@ namespace {
 
 constexpr int BLOCK = B381_BLOCK;
 constexpr int NG_SLOTS = MAX_NSLOTS - NS;                               // cold slots per thread
-constexpr size_t SMEM_BYTES = (size_t)NS * GPS * sizeof(u4) * BLOCK;    // 16*7*16*128 = 224 KB
+constexpr size_t SMEM_BYTES = (size_t)NS * GPS * sizeof(u4) * BLOCK;    // 9 slots x 96 B x 256 threads = 216 KB
 constexpr size_t GARENA_U4_PER_CTA = (size_t)NG_SLOTS * GPS * BLOCK;
 constexpr int RAW_WORDS = 6 * 28;                                       // internal-format Fp12
 
@@ -177,7 +177,7 @@ k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_
     int e = miller2_to_slots(cx, g1 + 24 * i0, g2 + 48 * i0, act0 ? (inf ? inf[i0] : 0) : 3,
                              g1 + 24 * i1, g2 + 48 * i1, act1 ? (inf ? inf[i1] : 0) : 3, mode);
     if (act0) report(e, err);
-    f12_mul(cx, M2_ACC, M2_ACC, ML_F, ML_T, ML_T + 6);   // scratch ML_T .. ML_T+13 overlaps R/Q/P of pair one, reloaded per round
+    f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);   // scratch: slots that are dead once the loop has left f in ML_F
   }
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), M2_ACC);
   B381_TMEM_END();
@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(128)
 k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int nwords, uint32_t* out, uint8_t* out8, size_t n, int* err) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0;
-#if B381_FMT == 32
     const int s = sgn ? (sgn[i] & 1) : 0;
     switch (op) {
       case H_FP_INV: r = prog_fp_inv(a + 12 * i, out + 12 * i); break;
@@ -395,9 +394,6 @@ k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int n
       case H_FP2_SQRT: r = prog_fp2_sqrt(a + 24 * i, s, out + 24 * i); break;
       default: r = prog_fp2_is_square(a + 24 * i, out8 + i); break;
     }
-#else
-    r = 16;                                          // helpers.cuh needs the 13 x 32-bit format
-#endif
     if (r) atomicOr(err, r);
   }
 }
@@ -409,7 +405,6 @@ __global__ void __launch_bounds__(128)
 k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, int* err) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0;
-#if B381_FMT == 32
     const uint8_t* inb = reinterpret_cast<const uint8_t*>(in);
     uint8_t* outb = reinterpret_cast<uint8_t*>(out);
     switch (op) {
@@ -429,9 +424,6 @@ k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t*
       } break;
       default: r = prog_g2_serialize(in + 48 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 96 : 192) * i); break;
     }
-#else
-    r = 16;
-#endif
     if (r) atomicOr(err, r);
   }
 }
@@ -535,7 +527,6 @@ int fail_arg(const char* what) {
 int map_err(int bits) {
   if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
   if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0), f_den == 0 or inverse of zero)"; return B381_E_ZERO_DIVISION; }
-  if (bits & 16) { g.last_error = "entry point not available in this build (witness helpers / wire formats need B381_FMT=32)"; return B381_E_ARG; }
   if (bits & 8) { g.last_error = "invalid point encoding (flag bits)"; return B381_E_BAD_ENCODING; }
   if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1; point not on the curve)"; return B381_E_NOT_SQUARE; }
   return B381_OK;
@@ -815,7 +806,7 @@ int b381_init(int device) {
   g.cc_major = prop.major;
   g.cc_minor = prop.minor;
   if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) {
-    g.last_error = "device lacks 224 KB opt-in shared memory per block (built for sm_100a)";
+    g.last_error = "device lacks 216 KB opt-in shared memory per block (built for sm_100a)";
     return B381_E_CUDA;
   }
   CU(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
@@ -1026,7 +1017,7 @@ int b381_multi_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* in
 int b381_fp12_product(const uint32_t* in, uint32_t* out144, size_t n) {
   REQUIRE_INIT();
   if (!in || !out144 || n == 0) return fail_arg("b381_fp12_product: bad argument");
-  if (n > (size_t)g.sm_count * BLOCK) return fail_arg("b381_fp12_product: n too large (max sm_count * 128)");
+  if (n > (size_t)g.sm_count * BLOCK) return fail_arg("b381_fp12_product: n too large (max sm_count * 256)");
   std::lock_guard<std::mutex> lk(g.mu);
   int rc;
   if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * 144 * 4))) return rc;

@@ -15,13 +15,24 @@ enum ErrBits { ERR_NOT_CANONICAL = 1, ERR_ZERO_DIVISION = 2 };
 // Miller loop: f and the line coefficients and the first scratch slots are the hot set (shared
 // memory when NS = 16); R, Q, P are touched only by the curve steps.
 constexpr int ML_F = 0, ML_L = 6, ML_T = 9, ML_R = 19, ML_Q = 22, ML_P = 24, ML_ACC = 25, ML_NSLOTS = 31;
+// ARK Miller loop, ping-pong plan (tower.cuh ark_miller_loop_pp): banks A (= ML_F) and B, line, 5 scratch slots
+constexpr int PP_A = 0, PP_B = 6, PP_L = 12, PP_T = 15, PP_R = 20, PP_Q = 23, PP_P = 25;
+// ... second pair of the shared-squaring two-pair loop and the running product of k_multi_miller
+constexpr int PP_R2 = 26, PP_Q2 = 29, PP_P2 = 31, PP_ACC = 32, PP_NSLOTS = 38;
 // final exponentiation: ACC (the value being squared) and the first scratch slots are hot.
 constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_F = 28, FE_Y0 = 28 /* f is dead once y0 is first written */, FE_Y1 = 34, FE_Y2 = 40, FE_R = 46, FE_NSLOTS = 52;
 // literal loop
 constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
 // shared-squaring multi-Miller (two pairs per thread): second pair's R, Q, P and the running product
-constexpr int M2_R2 = 25, M2_Q2 = 28, M2_P2 = 30, M2_ACC = 31, M2_NSLOTS = 37;
+constexpr int M2_R2 = 25, M2_Q2 = 28, M2_P2 = 30, M2_ACC = 32 /* = PP_ACC: one accumulator slot range for both modes */, M2_NSLOTS = 38;
+constexpr int M2_SCRATCH = 6;   // 14 scratch slots of the accumulating Fp12 product: dead line / scratch / bank-B slots of either plan
 constexpr int MAX_NSLOTS = 52;
+// Stores under a per-thread `if (ident)` (miller_to_slots & co.) must never hit tensor memory (tcgen05.st is
+// .sync.aligned): the P / Q input slots live in the global-memory part of the arena, f in shared memory.
+static_assert(ML_Q >= NS + NT_MAX && ML_P >= NS + NT_MAX && M2_Q2 >= NS + NT_MAX && M2_P2 >= NS + NT_MAX, "P / Q slots must be global-memory slots");
+static_assert(ML_F + 5 < NS, "f must be a shared-memory slot range");
+static_assert(PP_Q >= NS + NT_MAX && PP_P >= NS + NT_MAX && PP_A == ML_F, "ping-pong plan: P / Q in global memory, result where ML_F is");
+static_assert(PP_NSLOTS <= MAX_NSLOTS && M2_NSLOTS <= MAX_NSLOTS && PP_ACC == M2_ACC, "arena size / shared accumulator");
 
 #define S_(i) slot(cx, (i))
 
@@ -58,17 +69,23 @@ B381_DEV B381_INL void f12_load_raw(const Ctx& cx, int f, const uint32_t* src) {
 B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const uint32_t* g2, int inf, int mode) {
   int err = 0;
   const bool ident = (inf & 3) != 0;               // identity pairs contribute 1 (ark drops them)
+  const int sP = mode == MODE_ZK ? ML_P : PP_P, sQ = mode == MODE_ZK ? ML_Q : PP_Q;
   if (ident) {                                     // run the (uniform) loop on zeros, discard the result
-    f2_set_small(S_(ML_P), 0); f2_set_small(S_(ML_Q), 0); f2_set_small(S_(ML_Q + 1), 0);
+    f2_set_small(S_(sP), 0); f2_set_small(S_(sQ), 0); f2_set_small(S_(sQ + 1), 0);
   } else {
-    if (!f2_load_ext(S_(ML_P), g1)) err |= ERR_NOT_CANONICAL;
-    if (!f2_load_ext(S_(ML_Q), g2)) err |= ERR_NOT_CANONICAL;
-    if (!f2_load_ext(S_(ML_Q + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(sP), g1)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(sQ), g2)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(sQ + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
   }
-  MillerSlots s;
-  s.f = ML_F; s.L = ML_L; s.T = ML_T; s.R = ML_R; s.Q = ML_Q; s.P = ML_P;
-  if (mode == MODE_ZK) zk_miller_loop(cx, s);
-  else ark_miller_loop(cx, s);
+  if (mode == MODE_ZK) {
+    MillerSlots s;
+    s.f = ML_F; s.L = ML_L; s.T = ML_T; s.R = ML_R; s.Q = ML_Q; s.P = ML_P;
+    zk_miller_loop(cx, s);
+  } else {
+    MillerSlotsPP s;
+    s.A = PP_A; s.B = PP_B; s.L = PP_L; s.T = PP_T; s.R[0] = PP_R; s.Q[0] = PP_Q; s.P[0] = PP_P;
+    ark_miller_loop_pp<1>(cx, s, nullptr);
+  }
   if (ident) f12_set_one(cx, ML_F);
   return err;
 }
@@ -78,7 +95,8 @@ B381_DEV B381_INL int miller2_to_slots(const Ctx& cx, const uint32_t* g1a, const
                                        const uint32_t* g1b, const uint32_t* g2b, int infb, int mode) {
   int err = 0;
   bool ident[2] = {(infa & 3) != 0, (infb & 3) != 0};
-  const int Pj[2] = {ML_P, M2_P2}, Qj[2] = {ML_Q, M2_Q2};
+  const bool zk = mode == MODE_ZK;
+  const int Pj[2] = {zk ? ML_P : PP_P, zk ? M2_P2 : PP_P2}, Qj[2] = {zk ? ML_Q : PP_Q, zk ? M2_Q2 : PP_Q2};
   const uint32_t* g1[2] = {g1a, g1b};
   const uint32_t* g2[2] = {g2a, g2b};
   for (int j = 0; j < 2; j++) {
@@ -90,12 +108,19 @@ B381_DEV B381_INL int miller2_to_slots(const Ctx& cx, const uint32_t* g1a, const
       if (!f2_load_ext(S_(Qj[j] + 1), g2[j] + 24)) err |= ERR_NOT_CANONICAL;
     }
   }
-  MultiSlots s;
-  s.f = ML_F; s.L = ML_L; s.T = ML_T;
-  s.R[0] = ML_R; s.Q[0] = ML_Q; s.P[0] = ML_P;
-  s.R[1] = M2_R2; s.Q[1] = M2_Q2; s.P[1] = M2_P2;
-  if (mode == MODE_ZK) zk_miller_loop_multi(cx, s, 2, ident);
-  else ark_miller_loop_multi(cx, s, 2, ident);
+  if (zk) {
+    MultiSlots s;
+    s.f = ML_F; s.L = ML_L; s.T = ML_T;
+    s.R[0] = ML_R; s.Q[0] = ML_Q; s.P[0] = ML_P;
+    s.R[1] = M2_R2; s.Q[1] = M2_Q2; s.P[1] = M2_P2;
+    zk_miller_loop_multi(cx, s, 2, ident);
+  } else {
+    MillerSlotsPP s;
+    s.A = PP_A; s.B = PP_B; s.L = PP_L; s.T = PP_T;
+    s.R[0] = PP_R; s.Q[0] = PP_Q; s.P[0] = PP_P;
+    s.R[1] = PP_R2; s.Q[1] = PP_Q2; s.P[1] = PP_P2;
+    ark_miller_loop_pp<2>(cx, s, ident);
+  }
   return err;
 }
 
@@ -185,10 +210,17 @@ B381_DEV B381_INL int miller_prepared_to_slots(const Ctx& cx, const uint32_t* g1
     ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); zk_ell(cx, ML_F, ML_L, ML_P, ML_T);
   } else {
     const uint64_t xabs = B381_X_ABS;
+    // ping-pong banks with static roles: squaring A -> B, line B -> A; an addition line goes A -> B and is copied back
     for (int b = 62; b >= 0; b--) {
-      if (b != 62) f12_sqr(cx, ML_F, ML_T, ML_L);
-      ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); ark_ell(cx, ML_F, ML_L, ML_P, ML_T);
-      if ((xabs >> b) & 1) { ok &= load_triple(cx, ML_L, coeffs + 72 * idx++); ark_ell(cx, ML_F, ML_L, ML_P, ML_T); }
+      if (b != 62) f12_sqr_oop(cx, PP_B, PP_A, PP_T, PP_L);
+      else f12_set_one(cx, PP_B);
+      ok &= load_triple(cx, PP_L, coeffs + 72 * idx++);
+      ark_ell_oop(cx, PP_A, PP_B, PP_L, ML_P, 0);
+      if ((xabs >> b) & 1) {
+        ok &= load_triple(cx, PP_L, coeffs + 72 * idx++);
+        ark_ell_oop(cx, PP_B, PP_A, PP_L, ML_P, 0);
+        f12_copy(cx, PP_A, PP_B);
+      }
     }
   }
   f12_conj(cx, ML_F);

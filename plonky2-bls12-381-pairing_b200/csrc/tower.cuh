@@ -1,28 +1,22 @@
 // tower.cuh -- Fp2/Fp6/Fp12 tower, G2 line functions, Miller loops and final exponentiation
 // over memory-resident operands ("slots"), one pairing per thread.
 //
-// Storage model.  Every per-thread value is an Fp2 "slot" of 28 words (2 x 14 limbs) = 7 uint4
-// groups.  Group g of a slot lives at ptr[g * B381_GS]: on the device B381_GS = block size, so a
-// warp touching the same group of its 32 pairings reads 512 contiguous bytes (LDS.128/LDG.128,
-// conflict-free); on the host simulation B381_GS = 1.  Slots [0, NS) are in shared memory, slots
-// >= NS in a per-CTA scratch region of global memory (L2 resident: the kernels are persistent,
-// one CTA per SM).  Fp6 = 3 consecutive slots (c0,c1,c2), Fp12 = 6 consecutive slots
+// Storage model.  Every per-thread value is an Fp2 "slot" of 24 words (2 x 12: every STORED value is
+// below 2^384, asserted by the bound tracker at each store) = 6 uint4 groups.  Group g of a slot
+// lives at ptr[g * B381_GS]: on the device B381_GS = block size, so a warp touching the same group
+// of its 32 pairings reads 512 contiguous bytes (LDS.128/LDG.128, conflict-free); on the host
+// simulation B381_GS = 1.  Slots [0, NS) are in shared memory, slots [NS, NS + nt) in tensor memory,
+// the rest in a per-CTA scratch region of global memory (L2 resident: one CTA per SM).
+// Fp6 = 3 consecutive slots (c0,c1,c2), Fp12 = 6 consecutive slots
 // (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2) -- the reference's tower order
 // (/root/reference/src/fields/helpers.rs:16-37).
 //
 // Heavy Fp2-level primitives (f2_mul, f2_sqr, ...) are __noinline__: they load their operands
-// into registers, do all arithmetic there (fp28.cuh) and store one result.  Everything above is
+// into registers, do all arithmetic there (fp32.cuh) and store one result.  Everything above is
 // orchestration.  Formulas follow the reference's tower twins (cited per function) and, for the
 // ARK mode, arkworks 0.4; values are bit-identical to the oracle.
 #pragma once
-#ifndef B381_FMT
-#define B381_FMT 32      // 32: 13 x 32-bit words with carry chains (fp32.cuh, default); 28: 14 x 28-bit carry-free columns (fp28.cuh)
-#endif
-#if B381_FMT == 32
 #include "fp32.cuh"
-#else
-#include "fp28.cuh"
-#endif
 
 #if defined(__CUDACC__)
 typedef uint4 u4;
@@ -48,10 +42,11 @@ struct alignas(16) u4 { uint32_t x, y, z, w; };
 
 namespace b381 {
 
-constexpr int GPS = 7;                 // uint4 groups per slot
+constexpr int GPS = 6;                 // uint4 groups per slot (2 x 12 words)
+constexpr int SW = 12;                 // stored words per Fp
 constexpr int SLOT = GPS * B381_GS;    // uint4 stride between slots
 #ifndef B381_NS
-#define B381_NS 8
+#define B381_NS 9
 #endif
 constexpr int NS = B381_NS;            // slots held in shared memory
 
@@ -66,9 +61,9 @@ struct Ctx {
 // Tensor memory (TMEM, 256 KB per SM) as a per-thread scratchpad.  The pairing kernels issue no MMA,
 // so the whole TMEM of the SM is free: a CTA allocates all 512 columns; warp w owns TMEM lanes
 // 32 (w % 4) .. +31 (the only lanes it may address) and columns 256 (w / 4) .. +255, i.e. every
-// thread owns 256 words = 9 Fp2 slots, moved with tcgen05.ld/st.32x32b (one thread per lane).
+// thread owns 256 words = 10 Fp2 slots of 24 columns, moved with tcgen05.ld/st.32x32b.x16 + .x8 (one thread per lane).
 // Pointers into TMEM are tagged (bit 62) so the slot primitives can take either kind.
-constexpr int NT_MAX = 9;
+constexpr int NT_MAX = 10;
 constexpr unsigned long long TMEM_TAG = 1ull << 62;
 
 // Warps of a CTA execute the identical instruction stream (control flow does not depend on the
@@ -93,14 +88,14 @@ B381_DEV B381_INL void sync_point(const Ctx& c) {
 B381_DEV B381_INL u4* slot(const Ctx& c, int s) {
   if (s < NS) return c.sm + s * SLOT;
 #if defined(__CUDA_ARCH__)
-  if (s < NS + c.nt) return reinterpret_cast<u4*>(TMEM_TAG | (unsigned long long)(c.tm + (uint32_t)(s - NS) * 28u));
+  if (s < NS + c.nt) return reinterpret_cast<u4*>(TMEM_TAG | (unsigned long long)(c.tm + (uint32_t)(s - NS) * 24u));
 #endif
   return c.gm + (s - NS) * SLOT;
 }
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ bool is_tmem(const u4* p) { return (reinterpret_cast<unsigned long long>(p) & TMEM_TAG) != 0; }
-__device__ __forceinline__ void tmem_ld28(uint32_t (&w)[28], uint32_t ta) {
+__device__ __forceinline__ void tmem_ld24(uint32_t (&w)[24], uint32_t ta) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
                  "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
@@ -108,18 +103,14 @@ __device__ __forceinline__ void tmem_ld28(uint32_t (&w)[28], uint32_t ta) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23])
                : "r"(ta + 16));
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]) : "r"(ta + 24));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st28(uint32_t ta, const uint32_t (&w)[28]) {
+__device__ __forceinline__ void tmem_st24(uint32_t ta, const uint32_t (&w)[24]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                :: "r"(ta), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
                   "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "r"(ta + 16), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]) : "memory");
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-               :: "r"(ta + 24), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]) : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 #endif
@@ -146,26 +137,15 @@ struct TrackEnt { double mag[2], lb[2]; };
 inline std::unordered_map<const void*, TrackEnt>& track_tab() { static std::unordered_map<const void*, TrackEnt> t; return t; }
 inline void track_ld(const u4* p, int h, Fp& a) {
   auto it = track_tab().find(p);
-#if B381_FMT == 32
   if (it == track_tab().end()) tb_range(a, 0.0, 1.0); else tb_range(a, it->second.lb[h], it->second.mag[h]);
-#else
-  if (it == track_tab().end()) { a.mag = 1.0; a.lb = 1.0; } else { a.mag = it->second.mag[h]; a.lb = it->second.lb[h]; }
-#endif
   a.nonneg = true;
 }
 inline void track_st(const u4* p, int h, const Fp& a) {
-#if B381_FMT == 32
   B381_CHECK(a.lb >= 0, "store of a possibly negative value");
-#else
-  B381_CHECK(a.lb < 1.01 && a.nonneg, "store of non-normalised limbs");
-#endif
   B381_CHECK(a.mag < 1000.0, "store of oversized value");
+  B381_CHECK(a.ub < 9.8, "stored value does not fit 12 words");
   auto& e = track_tab()[p];
-#if B381_FMT == 32
   e.mag[h] = a.ub; e.lb[h] = a.lb;
-#else
-  e.mag[h] = a.mag; e.lb[h] = a.lb;
-#endif
 }
 #endif
 
@@ -173,73 +153,43 @@ inline void track_st(const u4* p, int h, const Fp& a) {
 // slot loads / stores
 // ---------------------------------------------------------------------------------------------
 B381_DEV B381_INL void ld_f2(Fp& c0, Fp& c1, const u4* p) {
+  uint32_t w[2 * SW];
 #if defined(__CUDA_ARCH__)
   if (is_tmem(p)) {
-    uint32_t w[28];
-    tmem_ld28(w, (uint32_t)reinterpret_cast<unsigned long long>(p));
-#pragma unroll
-    for (int k = 0; k < NL; k++) { c0.l[k] = (limb_t)w[k]; c1.l[k] = (limb_t)w[NL + k]; }
-    return;
-  }
+    tmem_ld24(w, (uint32_t)reinterpret_cast<unsigned long long>(p));
+  } else
 #endif
-  u4 g[GPS];
-#pragma unroll
-  for (int i = 0; i < GPS; i++) g[i] = p[i * B381_GS];
-#if B381_FMT == 32
   {
-    const uint32_t w[28] = {g[0].x, g[0].y, g[0].z, g[0].w, g[1].x, g[1].y, g[1].z, g[1].w, g[2].x, g[2].y, g[2].z, g[2].w, g[3].x, g[3].y,
-                            g[3].z, g[3].w, g[4].x, g[4].y, g[4].z, g[4].w, g[5].x, g[5].y, g[5].z, g[5].w, g[6].x, g[6].y, g[6].z, g[6].w};
+    u4 g[GPS];
 #pragma unroll
-    for (int k = 0; k < NL; k++) { c0.l[k] = w[k]; c1.l[k] = w[NL + k]; }
+    for (int i = 0; i < GPS; i++) g[i] = p[i * B381_GS];
+#pragma unroll
+    for (int i = 0; i < GPS; i++) { w[4 * i] = g[i].x; w[4 * i + 1] = g[i].y; w[4 * i + 2] = g[i].z; w[4 * i + 3] = g[i].w; }
   }
-#else
-  c0.l[0] = g[0].x; c0.l[1] = g[0].y; c0.l[2] = g[0].z; c0.l[3] = g[0].w;
-  c0.l[4] = g[1].x; c0.l[5] = g[1].y; c0.l[6] = g[1].z; c0.l[7] = g[1].w;
-  c0.l[8] = g[2].x; c0.l[9] = g[2].y; c0.l[10] = g[2].z; c0.l[11] = g[2].w;
-  c0.l[12] = g[3].x; c0.l[13] = g[3].y; c1.l[0] = g[3].z; c1.l[1] = g[3].w;
-  c1.l[2] = g[4].x; c1.l[3] = g[4].y; c1.l[4] = g[4].z; c1.l[5] = g[4].w;
-  c1.l[6] = g[5].x; c1.l[7] = g[5].y; c1.l[8] = g[5].z; c1.l[9] = g[5].w;
-  c1.l[10] = g[6].x; c1.l[11] = g[6].y; c1.l[12] = g[6].z; c1.l[13] = g[6].w;
-#endif
+#pragma unroll
+  for (int k = 0; k < SW; k++) { c0.l[k] = w[k]; c1.l[k] = w[SW + k]; }
+  c0.l[NL - 1] = 0; c1.l[NL - 1] = 0;               // stored values are below 2^384
   B381_TB(track_ld(p, 0, c0); track_ld(p, 1, c1);)
 }
 
 B381_DEV B381_INL void st_f2(u4* p, const Fp& c0, const Fp& c1) {
+  B381_TB(track_st(p, 0, c0); track_st(p, 1, c1);)
+  B381_CHECK(c0.l[NL - 1] == 0 && c1.l[NL - 1] == 0, "stored value has a non-zero thirteenth word");
+  uint32_t w[2 * SW];
+#pragma unroll
+  for (int k = 0; k < SW; k++) { w[k] = c0.l[k]; w[SW + k] = c1.l[k]; }
 #if defined(__CUDA_ARCH__)
   if (is_tmem(p)) {
-    uint32_t w[28];
-#pragma unroll
-    for (int k = 2 * NL; k < 28; k++) w[k] = 0;
-#pragma unroll
-    for (int k = 0; k < NL; k++) { w[k] = (uint32_t)c0.l[k]; w[NL + k] = (uint32_t)c1.l[k]; }
-    tmem_st28((uint32_t)reinterpret_cast<unsigned long long>(p), w);
+    tmem_st24((uint32_t)reinterpret_cast<unsigned long long>(p), w);
     return;
   }
 #endif
-  u4 g[GPS];
-#if B381_FMT == 32
-  {
-    uint32_t w[28];
 #pragma unroll
-    for (int k = 0; k < NL; k++) { w[k] = c0.l[k]; w[NL + k] = c1.l[k]; }
-    w[26] = 0; w[27] = 0;
-    g[0].x = w[0]; g[0].y = w[1]; g[0].z = w[2]; g[0].w = w[3]; g[1].x = w[4]; g[1].y = w[5]; g[1].z = w[6]; g[1].w = w[7];
-    g[2].x = w[8]; g[2].y = w[9]; g[2].z = w[10]; g[2].w = w[11]; g[3].x = w[12]; g[3].y = w[13]; g[3].z = w[14]; g[3].w = w[15];
-    g[4].x = w[16]; g[4].y = w[17]; g[4].z = w[18]; g[4].w = w[19]; g[5].x = w[20]; g[5].y = w[21]; g[5].z = w[22]; g[5].w = w[23];
-    g[6].x = w[24]; g[6].y = w[25]; g[6].z = w[26]; g[6].w = w[27];
+  for (int i = 0; i < GPS; i++) {
+    u4 g;
+    g.x = w[4 * i]; g.y = w[4 * i + 1]; g.z = w[4 * i + 2]; g.w = w[4 * i + 3];
+    p[i * B381_GS] = g;
   }
-#else
-  g[0].x = c0.l[0]; g[0].y = c0.l[1]; g[0].z = c0.l[2]; g[0].w = c0.l[3];
-  g[1].x = c0.l[4]; g[1].y = c0.l[5]; g[1].z = c0.l[6]; g[1].w = c0.l[7];
-  g[2].x = c0.l[8]; g[2].y = c0.l[9]; g[2].z = c0.l[10]; g[2].w = c0.l[11];
-  g[3].x = c0.l[12]; g[3].y = c0.l[13]; g[3].z = c1.l[0]; g[3].w = c1.l[1];
-  g[4].x = c1.l[2]; g[4].y = c1.l[3]; g[4].z = c1.l[4]; g[4].w = c1.l[5];
-  g[5].x = c1.l[6]; g[5].y = c1.l[7]; g[5].z = c1.l[8]; g[5].w = c1.l[9];
-  g[6].x = c1.l[10]; g[6].y = c1.l[11]; g[6].z = c1.l[12]; g[6].w = c1.l[13];
-#endif
-#pragma unroll
-  for (int i = 0; i < GPS; i++) p[i * B381_GS] = g[i];
-  B381_TB(track_st(p, 0, c0); track_st(p, 1, c1);)
 }
 
 // one half (h = 0: c0, h = 1: c1) of a slot
@@ -281,24 +231,16 @@ B381_DEV B381_INL void fp_const(Fp& r, const limb_t* v) {
 // ---------------------------------------------------------------------------------------------
 // register-level Fp2 helpers
 // ---------------------------------------------------------------------------------------------
-#if B381_FMT == 32
 // B381_W12 (default): the hot primitives multiply 12-word operands (144 instead of 169 IMAD.WIDE per
 // product).  Every value they load is a stored value below 5 p and every in-register sum / offset
 // difference stays below 2^384 = 9.84 p; the bound tracker asserts it at each multiplication.
 #ifndef B381_W12
 #define B381_W12 1
 #endif
-#if B381_W12
 #define HOT_MUL acc_mul12
 #define HOT_MAC acc_mac12
 #define HOT_MUL3 acc_mul3_12
 #define HOT_OFF fp_add_p5
-#else
-#define HOT_MUL acc_mul
-#define HOT_MAC acc_mac
-#define HOT_MUL3 acc_mul3
-#define HOT_OFF fp_add_p128
-#endif
 // (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba in the double-width domain, one reduction per
 // coefficient: 3 x 169 + 2 x 156 IMAD.WIDE.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
 B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
@@ -337,52 +279,6 @@ B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, 
   HOT_MUL(U, a1, s);
   acc_redc2(r0, T, r1, U);
 }
-#else
-// (r0, r1) = (a0 + a1 u)(b0 + b1 u), Karatsuba with one reduction per coefficient:
-// 3 x 196 + 2 x 225 = 1038 IMAD.  /root/reference/src/fields_as_trees/fq2_target_tree.rs:97-115
-B381_DEV B381_INL void f2_mul_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& b0, const Fp& b1) {
-  // re = a0 b0 - a1 b1 ; im = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1.
-  // Register diet: after the two products only the sums stay live, the butterfly runs in place on
-  // the column accumulators, and both reductions are interleaved.
-  Acc A, B;
-  acc_zero(A); acc_mac(A, a0, b0);
-  acc_zero(B); acc_mac(B, a1, b1);
-  Fp sa, sb;
-  fp_add(sa, a0, a1);
-  fp_add(sb, b0, b1);
-#pragma unroll
-  for (int k = 0; k < 2 * NL - 1; k++) {
-    const int64_t x = A.c[k], y = B.c[k];
-    A.c[k] = x - y;                                 // re
-    B.c[k] = -x - y;                                // -(a0 b0 + a1 b1)
-  }
-  B381_TB(A.cb = A.cb + B.cb; B.cb = A.cb; A.mag = A.mag + B.mag; B.mag = A.mag;)
-  acc_mac(B, sa, sb);
-  acc_redc2(r0, A, r1, B);
-}
-
-// ((a0+a1)(a0-a1), 2 a0 a1); fq2_target_tree.rs:80-91.  2 x 196 + 2 x 225 = 842 IMAD.
-B381_DEV B381_INL void f2_sqr_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) {
-  Fp s, d, t;
-  fp_add(s, a0, a1);
-  fp_sub(d, a0, a1);
-  fp_norm(d);                                       // multiplicand limbs 0..12 must be non-negative
-  fp_dbl(t, a0);
-  Acc T, U;
-  acc_zero(T); acc_mac(T, s, d);
-  acc_zero(U); acc_mac(U, t, a1);
-  acc_redc2(r0, T, r1, U);
-}
-
-// (a0 s, a1 s) for an Fp scalar s
-B381_DEV B381_INL void f2_mulfp_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1, const Fp& s) {
-  Acc T, U;
-  acc_zero(T); acc_mac(T, a0, s);
-  acc_zero(U); acc_mac(U, a1, s);
-  acc_redc2(r0, T, r1, U);
-}
-
-#endif
 
 B381_DEV B381_INL void f2_norm(Fp& a0, Fp& a1) { fp_norm(a0); fp_norm(a1); }
 
@@ -396,11 +292,7 @@ B381_DEV B381_INL void f2_mulxi_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) 
 
 // Fermat inversion a^(p-2), 4-bit fixed windows, table in registers is too large -> binary
 // square-and-multiply driven by the nibble table (uniform control flow across the warp).
-#if B381_FMT == 32 && B381_W12
 #define FP_MUL_SMALL fp_mul12      // x and a are reduction outputs (at most 1.03 p): 12-word products
-#else
-#define FP_MUL_SMALL fp_mul
-#endif
 B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
   Fp x;
   fp_const(x, g_ct.one);
@@ -422,60 +314,107 @@ B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
 // ---------------------------------------------------------------------------------------------
 // noinline slot primitives
 // ---------------------------------------------------------------------------------------------
-B381_NOINL void f2_mul(u4* r, const u4* a, const u4* b) {
-  Fp a0, a1, b0, b1, r0, r1;
-  ld_f2(a0, a1, a);
-  ld_f2(b0, b1, b);
-  f2_mul_reg(r0, r1, a0, a1, b0, b1);
-  st_f2(r, r0, r1);
+// Pre- / post-operations of the multiplication primitives.  A linear operation on a slot (load, a few carry
+// chains, weak reduction, store, plus a call and a barrier) costs about a twelfth of a three-product sum while
+// using the multiplier pipe hardly at all, so the hot paths (ARK Miller loop, Fp12 products) fold their
+// additions, differences, halvings, triplings and xi-multiplications into the operand loads and result
+// stores of the multiplications they feed.  All bounds (operands below 2^384 and non-negative, results
+// non-negative) are asserted by the bound tracker on the host simulation.
+enum PreOp {
+  PRE_NONE = 0,
+  PRE_ADD,        // a + a2, weak-reduced (any two stored values)
+  PRE_ADD_RAW,    // a + a2 as is (caller guarantees the sums stay below what the product takes)
+  PRE_SUB3P,      // a - a2 + 3 p          (a2 at most 3 p)
+  PRE_HALFSUM,    // (a + a2) / 2
+  PRE_NEG3P,      // 3 p - a               (a at most 3 p)
+};
+enum PostOp {
+  POST_NONE = 0,
+  POST_HALF,      // r / 2
+  POST_TRIPLE,    // 3 r   (below 6.1 p: feeds an Fp-scalar product or a POST_SUB1)
+  POST_SUB1,      // r - p1, weak-reduced
+  POST_SUB2,      // r - p1 - p2, weak-reduced
+};
+
+B381_DEV B381_INL void f2_pre(Fp& a0, Fp& a1, const u4* a2, int pre) {
+  if (pre == PRE_NONE) return;
+  if (pre == PRE_NEG3P) {
+    fp_neg(a0, a0); fp_neg(a1, a1);
+    fp_add_p3(a0, a0); fp_add_p3(a1, a1);
+    return;
+  }
+  Fp t0, t1;
+  ld_f2(t0, t1, a2);
+  if (pre == PRE_SUB3P) {
+    fp_sub(a0, a0, t0); fp_sub(a1, a1, t1);
+    fp_add_p3(a0, a0); fp_add_p3(a1, a1);
+    return;
+  }
+  fp_add(a0, a0, t0); fp_add(a1, a1, t1);
+  if (pre == PRE_ADD) { fp_wreduce(a0); fp_wreduce(a1); }
+  if (pre == PRE_HALFSUM) { fp_half(a0, a0); fp_half(a1, a1); }
 }
 
+B381_DEV B381_INL void f2_post(Fp& r0, Fp& r1, int post, const u4* p1, const u4* p2) {
+  if (post == POST_NONE) return;
+  if (post == POST_HALF) { fp_half(r0, r0); fp_half(r1, r1); return; }
+  if (post == POST_TRIPLE) {
+    Fp t;
+    fp_dbl(t, r0); fp_add(r0, r0, t);
+    fp_dbl(t, r1); fp_add(r1, r1, t);
+    return;
+  }
+  Fp x0, x1;
+  ld_f2(x0, x1, p1);
+  fp_sub(r0, r0, x0); fp_sub(r1, r1, x1);
+  if (post == POST_SUB2) {
+    ld_f2(x0, x1, p2);
+    fp_sub(r0, r0, x0); fp_sub(r1, r1, x1);
+  }
+  fp_wreduce(r0); fp_wreduce(r1);
+}
+
+// r = post( pre_a(a, a2) * pre_b(b, b2) )
+B381_NOINL void f2_mul_ex(u4* r, const u4* a, const u4* a2, int pre_a, const u4* b, const u4* b2, int pre_b, int post, const u4* p1, const u4* p2) {
+  Fp a0, a1, b0, b1, r0, r1;
+  ld_f2(a0, a1, a);
+  f2_pre(a0, a1, a2, pre_a);
+  ld_f2(b0, b1, b);
+  f2_pre(b0, b1, b2, pre_b);
+  f2_mul_reg(r0, r1, a0, a1, b0, b1);
+  f2_post(r0, r1, post, p1, p2);
+  st_f2(r, r0, r1);
+}
+B381_DEV B381_INL void f2_mul(u4* r, const u4* a, const u4* b) { f2_mul_ex(r, a, nullptr, PRE_NONE, b, nullptr, PRE_NONE, POST_NONE, nullptr, nullptr); }
 // r = (a + a2) * (b + b2); a2 / b2 may be null
-B381_NOINL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u4* b2) {
-  Fp a0, a1, b0, b1, r0, r1;
-  ld_f2(a0, a1, a);
-  if (a2) {
-    Fp t0, t1;
-    ld_f2(t0, t1, a2);
-    fp_add(a0, a0, t0); fp_add(a1, a1, t1);
-    f2_norm(a0, a1);
-#if B381_FMT == 32 && B381_W12
-    fp_wreduce(a0); fp_wreduce(a1);
-#endif
-  }
-  ld_f2(b0, b1, b);
-  if (b2) {
-    Fp t0, t1;
-    ld_f2(t0, t1, b2);
-    fp_add(b0, b0, t0); fp_add(b1, b1, t1);
-    f2_norm(b0, b1);
-#if B381_FMT == 32 && B381_W12
-    fp_wreduce(b0); fp_wreduce(b1);
-#endif
-  }
-  f2_mul_reg(r0, r1, a0, a1, b0, b1);
-  st_f2(r, r0, r1);
+B381_DEV B381_INL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, const u4* b2) {
+  f2_mul_ex(r, a, a2, a2 ? PRE_ADD : PRE_NONE, b, b2, b2 ? PRE_ADD : PRE_NONE, POST_NONE, nullptr, nullptr);
 }
 
-// Sum of products with ONE reduction per coefficient:  r = sum_{i<n} a_i * b_i  (n <= 3).
-//   P = sum a_i0 b_i0,  Q = sum a_i1 b_i1;   re = P - Q;   im = sum (a_i0+a_i1)(b_i0+b_i1) - P - Q
-// 3n MAC blocks + 2 reductions instead of n Fp2 multiplications (3n blocks + 2n reductions) followed
-// by memory-to-memory additions: the row-serial Montgomery reduction is the expensive half of a
-// multiplication, so the tower formulas are arranged as sums of products.
-// Column bound: limbs 0..12 of every stored value are non-negative, hence every partial sum of
-// -(P+Q) + sum_i (a_i0+a_i1)(b_i0+b_i1) lies between -(P+Q) and the final value
-// sum_i (a_i0 b_i1 + a_i1 b_i0), i.e. within 28 n units of 2^56, plus the (signed, tiny) products
-// of the top limbs, which the bound tracker adds from the operand magnitudes.
-#if B381_FMT == 32
-// r = a0 b0 + a1 b1 + a2 b2 in Fp2 (n = 3 only: the tower code uses nothing else), Karatsuba over
-// the SUMS: P = sum a_i0 b_i0, Q = sum a_i1 b_i1, X = sum (a_i0 + a_i1)(b_i0 + b_i1), each one fused
-// three-product accumulation (acc_mul3); re = P - Q (+ p), im = X - P - Q.
-B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
-  (void)n;
+// Sum of three products with ONE reduction per coefficient:  r = a0 b0 + a1 b1 + a2 b2  in Fp2.
+// Karatsuba over the SUMS: P = sum a_i0 b_i0, Q = sum a_i1 b_i1, X = sum (a_i0 + a_i1)(b_i0 + b_i1), each one
+// fused three-product accumulation (acc_mul3); re = P - Q (+ p), im = X - P - Q: 9 MAC blocks + 2 reductions
+// instead of 3 Fp2 multiplications (9 blocks + 6 reductions) followed by memory-to-memory additions -- the
+// row-serial Montgomery reduction is the expensive half of a multiplication, so the
+// tower formulas are arranged as sums of products.
+// flags: SOP_XIk multiplies b_k by xi = 1 + u while it sits in registers, (b0 - b1 + 3 p, b0 + b1): b_k must be a
+// stored value with b0 < 3.4 p and b1 <= 3 p (tracker-asserted through the 12-word products); SOP_DBL doubles
+// the result in the double-width domain (2 a b of the Fp12 squaring).
+enum SopFlags { SOP_XI0 = 1, SOP_XI1 = 2, SOP_XI2 = 4, SOP_DBL = 8 };
+B381_DEV B381_INL void f2_xi_pos(Fp& b0, Fp& b1) {
+  Fp d;
+  fp_sub(d, b0, b1);
+  fp_add(b1, b0, b1);
+  fp_add_p3(b0, d);
+}
+B381_NOINL void f2_sop(u4* r, int flags, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
   Fp x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1;
   ld_f2(x0, x1, a0p); ld_f2(u0, u1, b0p);
   ld_f2(y0, y1, a1p); ld_f2(v0, v1, b1p);
   ld_f2(z0, z1, a2p); ld_f2(w0, w1, b2p);
+  if (flags & SOP_XI0) f2_xi_pos(u0, u1);
+  if (flags & SOP_XI1) f2_xi_pos(v0, v1);
+  if (flags & SOP_XI2) f2_xi_pos(w0, w1);
   Acc P, Q, X;
   HOT_MUL3(P, x0, u0, y0, v0, z0, w0);
   HOT_MUL3(Q, x1, u1, y1, v1, z1, w1);
@@ -487,73 +426,30 @@ B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p
   acc_sub(X, X, Q);                                 // im = sum (a_i0 b_i1 + a_i1 b_i0) >= 0
   B381_TB(X.cb = 0;)
   acc_sub(P, P, Q);                                 // re
+  if (flags & SOP_DBL) { acc_dbl(P); acc_dbl(X); }
   Fp r0, r1;
   acc_redc2(r0, P, r1, X);
   fp_add_p(r0, r0);
   st_f2(r, r0, r1);
 }
-#else
-B381_NOINL void f2_sop(u4* r, int n, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
-  Acc P, Q;
-  acc_zero(P); acc_zero(Q);
-  B381_TB(double slack = 0;)
-  for (int i = 0; i < n; i++) {
-    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
-    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
-    Fp a0, a1, b0, b1;
-    ld_f2(a0, a1, ap);
-    ld_f2(b0, b1, bp);
-    acc_mac(P, a0, b0);
-    acc_mac(Q, a1, b1);
-    B381_TB(slack += 2 * 3.97e-4 * ((a0.mag + a1.mag + 2) * 2 + (b0.mag + b1.mag + 2) * 2) + 0.01;)
-  }
-#pragma unroll
-  for (int k = 0; k < 2 * NL - 1; k++) {
-    const int64_t x = P.c[k], y = Q.c[k];
-    P.c[k] = x - y;                                 // re
-    Q.c[k] = -x - y;
-  }
-  B381_TB(P.cb = P.cb + Q.cb; Q.cb = P.cb; P.mag = P.mag + Q.mag; Q.mag = P.mag;)
-  for (int i = 0; i < n; i++) {
-    const u4* ap = i == 0 ? a0p : (i == 1 ? a1p : a2p);
-    const u4* bp = i == 0 ? b0p : (i == 1 ? b1p : b2p);
-    Fp a0, a1, b0, b1, sa, sb;
-    ld_f2(a0, a1, ap);
-    ld_f2(b0, b1, bp);
-    fp_add(sa, a0, a1);
-    fp_add(sb, b0, b1);
-    acc_mac_cross(Q, sa, sb);
-  }
-  B381_TB(Q.cb = 28.0 * n + slack;)                 // see the bound argument above
-  B381_CHECK(28.0 * n + slack + 16.0 < 127.0, "f2_sop: column bound");
-  Fp r0, r1;
-  acc_redc2(r0, P, r1, Q);
-  st_f2(r, r0, r1);
-}
 
-#endif
-
-// r = (a + a2)^2 ; a2 may be null
-B381_NOINL void f2_sqr(u4* r, const u4* a, const u4* a2) {
+// r = post( pre(a, a2)^2 )
+B381_NOINL void f2_sqr_ex(u4* r, const u4* a, const u4* a2, int pre, int post, const u4* p1, const u4* p2) {
   Fp a0, a1, r0, r1;
   ld_f2(a0, a1, a);
-  if (a2) {
-    Fp t0, t1;
-    ld_f2(t0, t1, a2);
-    fp_add(a0, a0, t0); fp_add(a1, a1, t1);
-    f2_norm(a0, a1);
-#if B381_FMT == 32 && B381_W12
-    fp_wreduce(a0); fp_wreduce(a1);                 // a sum of two stored values may exceed what the 12-word squaring takes
-#endif
-  }
+  f2_pre(a0, a1, a2, pre);
   f2_sqr_reg(r0, r1, a0, a1);
+  f2_post(r0, r1, post, p1, p2);
   st_f2(r, r0, r1);
 }
+// r = (a + a2)^2 ; a2 may be null
+B381_DEV B381_INL void f2_sqr(u4* r, const u4* a, const u4* a2) { f2_sqr_ex(r, a, a2, a2 ? PRE_ADD : PRE_NONE, POST_NONE, nullptr, nullptr); }
 
-// r = a * s where s is half h of slot sp (an Fp scalar): 2 x 196 + 2 x 225 IMAD
-B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h) {
+// r = (neg ? 3 p - a : a) * s where s is half h of slot sp (an Fp scalar)
+B381_NOINL void f2_mulfp(u4* r, const u4* a, const u4* sp, int h, int neg = 0) {
   Fp a0, a1, s, r0, r1;
   ld_f2(a0, a1, a);
+  if (neg) f2_pre(a0, a1, nullptr, PRE_NEG3P);
   ld_fp(s, sp, h);
   f2_mulfp_reg(r0, r1, a0, a1, s);
   st_f2(r, r0, r1);
@@ -565,9 +461,7 @@ B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
   ld_f2(a0, a1, a);
   if (conj) {
     fp_neg(a1, a1); fp_norm(a1);
-#if B381_FMT == 32
     HOT_OFF(a1, a1);                                // -a1 + 5 p (or 128 p): non-negative, same residue
-#endif
   }
   fp_const(g0, g_ct.frob[k - 1][j - 1][0]);
   fp_const(g1, g_ct.frob[k - 1][j - 1][1]);
@@ -592,9 +486,7 @@ B381_NOINL void f2_inv(u4* r, const u4* a) {
   fp_mul(r0, a0, ni);
   fp_neg(a1, a1);
   fp_norm(a1);
-#if B381_FMT == 32
   fp_add_p128(a1, a1);
-#endif
   fp_mul(r1, a1, ni);
   st_f2(r, r0, r1);
 }
@@ -673,7 +565,6 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
       fp_dbl(r0, a0); fp_dbl(r0, r0); fp_dbl(r1, a1); fp_dbl(r1, r1);
       break;
   }
-#if B381_FMT == 32
   // stored values must be non-negative: the weak reduction (output in [0, 11 p)) where a difference occurs
   // ... and (B381_W12) wherever the result could exceed 5 p, so that it fits the 12-word multiplications
   const bool grow = (B381_W12 && (op == L_TRIPLE || op == L_MUL4 || op == L_MUL8 || op == L_MUL12XI || op == L_XIADD)) || op == L_ADD_R;
@@ -681,10 +572,6 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
   const bool n1 = grow || op == L_SUB || op == L_NEG || op == L_CONJ || op == L_3A_M2B || op == L_3A_P2B || op == L_2A_MB;
   if (n0) fp_wreduce(r0);
   if (n1) fp_wreduce(r1);
-#else
-  if (op == L_3A_M2B || op == L_3A_P2B) { fp_wreduce(r0); fp_wreduce(r1); }   // linear feedback of b (cyclotomic squaring)
-  else f2_norm(r0, r1);
-#endif
   st_f2(r, r0, r1);
 }
 
@@ -693,11 +580,25 @@ B381_NOINL void f2_lin(u4* r, const u4* a, const u4* b, int op) {
 //   K_XI_INNER  r = xi t + d
 //   K_XI_D      r = t + xi d
 //   K_XI_C      r = a - b - xi c  (+ d)
-enum KOp { K_PLAIN = 0, K_XI_INNER, K_XI_D, K_XI_C };
+//   K_HALFSUB    r = a - (b + c) / 2        (Fp12 squaring with 2ab in hand: c0 = s u - (2ab + v 2ab) / 2)
+//   K_HALFSUB_XI r = a - (b + xi c) / 2
+enum KOp { K_PLAIN = 0, K_XI_INNER, K_XI_D, K_XI_C, K_HALFSUB, K_HALFSUB_XI };
 
 B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4* d, int mode) {
   Fp t0, t1, x0, x1;
   ld_f2(t0, t1, a);
+  if (mode == K_HALFSUB || mode == K_HALFSUB_XI) {
+    Fp y0, y1;
+    ld_f2(x0, x1, b);
+    ld_f2(y0, y1, c);
+    if (mode == K_HALFSUB_XI) f2_mulxi_reg(y0, y1, y0, y1);
+    fp_add(x0, x0, y0); fp_add(x1, x1, y1);
+    fp_half(x0, x0); fp_half(x1, x1);
+    fp_sub(t0, t0, x0); fp_sub(t1, t1, x1);
+    fp_wreduce(t0); fp_wreduce(t1);
+    st_f2(r, t0, t1);
+    return;
+  }
   if (b) { ld_f2(x0, x1, b); fp_sub(t0, t0, x0); fp_sub(t1, t1, x1); }
   if (c) {
     ld_f2(x0, x1, c);
@@ -711,10 +612,27 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
     fp_add(t0, t0, x0); fp_add(t1, t1, x1);
   }
   f2_norm(t0, t1);
-#if B381_FMT == 32
   fp_wreduce(t0); fp_wreduce(t1);
-#endif
   st_f2(r, t0, t1);
+}
+
+// The three linear values of the ARK doubling step (ark-ec g2.rs double_in_place) in one pass:
+//   e = 12 xi c  (= COEFF_B * 3c),   i = e - b,   f = 3 e      all weak-reduced
+B381_NOINL void f2_dbl_lin3(u4* re, u4* ri, u4* rf, const u4* c, const u4* b) {
+  Fp c0, c1, b0, b1, t0, t1, e0, e1, x0, x1;
+  ld_f2(c0, c1, c);
+  ld_f2(b0, b1, b);
+  fp_dbl(t0, c0); fp_add(t0, t0, c0); fp_dbl(t1, c1); fp_add(t1, t1, c1);   // 3c
+  fp_dbl(t0, t0); fp_dbl(t0, t0); fp_dbl(t1, t1); fp_dbl(t1, t1);           // 12c
+  f2_mulxi_reg(e0, e1, t0, t1);
+  fp_wreduce(e0); fp_wreduce(e1);
+  st_f2(re, e0, e1);
+  fp_sub(x0, e0, b0); fp_sub(x1, e1, b1);
+  fp_wreduce(x0); fp_wreduce(x1);
+  st_f2(ri, x0, x1);
+  fp_dbl(x0, e0); fp_add(x0, x0, e0); fp_dbl(x1, e1); fp_add(x1, x1, e1);
+  fp_wreduce(x0); fp_wreduce(x1);
+  st_f2(rf, x0, x1);
 }
 
 // Fused step of the Granger-Scott cyclotomic squaring (/root/reference/src/fields_as_trees/miller_loop.rs:29-104):
@@ -726,7 +644,6 @@ B381_NOINL void f2_kcomb(u4* r, const u4* a, const u4* b, const u4* c, const u4*
 // squarings (6 x 196 + 6 x 225) plus seven memory-to-memory linear operations.  The linear feedback
 // of z (magnitude M -> 9 + 2M) is absorbed by the weak reduction when `reduce` is set; callers set it
 // at least every sixth squaring (2 -> 13 -> 35 -> 79 -> 167 -> 343 stays far below the 14-limb range).
-#if B381_FMT == 32 && B381_W12 && !defined(B381_CYC7)
 // Six-product form: with A = a^2 = (PA, QA), B = b^2 = (PB, QB), C = (a + b)^2 = (PC, QC), where
 // P = (x0 + x1)(x0 - x1 + 5p) and Q = 2 x0 x1 for x = (x0, x1):
 //   t0 = a^2 + xi b^2 = (PA + PB - QB, QA + PB + QB);   t1 = 2ab = (PC - PA - PB, QC - QA - QB)
@@ -792,105 +709,6 @@ B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* z
   fp_wreduce(x0); fp_wreduce(x1);
   st_f2(mode == 0 ? rb : ra, x0, x1);
 }
-#elif B381_FMT == 32
-B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
-  Fp a0, a1, b0, b1, t00, t01, t10, t11;
-  ld_f2(a0, a1, a);
-  ld_f2(b0, b1, b);
-  {
-    // t0 = a^2 + xi b^2:  re = PA + (PB - QB) ; im = QA + (PB + QB)   with
-    // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
-    Fp s, d, e;
-    Acc X, Y, U;
-    fp_add(s, b0, b1); fp_sub(d, b0, b1); HOT_OFF(d, d);
-    HOT_MUL(X, s, d);                               // PB
-    fp_dbl(e, b0);
-    HOT_MUL(U, e, b1);                              // QB
-    acc_add(Y, X, U);                               // PB + QB
-    acc_sub(X, X, U);                               // PB - QB
-    fp_add(s, a0, a1); fp_sub(d, a0, a1); HOT_OFF(d, d);
-    HOT_MAC(X, s, d);                               // + PA
-    fp_dbl(e, a0);
-    HOT_MAC(Y, e, a1);                              // + QA
-    acc_redc2(t00, X, t01, Y);
-  }
-  // In this format every output goes through the weak reduction (it also makes the value
-  // non-negative, which the unsigned multiplications require); `reduce` is ignored.
-  (void)reduce;
-  Fp z0, z1;
-  {
-    const u4* zt0 = mode == 0 ? za : zb;
-    if (zt0 == a) { z0 = a0; z1 = a1; } else ld_f2(z0, z1, zt0);
-    Fp w0, w1;
-    fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
-    fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
-    fp_wreduce(w0); fp_wreduce(w1);
-    st_f2(mode == 0 ? ra : rb, w0, w1);
-  }
-  f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
-  const u4* zt1 = mode == 0 ? zb : za;
-  if (zt1 == b) { z0 = b0; z1 = b1; } else ld_f2(z0, z1, zt1);
-  if (mode == 1) f2_mulxi_reg(t10, t11, t10, t11);
-  Fp x0, x1;
-  fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
-  fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
-  fp_wreduce(x0); fp_wreduce(x1);
-  fp_dbl(x0, x0); fp_dbl(x1, x1);
-  st_f2(mode == 0 ? rb : ra, x0, x1);
-}
-#else
-B381_NOINL void f2_cyc_fp4(u4* ra, u4* rb, const u4* a, const u4* b, const u4* za, const u4* zb, int mode, int reduce) {
-  Fp a0, a1, b0, b1, t00, t01, t10, t11;
-  ld_f2(a0, a1, a);
-  ld_f2(b0, b1, b);
-  {
-    // t0 = a^2 + xi b^2:  re = PA + (PB - QB) ; im = QA + (PB + QB)   with
-    // PA = (a0+a1)(a0-a1), QA = 2 a0 a1, PB = (b0+b1)(b0-b1), QB = 2 b0 b1
-    Fp s, d, e;
-    Acc X, Y;
-    fp_add(s, b0, b1); fp_sub(d, b0, b1); fp_norm(d);
-    acc_zero(X); acc_mac(X, s, d);                  // PB
-    fp_dbl(e, b0);
-    acc_zero(Y); acc_mac(Y, e, b1);                 // QB
-#pragma unroll
-    for (int k = 0; k < 2 * NL - 1; k++) {
-      const int64_t x = X.c[k], y = Y.c[k];
-      X.c[k] = x - y;
-      Y.c[k] = x + y;
-    }
-    B381_TB(X.cb = X.cb + Y.cb; Y.cb = X.cb; X.mag = X.mag + Y.mag; Y.mag = X.mag;)
-    fp_add(s, a0, a1); fp_sub(d, a0, a1); fp_norm(d);
-    acc_mac(X, s, d);                               // + PA
-    fp_dbl(e, a0);
-    acc_mac(Y, e, a1);                              // + QA
-    acc_redc2(t00, X, t01, Y);
-  }
-  Fp z0, z1;
-  {
-    // outputs built from t0: 3 t0 - 2 z, stored at once so t0 is dead before the a*b product starts
-    const u4* zt0 = mode == 0 ? za : zb;
-    if (zt0 == a) { z0 = a0; z1 = a1; } else ld_f2(z0, z1, zt0);
-    Fp w0, w1;
-    fp_sub(w0, t00, z0); fp_dbl(w0, w0); fp_add(w0, w0, t00);
-    fp_sub(w1, t01, z1); fp_dbl(w1, w1); fp_add(w1, w1, t01);
-    if (reduce) { fp_wreduce(w0); fp_wreduce(w1); } else f2_norm(w0, w1);
-    st_f2(mode == 0 ? ra : rb, w0, w1);
-  }
-  f2_mul_reg(t10, t11, a0, a1, b0, b1);             // a b  (t1 = 2 a b is folded into the combination)
-  // outputs built from t1 = 2ab:  3 t1 + 2 z = 2 (3 ab + z)   or   3 xi t1 + 2 z = 2 (3 xi ab + z)
-  const u4* zt1 = mode == 0 ? zb : za;
-  if (zt1 == b) { z0 = b0; z1 = b1; } else ld_f2(z0, z1, zt1);
-  if (mode == 1) f2_mulxi_reg(t10, t11, t10, t11);
-  Fp x0, x1;
-  fp_dbl(x0, t10); fp_add(x0, x0, t10); fp_add(x0, x0, z0);
-  fp_dbl(x1, t11); fp_add(x1, x1, t11); fp_add(x1, x1, z1);
-  if (reduce) { fp_wreduce(x0); fp_wreduce(x1); } else f2_norm(x0, x1);
-  fp_dbl(x0, x0); fp_dbl(x1, x1);
-  f2_norm(x0, x1);
-  st_f2(mode == 0 ? rb : ra, x0, x1);
-}
-
-#endif
 
 // set slot to the Fp2 constant (one, 0) or (0, 0)
 B381_NOINL void f2_set_small(u4* r, int one) {
@@ -969,9 +787,17 @@ B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2
   sync_point(cx);
   f2_mul_ss(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, S_(b), b2 >= 0 ? S_(b2) : nullptr);
 }
-B381_DEV B381_INL void sop3(const Ctx& cx, int r, int a0, int b0, int a1, int b1, int a2, int b2) {
+B381_DEV B381_INL void sop3(const Ctx& cx, int r, int a0, int b0, int a1, int b1, int a2, int b2, int flags = 0) {
   sync_point(cx);
-  f2_sop(S_(r), 3, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2));
+  f2_sop(S_(r), flags, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2));
+}
+B381_DEV B381_INL void mul_ex(const Ctx& cx, int r, int a, int b, int b2, int pre_b, int post, int p1 = -1, int p2 = -1) {
+  sync_point(cx);
+  f2_mul_ex(S_(r), S_(a), nullptr, PRE_NONE, S_(b), b2 >= 0 ? S_(b2) : nullptr, pre_b, post, p1 >= 0 ? S_(p1) : nullptr, p2 >= 0 ? S_(p2) : nullptr);
+}
+B381_DEV B381_INL void sqr_ex(const Ctx& cx, int r, int a, int a2, int pre, int post, int p1 = -1, int p2 = -1) {
+  sync_point(cx);
+  f2_sqr_ex(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, pre, post, p1 >= 0 ? S_(p1) : nullptr, p2 >= 0 ? S_(p2) : nullptr);
 }
 B381_DEV B381_INL void sqr(const Ctx& cx, int r, int a) { sync_point(cx); f2_sqr(S_(r), S_(a), nullptr); }
 B381_DEV B381_INL void sqr_s(const Ctx& cx, int r, int a, int a2) { sync_point(cx); f2_sqr(S_(r), S_(a), S_(a2)); }
@@ -993,6 +819,15 @@ B381_DEV B381_INL void f6_mul(const Ctx& cx, int r, int a, int b, int t) {
   sop3(cx, r + 2, a, b + 2, a + 1, b + 1, a + 2, b);
 }
 
+// The same product with the two xi-multiplications folded into the operand loads of the sums (no scratch, no
+// linear passes); b1, b2 must satisfy the SOP_XI bounds (single stored values, or weak-reduced sums).  dbl: 2 a b.
+B381_DEV B381_INL void f6_mul_x(const Ctx& cx, int r, int a, int b, int dbl = 0) {
+  const int d = dbl ? SOP_DBL : 0;
+  sop3(cx, r, a, b, a + 1, b + 2, a + 2, b + 1, SOP_XI1 | SOP_XI2 | d);
+  sop3(cx, r + 1, a, b + 1, a + 1, b, a + 2, b + 2, SOP_XI2 | d);
+  sop3(cx, r + 2, a, b + 2, a + 1, b + 1, a + 2, b, d);
+}
+
 // Fp6 squaring via f6_mul-style Karatsuba with squarings (3 sqr + 3 mul)
 B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
   const int v0 = t, v1 = t + 1, v2 = t + 2, m = t + 3;
@@ -1008,16 +843,18 @@ B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
 }
 
 // Fp12 multiplication r = a * b (3 Fp6 muls); fq12_target_tree.rs:130-141.
-// r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 8 slots (sa, sb, 2 for f6_mul).
+// r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 6 slots (sa, sb).  The xi-multiplications of the
+// Fp6 products are folded into the sums of products (f6_mul_x): b and a + 3.. are stored values, the two
+// coefficients of sb that get multiplied by xi are weak-reduced sums.
 B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
-  const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3, w = t2 + 6;   // w: 2 slots
-  f6_mul(cx, aa, a, b, w);
-  f6_mul(cx, bb, a + 3, b + 3, w);
+  const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3;
+  f6_mul_x(cx, aa, a, b);
+  f6_mul_x(cx, bb, a + 3, b + 3);
   for (int i = 0; i < 3; i++) {
     lin(cx, sa + i, a + i, a + 3 + i, L_ADD);
-    lin(cx, sb + i, b + i, b + 3 + i, L_ADD);
+    lin(cx, sb + i, b + i, b + 3 + i, i == 0 ? L_ADD : L_ADD_R);
   }
-  f6_mul(cx, r + 3, sa, sb, w);                   // (a0+a1)(b0+b1)   (a, b dead from here on)
+  f6_mul_x(cx, r + 3, sa, sb);                    // (a0+a1)(b0+b1)   (a, b dead from here on)
   for (int i = 0; i < 3; i++) kcomb(cx, r + 3 + i, r + 3 + i, aa + i, bb + i, -1, K_PLAIN);
   lin(cx, r, aa, bb + 2, L_XIADD);                // c0 = aa + v bb ; v bb = (xi bb2, bb0, bb1)
   lin(cx, r + 1, aa + 1, bb, L_ADD_R);
@@ -1061,6 +898,34 @@ B381_DEV void f12_mul_by_014(const Ctx& cx, int f, int c0, int c1, int c4, int t
   sop3(cx, t + 4, b0, c1, b1, c0, a0, c4);
   sop3(cx, t + 5, b1, c1, b2, c0, a1, c4);
   for (int i = 0; i < 6; i++) lin(cx, f + i, t + i, -1, L_COPY);
+}
+
+// Fp12 complex squaring OUT OF PLACE, d = f^2 (d, f distinct slot ranges), for the ARK Miller loops:
+//   c1 = 2 a0 a1 straight from the sums (SOP_DBL) into d + 3..5;  c0 = (a0 + a1)(a0 + v a1) - (c1 + v c1) / 2.
+// Six linear passes (s, u) and three recombinations instead of fourteen and three.  s3, t: 3 scratch slots each.
+B381_DEV void f12_sqr_oop(const Ctx& cx, int d, int f, int t, int s3) {
+  const int s = s3, u = t;
+  for (int i = 0; i < 3; i++) lin(cx, s + i, f + i, f + 3 + i, L_ADD);      // s = a0 + a1
+  lin(cx, u, f, f + 5, L_XIADD);                  // u = a0 + v a1 = (a00 + xi a12, a01 + a10, a02 + a11), weak-reduced
+  lin(cx, u + 1, f + 1, f + 3, L_ADD_R);
+  lin(cx, u + 2, f + 2, f + 4, L_ADD_R);
+  f6_mul_x(cx, d + 3, f + 3, f, 1);               // c1 = 2 a1 a0
+  f6_mul_x(cx, d, s, u);                          // s u
+  kcomb(cx, d, d, d + 3, d + 5, -1, K_HALFSUB_XI);     // c0 = s u - (c1 + v c1) / 2 ; v c1 = (xi c12, c10, c11)
+  kcomb(cx, d + 1, d + 1, d + 4, d + 3, -1, K_HALFSUB);
+  kcomb(cx, d + 2, d + 2, d + 5, d + 4, -1, K_HALFSUB);
+}
+
+// sparse multiplication d = f * (c0 + c1 v + c4 v w) OUT OF PLACE, xi c1 and xi c4 formed in registers:
+// six sums of three products and nothing else.  c1, c4 are Fp-scalar products (below 1.03 p).
+B381_DEV void f12_mul_by_014_oop(const Ctx& cx, int d, int f, int c0, int c1, int c4) {
+  const int a0 = f, a1 = f + 1, a2 = f + 2, b0 = f + 3, b1 = f + 4, b2 = f + 5;
+  sop3(cx, d + 0, a0, c0, a2, c1, b1, c4, SOP_XI1 | SOP_XI2);
+  sop3(cx, d + 1, a0, c1, a1, c0, b2, c4, SOP_XI2);
+  sop3(cx, d + 2, a1, c1, a2, c0, b0, c4);
+  sop3(cx, d + 3, b0, c0, b2, c1, a2, c4, SOP_XI1 | SOP_XI2);
+  sop3(cx, d + 4, b0, c1, b1, c0, a0, c4);
+  sop3(cx, d + 5, b1, c1, b2, c0, a1, c4);
 }
 
 B381_DEV B381_INL void f12_set_one(const Ctx& cx, int f) {
@@ -1200,65 +1065,102 @@ B381_DEV B381_INL void ark_ell(const Ctx& cx, int f, int L, int Pt, int t) {
   f12_mul_by_014(cx, f, L, L + 1, L + 2, t);
 }
 
+// The doubling step with its linear operations folded into the multiplications (same values as
+// ark_double_step; coefficients (i, 3j, h) -- the sign of h is applied by ark_ell_oop's scalar product).
+// 9 multiplication primitives + 1 linear pass instead of 9 + 11.  t = 5 scratch slots (t + 3 unused).
+B381_DEV void ark_double_step_fused(const Ctx& cx, int R, int L, int t) {
+  const int X = R, Y = R + 1, Z = R + 2, T0 = t, T1 = t + 1, T2 = t + 2, T4 = t + 4;
+  mul_ex(cx, T0, X, Y, -1, PRE_NONE, POST_HALF);                   // a = X Y / 2
+  sqr(cx, T1, Y);                                                  // b = Y^2
+  sqr(cx, T2, Z);                                                  // c = Z^2
+  sqr_ex(cx, L + 1, X, -1, PRE_NONE, POST_TRIPLE);                 // 3 j = 3 X^2
+  sqr_ex(cx, L + 2, Y, Z, PRE_ADD_RAW, POST_SUB2, T1, T2);         // h = (Y+Z)^2 - (b + c)
+  sync_point_lin(cx);
+  f2_dbl_lin3(S_(T2), S_(L), S_(T4), S_(T2), S_(T1));              // e = 12 xi c ; i = e - b ; f = 3 e
+  mul_ex(cx, X, T0, T1, T4, PRE_SUB3P, POST_NONE);                 // X' = a (b - f)
+  mul(cx, Z, T1, L + 2);                                           // Z' = b h
+  sqr_ex(cx, T2, T2, -1, PRE_NONE, POST_TRIPLE);                   // 3 e^2
+  sqr_ex(cx, Y, T1, T4, PRE_HALFSUM, POST_SUB1, T2);               // Y' = ((b + f) / 2)^2 - 3 e^2
+}
+
+// ell, out of place: d = f * line;  c2 *= py (negated first when the step left h instead of -h), c1 *= px
+B381_DEV B381_INL void ark_ell_oop(const Ctx& cx, int d, int f, int L, int Pt, int neg2) {
+  sync_point(cx);
+  f2_mulfp(S_(L + 2), S_(L + 2), S_(Pt), 1, neg2);
+  f2_mulfp(S_(L + 1), S_(L + 1), S_(Pt), 0);
+  f12_mul_by_014_oop(cx, d, f, L, L + 1, L + 2);
+}
+
 // slot plan shared by the Miller-loop kernels
 struct MillerSlots { int f, L, T, R, Q, P; };
-
-// Bls12::multi_miller_loop for one pair: f = 1; per bit: f = f^2; ell(double);
-// if bit: ell(add); finally conjugate (x < 0).  Q (affine) at slots (Q, Q+1), P at slot P,
-// R scratch at (R..R+2).  T = 10 scratch slots.
-B381_DEV void ark_miller_loop(const Ctx& cx, const MillerSlots& s) {
-  f12_set_one(cx, s.f);
-  lin(cx, s.R, s.Q, -1, L_COPY);
-  lin(cx, s.R + 1, s.Q + 1, -1, L_COPY);
-  f2_set_small(S_(s.R + 2), 1);
-  const uint64_t xabs = B381_X_ABS;
-  for (int b = 62; b >= 0; b--) {
-    if (b != 62) f12_sqr(cx, s.f, s.T, s.L);      // first squaring is 1^2
-    ark_double_step(cx, s.R, s.L, s.T);
-    ark_ell(cx, s.f, s.L, s.P, s.T);
-    if ((xabs >> b) & 1) {
-      ark_add_step(cx, s.R, s.Q, s.L, s.T);
-      ark_ell(cx, s.f, s.L, s.P, s.T);
-    }
-  }
-  f12_conj(cx, s.f);
-}
-
-// Multi-Miller loop with SHARED squarings (ark Bls12::multi_miller_loop squares f once per bit for
-// a whole chunk of pairs): k pairs per thread accumulate into one f.  Pair j uses
-// R at s.R + 6 j? no: slot bases are given per pair.  A pair flagged as identity multiplies by the
-// line (1, 0, 0), i.e. by one, so control flow stays uniform.
-struct MultiSlots { int f, L, T; int R[2], Q[2], P[2]; };
+// Ping-pong plan of the ARK loops: f alternates between the banks A and B (every squaring and every line
+// multiplication is out of place); up to KPP pairs per thread share the squarings.  Result in A.
+constexpr int KPP = 4;
+struct MillerSlotsPP { int A, B, L, T; int R[KPP], Q[KPP], P[KPP]; };
 
 B381_DEV B381_INL void line_to_one_if(const Ctx& cx, int L, bool ident, int one_at) {
-  for (int i = 0; i < 3; i++) f2_override_if(S_(L + i), ident, i == one_at);   // uniform: L + 2 is a TMEM slot
+  for (int i = 0; i < 3; i++) f2_override_if(S_(L + i), ident, i == one_at);   // uniform: the line may sit in tensor memory
 }
 
-B381_DEV void ark_miller_loop_multi(const Ctx& cx, const MultiSlots& s, int k, const bool* ident) {
-  f12_set_one(cx, s.f);
-  for (int j = 0; j < k; j++) {
-    lin(cx, s.R[j], s.Q[j], -1, L_COPY);
-    lin(cx, s.R[j] + 1, s.Q[j] + 1, -1, L_COPY);
-    f2_set_small(S_(s.R[j] + 2), 1);
+// Bls12::multi_miller_loop for k pairs per thread with SHARED squarings (ark squares f once per
+// bit for a whole chunk of pairs): f = 1; per bit: f = f^2; ell(double) per pair; if bit:
+// ell(add) per pair; finally conjugate (x < 0).  Pair j: Q (affine) at slots (Q[j], Q[j]+1), P at P[j], running
+// point at R[j]..+2.  A pair flagged in `ident` (may be null) multiplies by the line (1, 0, 0), i.e. by one, so
+// control flow stays uniform.  T = 5 scratch slots.
+// One bit of the loop with f in bank `cur` on entry.  All bank swaps are resolved at compile time (the function
+// is inlined with constant cur / oth: runtime bank indices cost the single-pair loop 4 %): a bit does 1 + K out-of-
+// place operations, K more on an addition bit; for odd K the addition lines are followed by a copy back, so the
+// bank after the bit does not depend on the bit's value.  Returns nothing: the caller knows the parity.
+template <int K>
+B381_DEV B381_INL void ark_bit_pp(const Ctx& cx, const MillerSlotsPP& s, int cur, int oth, bool square, bool add, const bool* ident) {
+  if (square) {
+    f12_sqr_oop(cx, oth, cur, s.T, s.L);
+    const int sw = cur; cur = oth; oth = sw;
   }
-  const uint64_t xabs = B381_X_ABS;
-  for (int b = 62; b >= 0; b--) {
-    if (b != 62) f12_sqr(cx, s.f, s.T, s.L);
-    for (int j = 0; j < k; j++) {
-      ark_double_step(cx, s.R[j], s.L, s.T);
-      line_to_one_if(cx, s.L, ident[j], 0);
-      ark_ell(cx, s.f, s.L, s.P[j], s.T);
-    }
-    if ((xabs >> b) & 1) {
-      for (int j = 0; j < k; j++) {
-        ark_add_step(cx, s.R[j], s.Q[j], s.L, s.T);
-        line_to_one_if(cx, s.L, ident[j], 0);
-        ark_ell(cx, s.f, s.L, s.P[j], s.T);
-      }
-    }
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    ark_double_step_fused(cx, s.R[j], s.L, s.T);
+    if (ident) line_to_one_if(cx, s.L, ident[j], 0);
+    ark_ell_oop(cx, oth, cur, s.L, s.P[j], 1);
+    const int sw = cur; cur = oth; oth = sw;
   }
-  f12_conj(cx, s.f);
+  if (add) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      ark_add_step(cx, s.R[j], s.Q[j], s.L, s.T);
+      if (ident) line_to_one_if(cx, s.L, ident[j], 0);
+      ark_ell_oop(cx, oth, cur, s.L, s.P[j], 0);
+      const int sw = cur; cur = oth; oth = sw;
+    }
+    if (K & 1) f12_copy(cx, oth, cur);              // odd K: back to the bank a bit without addition ends in
+  }
 }
+
+template <int K>
+B381_DEV void ark_miller_loop_pp(const Ctx& cx, const MillerSlotsPP& s, const bool* ident) {
+  const uint64_t xabs = B381_X_ABS;
+  // the leading one of |x| (bit 63) is implicit; bit 62 is handled like any other, only the squaring of f = 1 is skipped
+  if (K & 1) {
+    // odd K: the first bit (no squaring) flips the bank, every later bit keeps it: start in B, live in A
+    f12_set_one(cx, s.B);
+    for (int j = 0; j < K; j++) { lin(cx, s.R[j], s.Q[j], -1, L_COPY); lin(cx, s.R[j] + 1, s.Q[j] + 1, -1, L_COPY); f2_set_small(S_(s.R[j] + 2), 1); }
+    ark_bit_pp<K>(cx, s, s.B, s.A, false, (xabs >> 62) & 1, ident);
+    for (int b = 61; b >= 0; b--) ark_bit_pp<K>(cx, s, s.A, s.B, true, (xabs >> b) & 1, ident);
+  } else {
+    // even K: the first bit keeps the bank, every later bit flips it: 62 later bits, two per iteration
+    f12_set_one(cx, s.A);
+    for (int j = 0; j < K; j++) { lin(cx, s.R[j], s.Q[j], -1, L_COPY); lin(cx, s.R[j] + 1, s.Q[j] + 1, -1, L_COPY); f2_set_small(S_(s.R[j] + 2), 1); }
+    ark_bit_pp<K>(cx, s, s.A, s.B, false, (xabs >> 62) & 1, ident);
+    for (int b = 61; b >= 0; b -= 2) {
+      ark_bit_pp<K>(cx, s, s.A, s.B, true, (xabs >> b) & 1, ident);
+      ark_bit_pp<K>(cx, s, s.B, s.A, true, (xabs >> (b - 1)) & 1, ident);
+    }
+  }
+  f12_conj(cx, s.A);
+}
+
+// slot plan of the ZK-mode two-pair loop (in-place primitives)
+struct MultiSlots { int f, L, T; int R[2], Q[2], P[2]; };
 
 // ---------------------------------------------------------------------------------------------
 // ZK mode: /root/reference/src/miller_loop_native.rs:27-116 with ell (:139-152) wired in.

@@ -126,7 +126,7 @@ int hs_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, 
     const bool has1 = i + 1 < n;
     size_t j = has1 ? i + 1 : i;
     err |= miller2_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, g1 + 24 * j, g2 + 48 * j, has1 ? (inf ? inf[j] : 0) : 3, mode);
-    f12_mul(cx, M2_ACC, M2_ACC, ML_F, ML_T, ML_T + 6);
+    f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);   // scratch: slots that are dead once the loop has left f in ML_F
   }
   f12_store_ext(cx, out, M2_ACC);
   return err;
@@ -138,7 +138,6 @@ int hs_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, int inf, uint
   return prog_miller_prepared(cx, g1, coeffs, inf, out, mode, do_fe);
 }
 
-#if B381_FMT == 32
 int hs_fp_inv(const uint32_t* a, uint32_t* out) { return prog_fp_inv(a, out); }
 int hs_fp_pow(const uint32_t* a, const uint32_t* e, int nwords, uint32_t* out) { return prog_fp_pow(a, e, nwords, out); }
 int hs_fp_is_square(const uint32_t* a, uint8_t* out) { return prog_fp_is_square(a, out); }
@@ -153,7 +152,6 @@ int hs_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* 
 int hs_g1_serialize(const uint32_t* g1, int inf, int compressed, uint8_t* out) { return prog_g1_serialize(g1, inf, compressed, out); }
 int hs_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf) { return prog_g2_deserialize(in, compressed, g2, inf); }
 int hs_g2_serialize(const uint32_t* g2, int inf, int compressed, uint8_t* out) { return prog_g2_serialize(g2, inf, compressed, out); }
-#endif
 int hs_fp12_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_inv(cx, a, out); }
 int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f6_inv(cx, a, out); }
 
