@@ -18,8 +18,21 @@
  * All functions return 0 on success, a negative B381_E_* code otherwise; they never throw or
  * unwind.  Host-pointer functions are synchronous (H2D copy, kernels, D2H copy inside the call);
  * `_dev` functions take device pointers, enqueue on `stream` (a cudaStream_t, may be NULL) and do
- * not synchronise.  One process drives one GPU (the device given to b381_init); independent
- * pairings shard across GPUs by giving each process a slice of the batch.
+ * not synchronise.
+ *
+ * Contexts and threads (SURVEY 8b "Threading").  A context owns one device's streams, staging buffers and scratch.
+ * b381_init(device) creates the process-wide default context; b381_ctx_create makes further ones (one per GPU when
+ * one process drives several GPUs) and b381_ctx_set_current binds a context to the calling host thread.  Every
+ * function below works on the calling thread's current context (the default one if none was set), takes that
+ * context's mutex and makes its device current, so calls may come from any thread; calls on DIFFERENT contexts run
+ * concurrently.  All kernels of one context share its scratch: the library orders them on the device (each call's
+ * stream waits for the previous call of the context), so `_dev` calls on different streams are safe but serialised.
+ * The device error word is per context: b381_check_dev(stream) reports (and clears) errors of every `_dev` call
+ * enqueued on the context before it.  b381_last_error() is per host thread.
+ *
+ * Points are NOT validated beyond canonical limbs (as in arkworks, curve / subgroup membership is the caller's
+ * business): use b381_g1/g2_deserialize (curve equation), b381_g1/g2_in_subgroup or b381_g1/g2_clear_cofactor on
+ * untrusted input before pairing it.
  * There is NO CPU fallback: without a CUDA device every compute call fails with B381_E_CUDA.
  */
 #ifndef B381_H
@@ -49,9 +62,15 @@ extern "C" {
 #define B381_E_NOT_SQUARE (-6)      /* sqrt of a non-residue, or of zero with sgn0 = 1 (reference: x.sqrt().unwrap() / assert_eq! panic) */
 
 /* lifecycle ------------------------------------------------------------------------------------ */
-int b381_init(int device);                  /* bind this process to one GPU, allocate scratch */
+int b381_init(int device);                  /* create the default context on one GPU, allocate scratch */
 int b381_shutdown(void);
-const char* b381_last_error(void);
+const char* b381_last_error(void);          /* last error of the calling thread; valid until that thread's next call */
+/* further contexts: one per GPU for a host that shards a batch over several GPUs from one process */
+typedef struct b381_ctx_s* b381_ctx_t;
+int b381_ctx_create(int device, b381_ctx_t* out);
+int b381_ctx_destroy(b381_ctx_t ctx);
+int b381_ctx_set_current(b381_ctx_t ctx);   /* per host thread; NULL selects the default context again */
+int b381_ctx_get_current(b381_ctx_t* out);
 int b381_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* scratch_bytes);
 /* number of kernels this library has launched since b381_init (bench.py reports it as gpu_launches) */
 unsigned long long b381_kernel_launches(void);
@@ -137,10 +156,16 @@ int b381_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t
 int b381_g1_serialize(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
 int b381_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n);
 int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n);
-/* out[i] = 1 iff [r] P_i is the identity (r = x^4 - x^2 + 1, decimal at src/miller_loop_native_optimized.rs:110):
-   the check untrusted, deserialised points need before they are paired.  Points must be on the curve. */
+/* out[i] = 1 iff P_i lies in the prime-order subgroup (order r = x^4 - x^2 + 1, decimal at
+   src/miller_loop_native_optimized.rs:110): the check untrusted, deserialised points need before they are paired.
+   Endomorphism tests of ark-bls12-381 0.4 (eprint 2021/1130): G1 (BETA x, y) == -[x^2] P, G2 psi(P) == [x] P -- two /
+   one 64-bit ladders instead of a 255-bit one; same answers as [r] P == identity.  Points must be on the curve. */
 int b381_g1_in_subgroup(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n);
 int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n);
+/* out[i] = [h_eff] P_i: maps any curve point into the subgroup (ark-bls12-381 0.4 clear_cofactor; the effective
+   cofactors of RFC 9380 section 8.8): G1 [1 - x] P, G2 Budroni-Pintore [x^2 - x - 1] P + [x - 1] psi(P) + psi^2(2P). */
+int b381_g1_clear_cofactor(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
+int b381_g2_clear_cofactor(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
 /* out[i] = [k_i] P_i (affine, + identity flag), k_i = 256-bit scalar as 8 little-endian u32 words; the group
    law is the ark-ec Jacobian add / double the reference's native loop uses (`R + R`, `R + Q`,
    src/miller_loop_native_optimized.rs:93,98).  Generates (a_i G1, b_i G2) test points and aggregates keys
@@ -148,8 +173,9 @@ int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, si
 int b381_g1_scalar_mul(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
 int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
 /* ONE point out: the sum of the n points (public-key aggregation), and sum_i [k_i] P_i (multi-scalar
-   multiplication; this version is n independent scalar multiplications + a 16-ary reduction tree on the
-   device, not yet the bucket method). */
+   multiplication).  G1: bucket method (Pippenger) over the base field -- window digits, counting sort of the point
+   indices by bucket, one thread per bucket, running-sum reduction.  G2: n scalar multiplications + a 16-ary
+   reduction tree.  n < 2^32. */
 int b381_g1_sum(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
 int b381_g2_sum(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n);
 int b381_g1_msm(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n);
@@ -166,7 +192,35 @@ int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t
 int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
 int b381_g2_prepare_dev(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, void* stream);
 int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream);
-/* fetch-and-clear the device error word after synchronising `stream`; returns 0 or a B381_E_* code */
+int b381_multi_pairing_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, void* stream);
+int b381_fp12_mul_wbasis_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
+int b381_fp_inv_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream);
+int b381_fp_sqrt_dev(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n, void* stream);
+int b381_fp_is_square_dev(const uint32_t* a, uint8_t* out, size_t n, void* stream);
+int b381_fp_pow_dev(const uint32_t* a, const uint64_t* exp /* host */, size_t exp_limbs, uint32_t* out, size_t n, void* stream);
+int b381_fp2_inv_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream);
+int b381_fp2_sqrt_dev(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n, void* stream);
+int b381_fp2_is_square_dev(const uint32_t* a, uint8_t* out, size_t n, void* stream);
+int b381_fp6_inv_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream);
+int b381_fp12_inv_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream);
+int b381_fp_to_u32_digits_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream);
+int b381_fp_from_u32_digits_dev(const uint32_t* digits, uint32_t* out, size_t n, void* stream);
+int b381_fp12_to_witness_limbs_dev(const uint32_t* f, uint32_t* out, size_t n, void* stream);
+int b381_g1_deserialize_dev(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* inf, size_t n, void* stream);
+int b381_g1_serialize_dev(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n, void* stream);
+int b381_g2_deserialize_dev(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n, void* stream);
+int b381_g2_serialize_dev(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n, void* stream);
+int b381_g1_in_subgroup_dev(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n, void* stream);
+int b381_g2_in_subgroup_dev(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n, void* stream);
+int b381_g1_clear_cofactor_dev(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g2_clear_cofactor_dev(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g1_scalar_mul_dev(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g2_scalar_mul_dev(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g1_sum_dev(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g2_sum_dev(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g1_msm_dev(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+int b381_g2_msm_dev(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n, void* stream);
+/* fetch-and-clear the context's device error word after synchronising `stream`; returns 0 or a B381_E_* code */
 int b381_check_dev(void* stream);
 
 /* integer-multiply roofline probe: sustained IMAD.WIDE issue rate of this GPU, in 1e9 thread-instructions/s,

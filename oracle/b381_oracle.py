@@ -714,6 +714,102 @@ def g2_on_curve(q):
 G1_GEN = (G1_X, G1_Y)
 G2_GEN = (G2_X, G2_Y)
 
+
+# ----------------------------------------------------------------------------------------------
+# Endomorphisms, fast subgroup membership and cofactor clearing: ark-bls12-381 0.4 `curves/g1.rs`, `curves/g2.rs`
+# (third-party, restated from the published algorithms; pinned below by the RFC 9380 effective cofactors and by
+# agreement with the plain [r] P test).  The reference's circuit side needs them before untrusted points can be
+# paired (/root/reference/src/fields/fq_target.rs:288-313, src/fields/fq12_target.rs:408-416).
+# ----------------------------------------------------------------------------------------------
+# BETA: the non-trivial cube root of unity ark-bls12-381 uses for (x, y) -> (BETA x, y)   (g1.rs `BETA`)
+G1_BETA = 793479390729215512621379701633421447060886740281060493010456487427281649075476305620758731620350
+assert pow(G1_BETA, 3, P) == 1 and G1_BETA != 1
+# effective cofactors of RFC 9380 section 8.8 (BLS12381G1: 1 - x; BLS12381G2: Budroni-Pintore h_eff)
+G1_H_EFF = 0xD201000000010001
+G2_H_EFF = 0xBC69F08F2EE75B3584C6A0EA91B352888E2A8E9145AD7689986FF031508FFE1329C2F178731DB956D82BF015D1212B02EC0EC69D7477C1AE954CBC06689F6A359894C0ADEBBF6B4E8020005AAA95551
+assert G1_H_EFF == 1 + BLS_X
+
+
+def g1_neg(p):
+    return None if p is None else (p[0], (-p[1]) % P)
+
+
+def g2_neg(q):
+    return None if q is None else (q[0], f2_neg(q[1]))
+
+
+def g1_endomorphism(p):
+    """ark g1.rs endomorphism(): (x, y) -> (BETA x, y)"""
+    return None if p is None else (G1_BETA * p[0] % P, p[1])
+
+
+def g1_in_subgroup_fast(p):
+    """ark g1.rs is_in_correct_subgroup_assuming_on_curve (eprint 2021/1130 section 6):
+    endomorphism(P) == -[X^2] P with X = |x|, plus the early-out [X] P == P for P != identity."""
+    if p is None:
+        return True
+    xp = g1_mul(p, BLS_X)
+    if xp == p:
+        return False
+    return g1_neg(g1_mul(xp, BLS_X)) == g1_endomorphism(p)
+
+
+def g1_clear_cofactor(p):
+    """ark g1.rs clear_cofactor: multiplication by the effective cofactor 1 - x = 1 + |x| (eprint 2019/403 section 5)"""
+    return g1_add(g1_mul(p, BLS_X), p)
+
+
+# psi = twist o Frobenius o untwist on E'(Fq2): (x, y) -> (conj(x) / xi^((p-1)/3), conj(y) / xi^((p-1)/2))   (g2.rs
+# P_POWER_ENDOMORPHISM_COEFF_0 / _1);  psi^2: (x, y) -> (x / xi^((p^2-1)/3), -y)   (DOUBLE_P_POWER_ENDOMORPHISM_COEFF_0)
+def _f2_pow(a, e):
+    r = F2_ONE
+    while e:
+        if e & 1:
+            r = f2_mul(r, a)
+        a = f2_mul(a, a)
+        e >>= 1
+    return r
+
+
+PSI_CX = f2_inv(_f2_pow((1, 1), (P - 1) // 3))
+PSI_CY = f2_inv(_f2_pow((1, 1), (P - 1) // 2))
+PSI2_CX = f2_inv(_f2_pow((1, 1), (P * P - 1) // 3))
+assert PSI2_CX[1] == 0 and _f2_pow((1, 1), (P * P - 1) // 2) == ((-1) % P, 0)
+
+
+def g2_psi(q):
+    if q is None:
+        return None
+    return (f2_mul(f2_conj(q[0]), PSI_CX), f2_mul(f2_conj(q[1]), PSI_CY))
+
+
+def g2_psi2(q):
+    if q is None:
+        return None
+    return (f2_mul_fp(q[0], PSI2_CX[0]), f2_neg(q[1]))
+
+
+def g2_in_subgroup_fast(q):
+    """ark g2.rs is_in_correct_subgroup_assuming_on_curve (eprint 2021/1130 section 4): psi(P) == [x] P, x < 0"""
+    if q is None:
+        return True
+    return g2_neg(g2_mul(q, BLS_X)) == g2_psi(q)
+
+
+def g2_clear_cofactor(q):
+    """ark g2.rs clear_cofactor (Budroni-Pintore, eprint 2017/419 section 4.1):
+    [x^2 - x - 1] P + [x - 1] psi(P) + psi^2(2 P), evaluated as ark does with X = |x| and negations."""
+    if q is None:
+        return None
+    x_p = g2_neg(g2_mul(q, BLS_X))                       # [x] P
+    psi_p = g2_psi(q)
+    psi2_p2 = g2_psi2(g2_add(q, q))
+    tmp2 = g2_neg(g2_mul(g2_add(x_p, psi_p), BLS_X))     # [x^2] P + [x] psi(P)
+    acc = g2_add(psi2_p2, tmp2)
+    acc = g2_add(acc, g2_neg(x_p))
+    acc = g2_add(acc, g2_neg(psi_p))
+    return g2_add(acc, g2_neg(q))
+
 # ----------------------------------------------------------------------------------------------
 # ARK mode: ark-ec 0.4 models/bls12/g2.rs (G2Prepared) + models/bls12/mod.rs; SURVEY A.2-A.5.
 # Truth the reference defers to: src/miller_loop_native_optimized.rs:131-132,151,163.

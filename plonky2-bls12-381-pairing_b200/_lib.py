@@ -25,6 +25,7 @@ class B381Error(RuntimeError):
 _lib = None
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _u8p = ctypes.POINTER(ctypes.c_uint8)
+_V = ctypes.c_void_p
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -83,6 +84,40 @@ SIGNATURES = {
     "b381_g2_prepare_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
     "b381_miller_loop_prepared_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_check_dev": [ctypes.c_void_p],
+    "b381_ctx_create": [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)],
+    "b381_ctx_destroy": [ctypes.c_void_p],
+    "b381_ctx_set_current": [ctypes.c_void_p],
+    "b381_ctx_get_current": [ctypes.POINTER(ctypes.c_void_p)],
+    "b381_g1_clear_cofactor": [_u32p, _u8p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_g2_clear_cofactor": [_u32p, _u8p, _u32p, _u8p, ctypes.c_size_t],
+    "b381_multi_pairing_dev": [_V, _V, _V, _V, ctypes.c_size_t, ctypes.c_int, _V],
+    "b381_fp12_mul_wbasis_dev": [_V, _V, _V, ctypes.c_size_t, _V],
+    "b381_fp_inv_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp_sqrt_dev": [_V, _V, _V, ctypes.c_size_t, _V],
+    "b381_fp_is_square_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp_pow_dev": [_V, ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t, _V, ctypes.c_size_t, _V],
+    "b381_fp2_inv_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp2_sqrt_dev": [_V, _V, _V, ctypes.c_size_t, _V],
+    "b381_fp2_is_square_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp6_inv_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp12_inv_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp_to_u32_digits_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp_from_u32_digits_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_fp12_to_witness_limbs_dev": [_V, _V, ctypes.c_size_t, _V],
+    "b381_g1_deserialize_dev": [_V, ctypes.c_int, _V, _V, ctypes.c_size_t, _V],
+    "b381_g1_serialize_dev": [_V, _V, ctypes.c_int, _V, ctypes.c_size_t, _V],
+    "b381_g2_deserialize_dev": [_V, ctypes.c_int, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_serialize_dev": [_V, _V, ctypes.c_int, _V, ctypes.c_size_t, _V],
+    "b381_g1_in_subgroup_dev": [_V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_in_subgroup_dev": [_V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g1_clear_cofactor_dev": [_V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_clear_cofactor_dev": [_V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g1_scalar_mul_dev": [_V, _V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_scalar_mul_dev": [_V, _V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g1_sum_dev": [_V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_sum_dev": [_V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g1_msm_dev": [_V, _V, _V, _V, _V, ctypes.c_size_t, _V],
+    "b381_g2_msm_dev": [_V, _V, _V, _V, _V, ctypes.c_size_t, _V],
     "b381_imad_peak": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
 }
 G2PREP_WORDS = 68 * 72

@@ -22,7 +22,7 @@ struct ExpTab {
   uint32_t pm1d2[12];    // (p - 1) / 2    (Legendre symbol)
 };
 #if defined(__CUDACC__)
-__constant__ ExpTab g_et = {B381_EXP_PM2, B381_EXP_PP1D4, B381_EXP_PM1D2};
+static __constant__ ExpTab g_et = {B381_EXP_PM2, B381_EXP_PP1D4, B381_EXP_PM1D2};
 #else
 static const ExpTab g_et = {B381_EXP_PM2, B381_EXP_PP1D4, B381_EXP_PM1D2};
 #endif

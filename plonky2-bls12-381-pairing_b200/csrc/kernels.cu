@@ -17,6 +17,7 @@
 #include "../../include/b381.h"
 #include "programs.cuh"
 #include "helpers.cuh"
+#include "g1_launch.h"
 
 using namespace b381;
 
@@ -244,46 +245,35 @@ k_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out, size_t n, u4*
   }
 }
 
-// subgroup membership [r] P == infinity: uniform ladder, data-dependent cases inside the group law -> no lock step
-__global__ void __launch_bounds__(BLOCK, 1)
-k_subgroup(const uint32_t* pts, const uint8_t* inf, int is_g2, uint32_t* out_words, size_t n, u4* garena, int* err) {
-  Ctx cx = make_ctx(garena, 0);
-  const int w = is_g2 ? 48 : 24;
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
-    size_t i = base + threadIdx.x;
-    if (i < n) {
-      uint8_t r = 0;
-      report(prog_subgroup_check(cx, pts + (size_t)w * i, is_g2, inf ? inf[i] : 0, &r), err);
-      out_words[i] = r;
-    }
-  }
-}
+// ---- group kernels.  Points and identity flags are separate arrays (points: 24 / 48 words, flags: one byte).
+// G2 runs on the slot arena (divergent special cases inside the group law -> no lock step); G1 runs in registers
+// over the base field (g1.cuh) and is compiled as its own translation unit (g1_kernels.cu, launchers in g1_launch.h).
 
-// [k_i] P_i with per-element 256-bit scalars: divergent control flow -> no lock step
 __global__ void __launch_bounds__(BLOCK, 1)
-k_scalar_mul(const uint32_t* pts, const uint32_t* scalars, const uint8_t* inf, int is_g2, uint32_t* out, size_t n, u4* garena, int* err) {
+k_g2_point_op(int op, const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out8, size_t n, u4* garena, int* err) {
   Ctx cx = make_ctx(garena, 0);
-  const int w = is_g2 ? 48 : 24;
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     size_t i = base + threadIdx.x;
     if (i < n) {
       uint8_t f = 0;
-      report(prog_scalar_mul(cx, pts + (size_t)w * i, is_g2, inf ? inf[i] : 0, scalars + 8 * i, out + (size_t)(w + 1) * i, &f), err);
-      out[(size_t)(w + 1) * i + w] = f;
+      const int in_f = inf ? inf[i] : 0;
+      if (op == PO_SUBGROUP) report(prog_g2_in_subgroup(cx, pts + 48 * i, in_f, &f), err);
+      else if (op == PO_CLEAR_COFACTOR) report(prog_g2_clear_cofactor(cx, pts + 48 * i, in_f, out + 48 * i, &f), err);
+      else report(prog_scalar_mul(cx, pts + 48 * i, 1, in_f, scalars + 8 * i, out + 48 * i, &f), err);
+      out8[i] = f;
     }
   }
 }
 
-// out[j] = sum of in[j*K .. min((j+1)K, n_in)) in the packed point layout (trip counts differ -> no lock step)
+// G2: out[j] = sum of the points j*K .. min((j+1)K, n_in) (trip counts differ -> no lock step)
 __global__ void __launch_bounds__(BLOCK, 1)
-k_point_sum(const uint32_t* in, size_t n_in, uint32_t* out, size_t n_out, int K, int is_g2, u4* garena, int* err) {
+k_g2_point_sum(const uint32_t* in, const uint8_t* in_inf, size_t n_in, uint32_t* out, uint8_t* out_inf, size_t n_out, int K, u4* garena, int* err) {
   Ctx cx = make_ctx(garena, 0);
-  const size_t w1 = (is_g2 ? 48 : 24) + 1;
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n_out; base += (size_t)gridDim.x * BLOCK) {
     size_t j = base + threadIdx.x;
     if (j < n_out) {
       size_t lo = j * (size_t)K, hi = lo + K < n_in ? lo + K : n_in;
-      report(prog_point_sum(cx, in + lo * w1, hi - lo, is_g2, out + j * w1), err);
+      report(prog_g2_point_sum(cx, in + lo * 48, in_inf ? in_inf + lo : nullptr, hi - lo, out + j * 48, out_inf + j), err);
     }
   }
 }
@@ -402,7 +392,7 @@ k_helper(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e, int n
 enum WireOp { W_FP_TO_DIGITS = 0, W_FP_FROM_DIGITS, W_FP12_TO_WITNESS, W_G1_DESER, W_G1_SER, W_G2_DESER, W_G2_SER };
 
 __global__ void __launch_bounds__(128)
-k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, int* err) {
+k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, uint8_t* out8, size_t n, int* err) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0;
     const uint8_t* inb = reinterpret_cast<const uint8_t*>(in);
@@ -413,14 +403,14 @@ k_wire(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t*
       case W_FP12_TO_WITNESS: r = prog_fp12_to_witness(in + 144 * i, out + 144 * i); break;
       case W_G1_DESER: {
         uint8_t f = 0;
-        r = prog_g1_deserialize(inb + (compressed ? 48 : 96) * i, compressed, out + 25 * i, &f);
-        out[25 * i + 24] = f;
+        r = prog_g1_deserialize(inb + (compressed ? 48 : 96) * i, compressed, out + 24 * i, &f);
+        out8[i] = f;
       } break;
       case W_G1_SER: r = prog_g1_serialize(in + 24 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 48 : 96) * i); break;
       case W_G2_DESER: {
         uint8_t f = 0;
-        r = prog_g2_deserialize(inb + (compressed ? 96 : 192) * i, compressed, out + 49 * i, &f);
-        out[49 * i + 48] = f;
+        r = prog_g2_deserialize(inb + (compressed ? 96 : 192) * i, compressed, out + 48 * i, &f);
+        out8[i] = f;
       } break;
       default: r = prog_g2_serialize(in + 48 * i, inf ? inf[i] : 0, compressed, outb + (compressed ? 96 : 192) * i); break;
     }
@@ -488,990 +478,6 @@ k_imad_peak(uint32_t* out, const uint32_t* in, unsigned long long* cyc, int iter
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-// ---- host side ---------------------------------------------------------------------------------------
-struct State {
-  bool init = false;
-  int device = -1;
-  int sm_count = 0, cc_major = 0, cc_minor = 0;
-  cudaStream_t stream[2] = {nullptr, nullptr};   // stream[0]: all kernels of the host-pointer API; stream[1]: spare lane
-  cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined host-pointer API
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  u4* garena[2] = {nullptr, nullptr};
-  int* d_err = nullptr;
-  uint32_t* d_in1[2] = {nullptr, nullptr};      // staging (device) per lane
-  uint32_t* d_in2[2] = {nullptr, nullptr};
-  uint8_t* d_inf[2] = {nullptr, nullptr};
-  uint32_t* d_out[2] = {nullptr, nullptr};
-  size_t cap_in1 = 0, cap_in2 = 0, cap_inf = 0, cap_out = 0;   // bytes per lane
-  uint32_t* d_partial[2] = {nullptr, nullptr};  // raw partial products for multi_miller
-  uint32_t* d_dump[2] = {nullptr, nullptr};     // sink for the outputs of padding threads (BLOCK x 144 words)
-  const uint8_t* cur_inf = nullptr;             // identity flags of the chunk host_binary is launching
-  uint32_t* d_dump_coeffs = nullptr;            // same for k_g2_prepare (BLOCK x 4896 words), allocated on first use
-  unsigned long long launches = 0;
-  std::string last_error;
-  std::mutex mu;
-};
-State g;
-
-int fail_cuda(cudaError_t e, const char* what) {
-  g.last_error = std::string(what) + ": " + cudaGetErrorString(e);
-  return B381_E_CUDA;
-}
-#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, #x); } while (0)
-
-int fail_arg(const char* what) {
-  g.last_error = what;
-  return B381_E_ARG;
-}
-
-int map_err(int bits) {
-  if (bits & ERR_NOT_CANONICAL) { g.last_error = "input limbs not canonical (>= p)"; return B381_E_NOT_CANONICAL; }
-  if (bits & ERR_ZERO_DIVISION) { g.last_error = "division by zero (final_exponentiation(0), f_den == 0 or inverse of zero)"; return B381_E_ZERO_DIVISION; }
-  if (bits & 8) { g.last_error = "invalid point encoding (flag bits)"; return B381_E_BAD_ENCODING; }
-  if (bits & 4) { g.last_error = "square root of a non-residue (or of zero with sgn0 = 1; point not on the curve)"; return B381_E_NOT_SQUARE; }
-  return B381_OK;
-}
-
-int grid_for(size_t n) {
-  size_t batches = (n + BLOCK - 1) / BLOCK;
-  return (int)(batches < (size_t)g.sm_count ? batches : (size_t)g.sm_count);
-}
-
-template <typename K>
-int set_smem(K kernel) {
-  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  return 0;
-}
-
-
-int grow(uint32_t** p0, uint32_t** p1, size_t* cap, size_t need) {
-  if (need <= *cap) return 0;
-  if (*p0) cudaFree(*p0);
-  if (*p1) cudaFree(*p1);
-  *p0 = *p1 = nullptr; *cap = 0;
-  CU(cudaMalloc((void**)p0, need));
-  CU(cudaMalloc((void**)p1, need));
-  *cap = need;
-  return 0;
-}
-
-int read_err(cudaStream_t s) {
-  int h = 0;
-  CU(cudaMemcpyAsync(&h, g.d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (h) CU(cudaMemsetAsync(g.d_err, 0, sizeof(int), s));
-  return map_err(h);
-}
-
-constexpr size_t CHUNK = 1u << 17;    // elements per pipelined chunk of the element-wise host-pointer API
-// pair kernels: chunks are whole rounds (4 x #SM x 256 pairs) so that no launch runs a partly filled round
-size_t pair_chunk() { return 4 * (size_t)g.sm_count * BLOCK; }
-
-// launch helpers (device pointers) ----------------------------------------------------------------------
-// A launch is limited to a few rounds per CTA: CTAs of different SMs are only aligned at launch
-// start, and per-round time creeps up by ~8 % once they have drifted apart (tools/gpu_exp3.py);
-// back-to-back launches of one round each keep the whole chip on one instruction stream
-// (34.2 ms/round against 34.8 at four rounds and 37.6 at 28 rounds per launch).
-constexpr size_t MAX_ROUNDS_PER_LAUNCH = 1;
-size_t pairs_per_launch() { return MAX_ROUNDS_PER_LAUNCH * (size_t)g.sm_count * BLOCK; }
-
-int launch_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_miller<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-int launch_final_exp(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t s, int lane) {
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_final_exp<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(in + 144 * off, out + 144 * off, m, g.garena[lane], g.d_err, g.d_dump[lane]);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-int launch_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, cudaStream_t s, int lane) {
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_pairing<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, g.garena[lane], g.d_err, g.d_dump[lane]);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-
-int launch_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, cudaStream_t s, int lane) {
-  if (!g.d_dump_coeffs) CU(cudaMalloc((void**)&g.d_dump_coeffs, (size_t)BLOCK * G2PREP_WORDS * sizeof(uint32_t)));
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_g2_prepare<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g2 + 48 * off, coeffs + (size_t)G2PREP_WORDS * off, m, mode, g.garena[lane], g.d_err, g.d_dump_coeffs);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-int launch_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, cudaStream_t s, int lane) {
-  for (size_t off = 0; off < n; off += pairs_per_launch()) {
-    size_t m = n - off < pairs_per_launch() ? n - off : pairs_per_launch();
-    k_miller_prepared<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, coeffs + (size_t)G2PREP_WORDS * off, inf ? inf + off : nullptr, out + 144 * off, m, mode, do_fe, g.garena[lane], g.d_err, g.d_dump[lane]);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-
-// raw tree reduction of `cnt` partials living in buf (ping) using pong; returns pointer to the single result
-int reduce_raw(uint32_t* ping, uint32_t* pong, size_t cnt, cudaStream_t s, int lane, uint32_t** result) {
-  const int K = 16;
-  while (cnt > 1) {
-    size_t n_out = (cnt + K - 1) / K;
-    k_f12_reduce_raw<<<grid_for(n_out), BLOCK, SMEM_BYTES, s>>>(ping, cnt, pong, n_out, K, g.garena[lane]);
-    g.launches++;
-    CU(cudaGetLastError());
-    uint32_t* t = ping; ping = pong; pong = t;
-    cnt = n_out;
-  }
-  *result = ping;
-  return 0;
-}
-
-// accumulate the Miller values of `n` device-resident pairs into the per-thread partial products
-// (every launch uses the full grid so that partial[] always has sm_count * BLOCK entries)
-int launch_multi_accumulate(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, bool first, cudaStream_t s, int lane) {
-  uint32_t* ping = g.d_partial[lane];
-  const size_t per = 2 * pairs_per_launch();        // two pairs per thread per round
-  for (size_t off = 0; off < n; off += per) {
-    size_t m = n - off < per ? n - off : per;
-    k_multi_miller<<<g.sm_count, BLOCK, SMEM_BYTES, s>>>(g1 + 24 * off, g2 + 48 * off, inf ? inf + off : nullptr, m, mode, ping, !(first && off == 0), g.garena[lane], g.d_err);
-    g.launches++;
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-
-// tree-reduce the partial products, optional final exponentiation, result (external format) -> out144
-int launch_multi_finish(uint32_t* out144, int do_fe, cudaStream_t s, int lane) {
-  uint32_t* ping = g.d_partial[lane];
-  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
-  uint32_t* res = nullptr;
-  int rc = reduce_raw(ping, pong, (size_t)g.sm_count * BLOCK, s, lane, &res);
-  if (rc) return rc;
-  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, out144, do_fe, g.garena[lane], g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-// product of all Miller values of device-resident pairs -> out144 (device, external format), optional final exp
-int launch_multi(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe, cudaStream_t s, int lane) {
-  if (mode == B381_MODE_LITERAL) {                 // the reference's multi_miller_loop as written returns 1
-    k_fill_one_ext<<<1, 32, 0, s>>>(out144);
-    g.launches++;
-    CU(cudaGetLastError());
-    if (do_fe) { int rc = launch_final_exp(out144, out144, 1, s, lane); if (rc) return rc; }
-    return 0;
-  }
-  int rc = launch_multi_accumulate(g1, g2, inf, n, mode, true, s, lane);
-  if (rc) return rc;
-  return launch_multi_finish(out144, do_fe, s, lane);
-}
-
-bool bad_mode(int mode) { return mode != B381_MODE_ARK && mode != B381_MODE_ZK && mode != B381_MODE_LITERAL; }
-
-#define REQUIRE_INIT() do { if (!g.init) { g.last_error = "b381_init not called"; return B381_E_NOT_INIT; } } while (0)
-
-// host-pointer pipelines --------------------------------------------------------------------------------
-enum PairKind { PK_MILLER, PK_PAIRING };
-
-int host_pairs(PairKind kind, const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
-  const size_t CHUNK = pair_chunk();
-  size_t c = n < CHUNK ? n : CHUNK;
-  int rc;
-  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * 24 * 4))) return rc;
-  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * 48 * 4))) return rc;
-  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * 144 * 4))) return rc;
-  if (inf) {
-    if (c > g.cap_inf) {
-      for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
-      g.cap_inf = 0;
-      for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
-      g.cap_inf = c;
-    }
-  }
-  // three-stream pipeline over double-buffered staging: copies of chunk c+1 / c-1 overlap the kernels
-  // of chunk c, and ALL kernels run on one stream (two kernels sharing the chip would break the
-  // chip-wide lock step the launches rely on).
-  cudaStream_t sk = g.stream[0];
-  int lane = 0;
-  size_t nchunks = 0;
-  for (size_t off = 0; off < n; off += CHUNK, lane ^= 1, nchunks++) {
-    size_t m = n - off < CHUNK ? n - off : CHUNK;
-    if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));        // staging inputs free again
-    CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, g.s_in));
-    CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, g.s_in));
-    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
-    CU(cudaEventRecord(g.ev_in[lane], g.s_in));
-    CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
-    if (nchunks >= 2) CU(cudaStreamWaitEvent(sk, g.ev_out[lane], 0));          // staging output drained
-    const uint8_t* dinf = inf ? g.d_inf[lane] : nullptr;
-    if (kind == PK_MILLER) rc = launch_miller(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, sk, 0);
-    else rc = launch_pairing(g.d_in1[lane], g.d_in2[lane], dinf, g.d_out[lane], m, mode, sk, 0);
-    if (rc) return rc;
-    CU(cudaEventRecord(g.ev_k[lane], sk));
-    CU(cudaStreamWaitEvent(g.s_out, g.ev_k[lane], 0));
-    CU(cudaMemcpyAsync(out + off * 144, g.d_out[lane], m * 144 * 4, cudaMemcpyDeviceToHost, g.s_out));
-    CU(cudaEventRecord(g.ev_out[lane], g.s_out));
-  }
-  CU(cudaStreamSynchronize(g.s_out));
-  return read_err(sk);
-}
-
-// generic element-wise host pipeline: two inputs of wi words, one output of wo words per element
-int ensure_inf_staging(size_t c) {
-  if (c > g.cap_inf) {
-    for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
-    g.cap_inf = 0;
-    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
-    g.cap_inf = c;
-  }
-  return 0;
-}
-
-template <typename L>
-int host_binary(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, size_t wa, size_t wb, size_t wo, size_t chunk, L launch, const uint8_t* inf = nullptr) {
-  size_t c = n < chunk ? n : chunk;
-  int rc;
-  if (inf && (rc = ensure_inf_staging(c))) return rc;
-  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * wa * 4))) return rc;
-  if (b && (rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * wb * 4))) return rc;
-  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, c * wo * 4))) return rc;
-  cudaStream_t sk = g.stream[0];                    // same three-stream pipeline as host_pairs
-  int lane = 0;
-  size_t nchunks = 0;
-  for (size_t off = 0; off < n; off += chunk, lane ^= 1, nchunks++) {
-    size_t m = n - off < chunk ? n - off : chunk;
-    if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));
-    CU(cudaMemcpyAsync(g.d_in1[lane], a + off * wa, m * wa * 4, cudaMemcpyHostToDevice, g.s_in));
-    if (b) CU(cudaMemcpyAsync(g.d_in2[lane], b + off * wb, m * wb * 4, cudaMemcpyHostToDevice, g.s_in));
-    if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
-    CU(cudaEventRecord(g.ev_in[lane], g.s_in));
-    CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
-    if (nchunks >= 2) CU(cudaStreamWaitEvent(sk, g.ev_out[lane], 0));
-    g.cur_inf = inf ? g.d_inf[lane] : nullptr;
-    if ((rc = launch(g.d_in1[lane], g.d_in2[lane], g.d_out[lane], m, sk, 0))) return rc;
-    CU(cudaEventRecord(g.ev_k[lane], sk));
-    CU(cudaStreamWaitEvent(g.s_out, g.ev_k[lane], 0));
-    CU(cudaMemcpyAsync(out + off * wo, g.d_out[lane], m * wo * 4, cudaMemcpyDeviceToHost, g.s_out));
-    CU(cudaEventRecord(g.ev_out[lane], g.s_out));
-  }
-  CU(cudaStreamSynchronize(g.s_out));
-  return read_err(sk);
-}
-
-int elem_grid(size_t n, int threads, int per_sm) {
-  size_t blocks = (n + threads - 1) / threads;
-  size_t cap = (size_t)g.sm_count * per_sm;
-  return (int)(blocks < cap ? blocks : cap);
-}
-
 }  // namespace
 
-// ======================================================================================================
-// C ABI
-// ======================================================================================================
-extern "C" {
-
-int b381_init(int device) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.init) {
-    if (g.device == device) return B381_OK;
-    g.last_error = "already initialised on another device";
-    return B381_E_ARG;
-  }
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    g.last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb381 has no CPU fallback)";
-    return B381_E_CUDA;
-  }
-  if (device < 0 || device >= count) return fail_arg("device index out of range");
-  CU(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  g.device = device;
-  g.sm_count = prop.multiProcessorCount;
-  g.cc_major = prop.major;
-  g.cc_minor = prop.minor;
-  if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) {
-    g.last_error = "device lacks 216 KB opt-in shared memory per block (built for sm_100a)";
-    return B381_E_CUDA;
-  }
-  CU(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
-  for (int l = 0; l < 2; l++) {
-    CU(cudaEventCreateWithFlags(&g.ev_in[l], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&g.ev_k[l], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&g.ev_out[l], cudaEventDisableTiming));
-    CU(cudaStreamCreateWithFlags(&g.stream[l], cudaStreamNonBlocking));
-    CU(cudaMalloc((void**)&g.garena[l], GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count));
-    CU(cudaMalloc((void**)&g.d_partial[l], 2 * (size_t)g.sm_count * BLOCK * RAW_WORDS * sizeof(uint32_t)));
-    CU(cudaMalloc((void**)&g.d_dump[l], (size_t)BLOCK * 144 * sizeof(uint32_t)));
-  }
-  CU(cudaMalloc((void**)&g.d_err, sizeof(int)));
-  CU(cudaMemset(g.d_err, 0, sizeof(int)));
-  int rc;
-  if ((rc = set_smem(k_miller)) || (rc = set_smem(k_final_exp)) || (rc = set_smem(k_pairing)) || (rc = set_smem(k_multi_miller)) ||
-      (rc = set_smem(k_f12_reduce_raw)) || (rc = set_smem(k_ext_to_raw)) || (rc = set_smem(k_raw_finish)) || (rc = set_smem(k_f12_mul)) ||
-      (rc = set_smem(k_literal)) || (rc = set_smem(k_g2_prepare)) || (rc = set_smem(k_miller_prepared)) || (rc = set_smem(k_tower_inv)) || (rc = set_smem(k_subgroup)) || (rc = set_smem(k_scalar_mul)) || (rc = set_smem(k_point_sum)))
-    return rc;
-  CU(cudaDeviceSynchronize());
-  g.launches = 0;
-  g.init = true;
-  return B381_OK;
-}
-
-int b381_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (!g.init) return B381_OK;
-  cudaDeviceSynchronize();
-  for (int l = 0; l < 2; l++) {
-    if (g.stream[l]) cudaStreamDestroy(g.stream[l]);
-    if (g.ev_in[l]) { cudaEventDestroy(g.ev_in[l]); cudaEventDestroy(g.ev_k[l]); cudaEventDestroy(g.ev_out[l]); g.ev_in[l] = g.ev_k[l] = g.ev_out[l] = nullptr; }
-    cudaFree(g.garena[l]); cudaFree(g.d_partial[l]); cudaFree(g.d_dump[l]); g.d_dump[l] = nullptr;
-    cudaFree(g.d_in1[l]); cudaFree(g.d_in2[l]); cudaFree(g.d_inf[l]); cudaFree(g.d_out[l]);
-    g.stream[l] = nullptr; g.garena[l] = nullptr; g.d_partial[l] = nullptr;
-    g.d_in1[l] = g.d_in2[l] = g.d_out[l] = nullptr; g.d_inf[l] = nullptr;
-  }
-  cudaFree(g.d_err);
-  g.d_err = nullptr;
-  if (g.s_in) { cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out); g.s_in = g.s_out = nullptr; }
-  g.cap_in1 = g.cap_in2 = g.cap_inf = g.cap_out = 0;
-  g.init = false;
-  return B381_OK;
-}
-
-const char* b381_last_error(void) { return g.last_error.c_str(); }
-
-int b381_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* scratch_bytes) {
-  REQUIRE_INIT();
-  if (sm_count) *sm_count = g.sm_count;
-  if (cc_major) *cc_major = g.cc_major;
-  if (cc_minor) *cc_minor = g.cc_minor;
-  if (scratch_bytes) *scratch_bytes = 2 * GARENA_U4_PER_CTA * sizeof(u4) * g.sm_count;
-  return B381_OK;
-}
-
-unsigned long long b381_kernel_launches(void) { return g.launches; }
-
-// ---- device-pointer API ---------------------------------------------------------------------------
-int b381_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode)) return fail_arg("b381_miller_loop_dev: bad argument");
-  if (mode == B381_MODE_LITERAL) return fail_arg("LITERAL per-pair values: use b381_literal_optimized / b381_multi_miller_loop");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_miller(g1, g2, inf, out, n, mode, (cudaStream_t)stream, 0);
-}
-
-int b381_final_exp_dev(const uint32_t* f, uint32_t* out, size_t n, void* stream) {
-  REQUIRE_INIT();
-  if (!f || !out || n == 0) return fail_arg("b381_final_exp_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_final_exp(f, out, n, (cudaStream_t)stream, 0);
-}
-
-int b381_pairing_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, void* stream) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_pairing(g1, g2, inf, out, n, mode, (cudaStream_t)stream, 0);
-}
-
-int b381_multi_miller_loop_dev(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, void* stream) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_miller_loop_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_multi(g1, g2, inf, out144, n, mode, 0, (cudaStream_t)stream, 0);
-}
-
-int b381_fp_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp_mul_dev: bad argument");
-  k_fp_mul<<<elem_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-int b381_fp_mul_chain_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k, void* stream) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0 || k < 0) return fail_arg("b381_fp_mul_chain_dev: bad argument");
-  k_fp_mul_chain<<<elem_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, k, g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp2_mul_dev: bad argument");
-  k_fp2_mul<<<elem_grid(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(a, b, out, n, g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  k_f12_mul<<<grid_for(n), BLOCK, SMEM_BYTES, (cudaStream_t)stream>>>(a, b, out, n, 0, g.garena[0], g.d_err, g.d_dump[0]);
-  g.launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-int b381_check_dev(void* stream) {
-  REQUIRE_INIT();
-  return read_err((cudaStream_t)stream);
-}
-
-// ---- host-pointer API -----------------------------------------------------------------------------
-int b381_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode)) return fail_arg("b381_miller_loop: bad argument");
-  if (mode == B381_MODE_LITERAL) return fail_arg("LITERAL per-pair values: use b381_literal_optimized / b381_multi_miller_loop");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_pairs(PK_MILLER, g1, g2, inf, out, n, mode);
-}
-
-int b381_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_pairs(PK_PAIRING, g1, g2, inf, out, n, mode);
-}
-
-int b381_final_exp(const uint32_t* f, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!f || !out || n == 0) return fail_arg("b381_final_exp: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(f, nullptr, out, n, 144, 0, 144, pair_chunk(),
-                     [](uint32_t* a, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) { return launch_final_exp(a, o, m, s, lane); });
-}
-
-static int multi_host(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode, int do_fe) {
-  // chunked like host_pairs: H2D of chunk c+1 overlaps the Miller kernels of chunk c; the per-thread
-  // partial products stay on the device and are reduced once at the end.
-  const size_t CHUNK = pair_chunk();
-  size_t c = n < CHUNK ? n : CHUNK;
-  int rc;
-  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, c * 24 * 4))) return rc;
-  if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, c * 48 * 4))) return rc;
-  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, 144 * 4))) return rc;
-  if (inf && c > g.cap_inf) {
-    for (int l = 0; l < 2; l++) { if (g.d_inf[l]) cudaFree(g.d_inf[l]); g.d_inf[l] = nullptr; }
-    g.cap_inf = 0;
-    for (int l = 0; l < 2; l++) CU(cudaMalloc((void**)&g.d_inf[l], c));
-    g.cap_inf = c;
-  }
-  cudaStream_t sk = g.stream[0];
-  if (mode == B381_MODE_LITERAL) {
-    if ((rc = launch_multi(nullptr, nullptr, nullptr, g.d_out[0], n, mode, do_fe, sk, 0))) return rc;
-  } else {
-    int lane = 0;
-    size_t nchunks = 0;
-    for (size_t off = 0; off < n; off += CHUNK, lane ^= 1, nchunks++) {
-      size_t m = n - off < CHUNK ? n - off : CHUNK;
-      if (nchunks >= 2) CU(cudaStreamWaitEvent(g.s_in, g.ev_k[lane], 0));
-      CU(cudaMemcpyAsync(g.d_in1[lane], g1 + off * 24, m * 24 * 4, cudaMemcpyHostToDevice, g.s_in));
-      CU(cudaMemcpyAsync(g.d_in2[lane], g2 + off * 48, m * 48 * 4, cudaMemcpyHostToDevice, g.s_in));
-      if (inf) CU(cudaMemcpyAsync(g.d_inf[lane], inf + off, m, cudaMemcpyHostToDevice, g.s_in));
-      CU(cudaEventRecord(g.ev_in[lane], g.s_in));
-      CU(cudaStreamWaitEvent(sk, g.ev_in[lane], 0));
-      if ((rc = launch_multi_accumulate(g.d_in1[lane], g.d_in2[lane], inf ? g.d_inf[lane] : nullptr, m, mode, off == 0, sk, 0))) return rc;
-      CU(cudaEventRecord(g.ev_k[lane], sk));
-    }
-    if ((rc = launch_multi_finish(g.d_out[0], do_fe, sk, 0))) return rc;
-  }
-  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, sk));
-  return read_err(sk);
-}
-
-int b381_multi_miller_loop(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_miller_loop: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return multi_host(g1, g2, inf, out144, n, mode, 0);
-}
-
-int b381_multi_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out144, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !g2 || !out144 || n == 0 || bad_mode(mode)) return fail_arg("b381_multi_pairing: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return multi_host(g1, g2, inf, out144, n, mode, 1);
-}
-
-int b381_fp12_product(const uint32_t* in, uint32_t* out144, size_t n) {
-  REQUIRE_INIT();
-  if (!in || !out144 || n == 0) return fail_arg("b381_fp12_product: bad argument");
-  if (n > (size_t)g.sm_count * BLOCK) return fail_arg("b381_fp12_product: n too large (max sm_count * 256)");
-  std::lock_guard<std::mutex> lk(g.mu);
-  int rc;
-  if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * 144 * 4))) return rc;
-  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, 144 * 4))) return rc;
-  cudaStream_t s = g.stream[0];
-  CU(cudaMemcpyAsync(g.d_in1[0], in, n * 144 * 4, cudaMemcpyHostToDevice, s));
-  uint32_t* ping = g.d_partial[0];
-  uint32_t* pong = ping + (size_t)g.sm_count * BLOCK * RAW_WORDS;
-  k_ext_to_raw<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g.d_in1[0], ping, n, g.garena[0], g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  uint32_t* res = nullptr;
-  if ((rc = reduce_raw(ping, pong, n, s, 0, &res))) return rc;
-  k_raw_finish<<<1, BLOCK, SMEM_BYTES, s>>>(res, g.d_out[0], 0, g.garena[0], g.d_err);
-  g.launches++;
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out144, g.d_out[0], 144 * 4, cudaMemcpyDeviceToHost, s));
-  return read_err(s);
-}
-
-int b381_literal_optimized(const uint32_t* g1proj, const uint32_t* g2proj, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!g1proj || !g2proj || !out || n == 0) return fail_arg("b381_literal_optimized: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(g1proj, g2proj, out, n, 36, 72, 144, CHUNK,
-                     [](uint32_t* a, uint32_t* b, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                       k_literal<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(a, b, o, m, g.garena[lane], g.d_err);
-                       g.launches++;
-                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_literal");
-                     });
-}
-
-int b381_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp_mul: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(a, b, out, n, 12, 12, 12, (size_t)1 << 22,
-                     [](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp_mul_dev(x, y, o, m, s); });
-}
-
-int b381_fp_mul_chain(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int k) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0 || k < 0) return fail_arg("b381_fp_mul_chain: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(a, b, out, n, 12, 12, 12, (size_t)1 << 22,
-                     [k](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp_mul_chain_dev(x, y, o, m, k, s); });
-}
-
-int b381_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp2_mul: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(a, b, out, n, 24, 24, 24, (size_t)1 << 21,
-                     [](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int) { return b381_fp2_mul_dev(x, y, o, m, s); });
-}
-
-static int f12_mul_host(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis) {
-  return host_binary(a, b, out, n, 144, 144, 144, CHUNK,
-                     [wbasis](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                       k_f12_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, o, m, wbasis, g.garena[lane], g.d_err, g.d_dump[lane]);
-                       g.launches++;
-                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_f12_mul");
-                     });
-}
-
-int b381_fp12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return f12_mul_host(a, b, out, n, 0);
-}
-
-int b381_fp12_mul_wbasis(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !b || !out || n == 0) return fail_arg("b381_fp12_mul_wbasis: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return f12_mul_host(a, b, out, n, 1);
-}
-
-// ---- G2Prepared (cached line coefficients) ---------------------------------------------------------
-int b381_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g2 || !coeffs || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_g2_prepare: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return host_binary(g2, (const uint32_t*)nullptr, coeffs, n, 48, 0, G2PREP_WORDS, pairs_per_launch(),
-                     [mode](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) { return launch_g2_prepare(x, o, m, mode, s, lane); });
-}
-
-static int miller_prepared_host(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe) {
-  return host_binary(g1, coeffs, out, n, 24, G2PREP_WORDS, 144, pairs_per_launch(),
-                     [mode, do_fe](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                       return launch_miller_prepared(x, y, g.cur_inf, o, m, mode, do_fe, s, lane);
-                     }, inf);
-}
-
-int b381_miller_loop_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_miller_loop_prepared: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return miller_prepared_host(g1, coeffs, inf, out, n, mode, 0);
-}
-
-int b381_pairing_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode) {
-  REQUIRE_INIT();
-  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_pairing_prepared: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return miller_prepared_host(g1, coeffs, inf, out, n, mode, 1);
-}
-
-int b381_g2_prepare_dev(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, void* stream) {
-  REQUIRE_INIT();
-  if (!g2 || !coeffs || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_g2_prepare_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_g2_prepare(g2, coeffs, n, mode, (cudaStream_t)stream, 0);
-}
-
-int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream) {
-  REQUIRE_INIT();
-  if (!g1 || !coeffs || !out || n == 0 || bad_mode(mode) || mode == B381_MODE_LITERAL) return fail_arg("b381_miller_loop_prepared_dev: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return launch_miller_prepared(g1, coeffs, inf, out, n, mode, final_exp ? 1 : 0, (cudaStream_t)stream, 0);
-}
-
-// ---- witness helpers -------------------------------------------------------------------
-// element-wise pipelines over host buffers; wi / wo = words per element in / out (wo = 0: byte output)
-static int helper_host(int op, const uint32_t* a, const uint8_t* sgn, const uint32_t* e_words, int nwords, uint32_t* out, uint8_t* out8, size_t n, size_t w) {
-  // exponent (shared by the batch) to the device once
-  uint32_t* d_e = nullptr;
-  if (e_words) {
-    CU(cudaMalloc((void**)&d_e, (size_t)nwords * 4));
-    CU(cudaMemcpy(d_e, e_words, (size_t)nwords * 4, cudaMemcpyHostToDevice));
-  }
-  const bool bytes_out = out8 != nullptr;
-  std::vector<uint32_t> tmp;                         // byte results: each chunk writes its m bytes at the start of an m-word window
-  uint32_t* hout = out;
-  if (bytes_out) { tmp.resize(n); hout = tmp.data(); }
-  int rc = host_binary(a, (const uint32_t*)nullptr, hout, n, w, 0, bytes_out ? 1 : w, CHUNK,
-                       [op, d_e, nwords, bytes_out](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int) {
-                         k_helper<<<elem_grid(m, 128, 8), 128, 0, s>>>(op, x, g.cur_inf, d_e, nwords, bytes_out ? nullptr : o, bytes_out ? reinterpret_cast<uint8_t*>(o) : nullptr, m, g.d_err);
-                         g.launches++;
-                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_helper");
-                       }, sgn);
-  if (d_e) cudaFree(d_e);
-  if (rc) return rc;
-  if (bytes_out) {
-    // each chunk wrote m bytes at the start of its m-word window of hout
-    for (size_t off = 0; off < n; off += CHUNK) {
-      size_t m = n - off < CHUNK ? n - off : CHUNK;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(tmp.data() + off);
-      for (size_t i = 0; i < m; i++) out8[off + i] = src[i];
-    }
-  }
-  return 0;
-}
-
-int b381_fp_inv(const uint32_t* a, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp_inv: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP_INV, a, nullptr, nullptr, 0, out, nullptr, n, 12);
-}
-int b381_fp_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp_sqrt: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP_SQRT, a, sgn, nullptr, 0, out, nullptr, n, 12);
-}
-int b381_fp_is_square(const uint32_t* a, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp_is_square: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP_IS_SQUARE, a, nullptr, nullptr, 0, nullptr, out, n, 12);
-}
-int b381_fp_pow(const uint32_t* a, const uint64_t* exp, size_t exp_limbs, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !exp || exp_limbs == 0 || exp_limbs > 64 || !out || n == 0) return fail_arg("b381_fp_pow: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  std::vector<uint32_t> e(2 * exp_limbs);
-  for (size_t i = 0; i < exp_limbs; i++) { e[2 * i] = (uint32_t)exp[i]; e[2 * i + 1] = (uint32_t)(exp[i] >> 32); }
-  return helper_host(H_FP_POW, a, nullptr, e.data(), (int)(2 * exp_limbs), out, nullptr, n, 12);
-}
-int b381_fp2_inv(const uint32_t* a, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp2_inv: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP2_INV, a, nullptr, nullptr, 0, out, nullptr, n, 24);
-}
-int b381_fp2_sqrt(const uint32_t* a, const uint8_t* sgn, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp2_sqrt: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP2_SQRT, a, sgn, nullptr, 0, out, nullptr, n, 24);
-}
-int b381_fp2_is_square(const uint32_t* a, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp2_is_square: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return helper_host(H_FP2_IS_SQUARE, a, nullptr, nullptr, 0, nullptr, out, n, 24);
-}
-static int tower_inv_host(const uint32_t* a, uint32_t* out, size_t n, int deg) {
-  const size_t w = deg == 12 ? 144 : 72;
-  return host_binary(a, (const uint32_t*)nullptr, out, n, w, 0, w, CHUNK,
-                     [deg](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                       k_tower_inv<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, o, m, deg, g.garena[lane], g.d_err, g.d_dump[lane]);
-                       g.launches++;
-                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_tower_inv");
-                     });
-}
-int b381_fp6_inv(const uint32_t* a, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp6_inv: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return tower_inv_host(a, out, n, 6);
-}
-int b381_fp12_inv(const uint32_t* a, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp12_inv: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return tower_inv_host(a, out, n, 12);
-}
-
-// ---- wire formats -------------------------------------------------------------------------
-static int wire_host(int op, const uint32_t* in, const uint8_t* inf, int compressed, uint32_t* out, size_t n, size_t wi, size_t wo) {
-  return host_binary(in, (const uint32_t*)nullptr, out, n, wi, 0, wo, CHUNK,
-                     [op, compressed](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int) {
-                       k_wire<<<elem_grid(m, 128, 8), 128, 0, s>>>(op, x, g.cur_inf, compressed, o, m, g.d_err);
-                       g.launches++;
-                       return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_wire");
-                     }, inf);
-}
-int b381_fp_to_u32_digits(const uint32_t* a, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!a || !out || n == 0) return fail_arg("b381_fp_to_u32_digits: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return wire_host(W_FP_TO_DIGITS, a, nullptr, 0, out, n, 12, 12);
-}
-int b381_fp_from_u32_digits(const uint32_t* digits, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!digits || !out || n == 0) return fail_arg("b381_fp_from_u32_digits: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return wire_host(W_FP_FROM_DIGITS, digits, nullptr, 0, out, n, 12, 12);
-}
-int b381_fp12_to_witness_limbs(const uint32_t* f, uint32_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!f || !out || n == 0) return fail_arg("b381_fp12_to_witness_limbs: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return wire_host(W_FP12_TO_WITNESS, f, nullptr, 0, out, n, 144, 144);
-}
-static int deser_host(int op, const uint8_t* in, int compressed, uint32_t* pts, uint8_t* inf, size_t n, size_t in_bytes, size_t pt_words) {
-  std::vector<uint32_t> tmp(n * (pt_words + 1));
-  int rc = wire_host(op, reinterpret_cast<const uint32_t*>(in), nullptr, compressed, tmp.data(), n, in_bytes / 4, pt_words + 1);
-  for (size_t i = 0; i < n; i++) {                  // results are written even when an error is reported
-    memcpy(pts + pt_words * i, tmp.data() + (pt_words + 1) * i, pt_words * 4);
-    if (inf) inf[i] = (uint8_t)tmp[(pt_words + 1) * i + pt_words];
-  }
-  return rc;
-}
-int b381_g1_deserialize(const uint8_t* in, int compressed, uint32_t* g1, uint8_t* inf, size_t n) {
-  REQUIRE_INIT();
-  if (!in || !g1 || !inf || n == 0) return fail_arg("b381_g1_deserialize: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return deser_host(W_G1_DESER, in, compressed ? 1 : 0, g1, inf, n, compressed ? 48 : 96, 24);
-}
-int b381_g2_deserialize(const uint8_t* in, int compressed, uint32_t* g2, uint8_t* inf, size_t n) {
-  REQUIRE_INIT();
-  if (!in || !g2 || !inf || n == 0) return fail_arg("b381_g2_deserialize: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return deser_host(W_G2_DESER, in, compressed ? 1 : 0, g2, inf, n, compressed ? 96 : 192, 48);
-}
-int b381_g1_serialize(const uint32_t* g1, const uint8_t* inf, int compressed, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!g1 || !out || n == 0) return fail_arg("b381_g1_serialize: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return wire_host(W_G1_SER, g1, inf, compressed ? 1 : 0, reinterpret_cast<uint32_t*>(out), n, 24, compressed ? 12 : 24);
-}
-int b381_g2_serialize(const uint32_t* g2, const uint8_t* inf, int compressed, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!g2 || !out || n == 0) return fail_arg("b381_g2_serialize: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return wire_host(W_G2_SER, g2, inf, compressed ? 1 : 0, reinterpret_cast<uint32_t*>(out), n, 48, compressed ? 24 : 48);
-}
-
-static int subgroup_host(const uint32_t* pts, const uint8_t* inf, int is_g2, uint8_t* out, size_t n) {
-  std::vector<uint32_t> tmp(n);
-  int rc = host_binary(pts, (const uint32_t*)nullptr, tmp.data(), n, is_g2 ? 48 : 24, 0, 1, CHUNK,
-                       [is_g2](uint32_t* x, uint32_t*, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                         k_subgroup<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, g.cur_inf, is_g2, o, m, g.garena[lane], g.d_err);
-                         g.launches++;
-                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_subgroup");
-                       }, inf);
-  for (size_t i = 0; i < n; i++) out[i] = (uint8_t)tmp[i];
-  return rc;
-}
-int b381_g1_in_subgroup(const uint32_t* g1, const uint8_t* inf, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!g1 || !out || n == 0) return fail_arg("b381_g1_in_subgroup: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return subgroup_host(g1, inf, 0, out, n);
-}
-int b381_g2_in_subgroup(const uint32_t* g2, const uint8_t* inf, uint8_t* out, size_t n) {
-  REQUIRE_INIT();
-  if (!g2 || !out || n == 0) return fail_arg("b381_g2_in_subgroup: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return subgroup_host(g2, inf, 1, out, n);
-}
-
-static int scalar_mul_host(const uint32_t* pts, const uint32_t* scalars, const uint8_t* inf, int is_g2, uint32_t* out, uint8_t* out_inf, size_t n) {
-  const size_t w = is_g2 ? 48 : 24;
-  std::vector<uint32_t> tmp(n * (w + 1));
-  int rc = host_binary(pts, scalars, tmp.data(), n, w, 8, w + 1, CHUNK,
-                       [is_g2](uint32_t* x, uint32_t* y, uint32_t* o, size_t m, cudaStream_t s, int lane) {
-                         k_scalar_mul<<<grid_for(m), BLOCK, SMEM_BYTES, s>>>(x, y, g.cur_inf, is_g2, o, m, g.garena[lane], g.d_err);
-                         g.launches++;
-                         return cudaGetLastError() == cudaSuccess ? 0 : fail_cuda(cudaGetLastError(), "k_scalar_mul");
-                       }, inf);
-  for (size_t i = 0; i < n; i++) {
-    memcpy(out + w * i, tmp.data() + (w + 1) * i, w * 4);
-    if (out_inf) out_inf[i] = (uint8_t)tmp[(w + 1) * i + w];
-  }
-  return rc;
-}
-int b381_g1_scalar_mul(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g1 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g1_scalar_mul: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return scalar_mul_host(g1, scalars, inf, 0, out, out_inf, n);
-}
-int b381_g2_scalar_mul(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g2 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g2_scalar_mul: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return scalar_mul_host(g2, scalars, inf, 1, out, out_inf, n);
-}
-
-// ---- point sums and the (naive) multi-scalar multiplication ---------------------------------------------
-// tree-reduce n packed points on the device (16-ary), result -> host
-static int point_tree(uint32_t* d_a, uint32_t* d_b, size_t n, int is_g2, uint32_t* out, uint8_t* out_inf) {
-  const size_t w = is_g2 ? 48 : 24;
-  cudaStream_t s = g.stream[0];
-  const int K = 16;
-  size_t cnt = n;
-  do {                                              // at least one level: it also normalises a single point
-    size_t n_out = (cnt + K - 1) / K;
-    k_point_sum<<<grid_for(n_out), BLOCK, SMEM_BYTES, s>>>(d_a, cnt, d_b, n_out, K, is_g2, g.garena[0], g.d_err);
-    g.launches++;
-    CU(cudaGetLastError());
-    uint32_t* t = d_a; d_a = d_b; d_b = t;
-    cnt = n_out;
-  } while (cnt > 1);
-  std::vector<uint32_t> res(w + 1);
-  CU(cudaMemcpyAsync(res.data(), d_a, (w + 1) * 4, cudaMemcpyDeviceToHost, s));
-  int rc = read_err(s);
-  memcpy(out, res.data(), w * 4);
-  *out_inf = (uint8_t)res[w];
-  return rc;
-}
-
-static int point_sum_host(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, int is_g2, uint32_t* out, uint8_t* out_inf, size_t n) {
-  const size_t w = is_g2 ? 48 : 24;
-  cudaStream_t s = g.stream[0];
-  int rc;
-  // the library's persistent staging buffers (no allocation per call): d_out[0] / d_out[1] ping-pong the packed points
-  if ((rc = grow(&g.d_out[0], &g.d_out[1], &g.cap_out, n * (w + 1) * 4))) return rc;
-  uint32_t *d_a = g.d_out[0], *d_b = g.d_out[1];
-  if (scalars) {                                    // MSM: [k_i] P_i on the device, straight into the packed layout
-    if ((rc = grow(&g.d_in1[0], &g.d_in1[1], &g.cap_in1, n * w * 4))) return rc;
-    if ((rc = grow(&g.d_in2[0], &g.d_in2[1], &g.cap_in2, n * 8 * 4))) return rc;
-    if (inf && (rc = ensure_inf_staging(n))) return rc;
-    CU(cudaMemcpyAsync(g.d_in1[0], pts, n * w * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(g.d_in2[0], scalars, n * 8 * 4, cudaMemcpyHostToDevice, s));
-    if (inf) CU(cudaMemcpyAsync(g.d_inf[0], inf, n, cudaMemcpyHostToDevice, s));
-    k_scalar_mul<<<grid_for(n), BLOCK, SMEM_BYTES, s>>>(g.d_in1[0], g.d_in2[0], inf ? g.d_inf[0] : nullptr, is_g2, d_a, n, g.garena[0], g.d_err);
-    g.launches++;
-    CU(cudaGetLastError());
-  } else {
-    std::vector<uint32_t> packed(n * (w + 1));
-    for (size_t i = 0; i < n; i++) {
-      memcpy(packed.data() + (w + 1) * i, pts + w * i, w * 4);
-      packed[(w + 1) * i + w] = inf ? (inf[i] & 1) : 0;
-    }
-    CU(cudaMemcpyAsync(d_a, packed.data(), n * (w + 1) * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s));
-  }
-  return point_tree(d_a, d_b, n, is_g2, out, out_inf);
-}
-
-int b381_g1_sum(const uint32_t* g1, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g1 || !out || !out_inf || n == 0) return fail_arg("b381_g1_sum: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return point_sum_host(g1, inf, nullptr, 0, out, out_inf, n);
-}
-int b381_g2_sum(const uint32_t* g2, const uint8_t* inf, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g2 || !out || !out_inf || n == 0) return fail_arg("b381_g2_sum: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return point_sum_host(g2, inf, nullptr, 1, out, out_inf, n);
-}
-int b381_g1_msm(const uint32_t* g1, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g1 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g1_msm: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return point_sum_host(g1, inf, scalars, 0, out, out_inf, n);
-}
-int b381_g2_msm(const uint32_t* g2, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out_inf, size_t n) {
-  REQUIRE_INIT();
-  if (!g2 || !scalars || !out || !out_inf || n == 0) return fail_arg("b381_g2_msm: bad argument");
-  std::lock_guard<std::mutex> lk(g.mu);
-  return point_sum_host(g2, inf, scalars, 1, out, out_inf, n);
-}
-
-int b381_imad_peak(double* imad_wide_ginst_per_s, double* sm_mhz) {
-  REQUIRE_INIT();
-  std::lock_guard<std::mutex> lk(g.mu);
-  const int threads = 1024, iters = 4096;
-  uint32_t *d_in = nullptr, *d_out = nullptr;
-  unsigned long long* d_cyc = nullptr;
-  CU(cudaMalloc((void**)&d_in, 4096 * 4));
-  CU(cudaMalloc((void**)&d_out, 4096 * 4));
-  CU(cudaMalloc((void**)&d_cyc, 1024 * 8));
-  std::vector<uint32_t> h(4096);
-  for (int i = 0; i < 4096; i++) h[i] = (0x9e3779b9u * (uint32_t)(i + 1)) | 1u;
-  CU(cudaMemcpy(d_in, h.data(), 4096 * 4, cudaMemcpyHostToDevice));
-  cudaStream_t s = g.stream[0];
-  double best_rate = 0, best_mhz = 0;
-  for (int variant = 0; variant < 2; variant++) {
-    if (variant == 0) k_imad_peak<0><<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, 256);
-    else k_imad_peak<1><<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, 256);
-    g.launches++;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, s));
-    if (variant == 0) k_imad_peak<0><<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, iters);
-    else k_imad_peak<1><<<g.sm_count, threads, 0, s>>>(d_out, d_in, d_cyc, iters);
-    g.launches++;
-    CU(cudaEventRecord(e1, s));
-    CU(cudaStreamSynchronize(s));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    std::vector<unsigned long long> hc(g.sm_count);
-    CU(cudaMemcpy(hc.data(), d_cyc, g.sm_count * 8, cudaMemcpyDeviceToHost));
-    double cavg = 0;
-    for (int i = 0; i < g.sm_count; i++) cavg += (double)hc[i];
-    cavg /= g.sm_count;
-    const double inst = 16.0 * 8.0 * iters * threads * (double)g.sm_count;
-    const double rate = inst / (ms * 1e-3) / 1e9;
-    if (rate > best_rate) { best_rate = rate; best_mhz = cavg / (ms * 1e-3) / 1e6; }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-  }
-  if (imad_wide_ginst_per_s) *imad_wide_ginst_per_s = best_rate;
-  if (sm_mhz) *sm_mhz = best_mhz;
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_cyc);
-  return B381_OK;
-}
-
-}  // extern "C"
+#include "host_api.inc"

@@ -350,34 +350,52 @@ B381_DEV B381_INL int prog_literal(const Ctx& cx, const uint32_t* g1p, const uin
   return err;
 }
 
-// ---- subgroup membership: [r] P == infinity, r the 255-bit group order -----------
-// The scalar is public and shared by the whole batch, so the double-and-add ladder has uniform
-// control flow apart from the identity / equal-point cases inside the Jacobian formulas (ark-ec
-// short-Weierstrass Jacobian add / double, tower.cuh jac_add / jac_double).  G1 points are embedded in
-// Fq2 (imaginary parts zero): the curve y^2 = x^3 + 4 and the formulas are the same over the subfield.
-// pt: affine x, y in the C-ABI layout (G1: 24 words, G2: 48 words).  out: 1 = in the subgroup.
-B381_DEV B381_INL int prog_subgroup_check(const Ctx& cx, const uint32_t* pt, int is_g2, int inf, uint8_t* out) {
+// ---- G2 endomorphism programs: subgroup membership and cofactor clearing -----------------
+// ark-bls12-381 0.4 curves/g2.rs, restated in the test oracle (g2_psi, g2_in_subgroup_fast,
+// g2_clear_cofactor).  The group law is the ark-ec Jacobian add / double of tower.cuh (jac_add / jac_double), the
+// scalar |x| is public: uniform ladders apart from the special cases inside the formulas.  (G1: g1.cuh.)
+
+// R <- [|x|] Base, Base Jacobian in slots Base..Base+2 (63 doublings + 5 additions); T = 9 scratch slots
+B381_DEV B381_INL void jac_mul_x_abs(const Ctx& cx, int R, int Base, int T) {
+  for (int k = 0; k < 3; k++) lin(cx, R + k, Base + k, -1, L_COPY);
+  const uint64_t xabs = B381_X_ABS;
+  for (int b = 62; b >= 0; b--) {
+    jac_double(cx, R, T);
+    if ((xabs >> b) & 1) jac_add(cx, R, Base, T);
+  }
+}
+B381_DEV B381_INL void jac_neg(const Ctx& cx, int R) { lin(cx, R + 1, R + 1, -1, L_NEG); }
+
+// psi(Q) for affine Q in slots Q, Q+1 -> slots D, D+1 (Z = 1 in D+2)
+B381_DEV B381_INL void g2_psi_affine(const Ctx& cx, int D, int Q) {
+  f2_mul_psi(S_(D), S_(Q), 0, 1);
+  f2_mul_psi(S_(D + 1), S_(Q + 1), 1, 1);
+  f2_set_small(S_(D + 2), 1);
+}
+
+// is the Jacobian point in R equal to the AFFINE point in A, A+1?  X == ax Z^2 and Y == ay Z^3; t = 3 scratch slots
+B381_DEV B381_INL bool jac_equals_affine(const Ctx& cx, int R, int A, int t) {
+  if (f2_is_zero(S_(R + 2))) return false;
+  sqr(cx, t, R + 2);
+  mul(cx, t + 1, A, t);
+  if (!f2_equal(S_(t + 1), S_(R))) return false;
+  mul(cx, t, t, R + 2);
+  mul(cx, t + 1, A + 1, t);
+  return f2_equal(S_(t + 1), S_(R + 1));
+}
+
+// ark g2.rs is_in_correct_subgroup_assuming_on_curve (eprint 2021/1130 section 4): psi(P) == [x] P, x = -|x|
+B381_DEV B381_INL int prog_g2_in_subgroup(const Ctx& cx, const uint32_t* pt, int inf, uint8_t* out) {
   int err = 0;
   if (inf & 1) { *out = 1; return 0; }              // the identity is in every subgroup
-  const int Q = 0, R = 3, T = 6;                    // Q (affine, Z = 1), accumulator R, 9 scratch slots
-  if (is_g2) {
-    if (!f2_load_ext(S_(Q), pt)) err |= ERR_NOT_CANONICAL;
-    if (!f2_load_ext(S_(Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
-  } else {
-    uint32_t w[24];
-    for (int c = 0; c < 2; c++) {
-      for (int k = 0; k < 12; k++) { w[k] = pt[12 * c + k]; w[12 + k] = 0; }
-      if (!f2_load_ext(S_(Q + c), w)) err |= ERR_NOT_CANONICAL;
-    }
-  }
+  const int Q = 0, R = 3, PS = 6, T = 9;            // Q (affine, Z = 1), [|x|] Q, psi(Q), 9 scratch slots
+  if (!f2_load_ext(S_(Q), pt)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
   f2_set_small(S_(Q + 2), 1);
-  for (int k = 0; k < 3; k++) lin(cx, R + k, Q + k, -1, L_COPY);
-  const uint64_t rw[4] = B381_R_ORDER_U64;          // little-endian limbs of r; bit 254 is the leading one
-  for (int b = 253; b >= 0; b--) {
-    jac_double(cx, R, T);
-    if ((rw[b >> 6] >> (b & 63)) & 1) jac_add(cx, R, Q, T);
-  }
-  *out = f2_is_zero(S_(R + 2)) ? 1 : 0;
+  jac_mul_x_abs(cx, R, Q, T);
+  jac_neg(cx, R);                                   // [x] Q
+  g2_psi_affine(cx, PS, Q);
+  *out = jac_equals_affine(cx, R, PS, T) ? 1 : 0;
   return err;
 }
 
@@ -425,22 +443,46 @@ B381_DEV B381_INL int load_affine_point(const Ctx& cx, int Q, const uint32_t* pt
   return err;
 }
 
-// sum of cnt points in the PACKED layout (w + 1 words per point: affine coordinates, then the identity
-// flag) -> one packed point.  One level of the reduction tree behind b381_g1/g2_sum and the MSM.
-B381_DEV B381_INL int prog_point_sum(const Ctx& cx, const uint32_t* in, size_t cnt, int is_g2, uint32_t* out) {
+// G2: sum of cnt affine points (48 words each, identity flags in a byte array, may be null) -> one affine point +
+// flag.  One level of the reduction tree behind b381_g2_sum and the G2 multi-scalar multiplication.
+B381_DEV B381_INL int prog_g2_point_sum(const Ctx& cx, const uint32_t* in, const uint8_t* in_inf, size_t cnt, uint32_t* out, uint8_t* out_inf) {
   int err = 0;
   const int Q = 0, R = 3, T = 6, ZI = 15;
-  const int w = is_g2 ? 48 : 24;
-  f2_set_small(S_(R), 0); f2_set_small(S_(R + 1), 1); f2_set_small(S_(R + 2), 0);     // identity
+  f2_set_small(S_(R), 1); f2_set_small(S_(R + 1), 1); f2_set_small(S_(R + 2), 0);     // identity (1, 1, 0)
   for (size_t i = 0; i < cnt; i++) {
-    const uint32_t* p = in + (size_t)(w + 1) * i;
-    if (p[w] & 1) continue;
-    err |= load_affine_point(cx, Q, p, is_g2);
+    if (in_inf && (in_inf[i] & 1)) continue;
+    err |= load_affine_point(cx, Q, in + 48 * i, 1);
     jac_add(cx, R, Q, T);
   }
-  uint8_t f = 0;
-  jac_store_affine(cx, R, ZI, is_g2, out, &f);
-  out[w] = f;
+  jac_store_affine(cx, R, ZI, 1, out, out_inf);
+  return err;
+}
+
+// ark g2.rs clear_cofactor (Budroni-Pintore, eprint 2017/419 section 4.1):
+//   [x^2 - x - 1] P + [x - 1] psi(P) + psi^2(2 P)  =  psi^2(2P) + (-[X](-[X] P + psi P)) - (-[X] P) - psi P - P,  X = |x|
+B381_DEV B381_INL int prog_g2_clear_cofactor(const Ctx& cx, const uint32_t* pt, int inf, uint32_t* out, uint8_t* out_inf) {
+  int err = 0;
+  if (inf & 1) { for (int i = 0; i < 48; i++) out[i] = 0; *out_inf = 1; return 0; }
+  const int P0 = 0, XP = 3, PS = 6, P2 = 9, TM = 12, AC = 15, T = 18, ZI = 27;
+  if (!f2_load_ext(S_(P0), pt)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(P0 + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
+  f2_set_small(S_(P0 + 2), 1);
+  jac_mul_x_abs(cx, XP, P0, T);
+  jac_neg(cx, XP);                                  // x_p = [x] P
+  g2_psi_affine(cx, PS, P0);                        // psi_p
+  for (int k = 0; k < 3; k++) lin(cx, P2 + k, P0 + k, -1, L_COPY);
+  jac_double(cx, P2, T);                            // 2 P ; psi^2 (X, Y, Z) = (c X, -Y, Z), c in Fq
+  f2_mul_psi(S_(P2), S_(P2), 2, 0);
+  jac_neg(cx, P2);                                  // psi2_p2
+  for (int k = 0; k < 3; k++) lin(cx, TM + k, XP + k, -1, L_COPY);
+  jac_add(cx, TM, PS, T);                           // tmp = x_p + psi_p
+  jac_mul_x_abs(cx, AC, TM, T);
+  jac_neg(cx, AC);                                  // tmp2 = [x] tmp = [x^2] P + [x] psi(P)
+  jac_add(cx, AC, P2, T);                           // + psi2_p2
+  jac_neg(cx, XP); jac_add(cx, AC, XP, T);          // - x_p
+  jac_neg(cx, PS); jac_add(cx, AC, PS, T);          // - psi_p
+  jac_neg(cx, P0); jac_add(cx, AC, P0, T);          // - P
+  jac_store_affine(cx, AC, ZI, 1, out, out_inf);
   return err;
 }
 

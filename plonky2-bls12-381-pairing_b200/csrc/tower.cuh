@@ -206,6 +206,7 @@ struct ConstTab {
   limb_t frob[3][5][2][NL];   // gamma_k[j] = xi^(j (p^k-1)/6), k = 1..3, j = 1..5, (c0, c1)
   limb_t one[NL];
   uint8_t pm2_nib[96];         // p - 2 as 4-bit windows, MSB first
+  limb_t psi[3][2][NL];        // psi: 1 / xi^((p-1)/3), 1 / xi^((p-1)/2); psi^2: 1 / xi^((p^2-1)/3) (in Fp; c1 = 0)
 };
 #define B381_CONST_INIT { \
   { { {B381_FROB1_1_C0, B381_FROB1_1_C1}, {B381_FROB1_2_C0, B381_FROB1_2_C1}, {B381_FROB1_3_C0, B381_FROB1_3_C1}, \
@@ -214,10 +215,11 @@ struct ConstTab {
       {B381_FROB2_4_C0, B381_FROB2_4_C1}, {B381_FROB2_5_C0, B381_FROB2_5_C1} }, \
     { {B381_FROB3_1_C0, B381_FROB3_1_C1}, {B381_FROB3_2_C0, B381_FROB3_2_C1}, {B381_FROB3_3_C0, B381_FROB3_3_C1}, \
       {B381_FROB3_4_C0, B381_FROB3_4_C1}, {B381_FROB3_5_C0, B381_FROB3_5_C1} } }, \
-  B381_ONE, B381_PM2_NIBBLES }
+  B381_ONE, B381_PM2_NIBBLES, \
+  { {B381_PSI_CX_C0, B381_PSI_CX_C1}, {B381_PSI_CY_C0, B381_PSI_CY_C1}, {B381_PSI2_CX, {0}} } }
 
 #if defined(__CUDACC__)
-__constant__ ConstTab g_ct = B381_CONST_INIT;
+static __constant__ ConstTab g_ct = B381_CONST_INIT;
 #else
 static const ConstTab g_ct = B381_CONST_INIT;
 #endif
@@ -470,6 +472,19 @@ B381_NOINL void f2_mul_gamma(u4* r, const u4* a, int k, int j, int conj) {
   } else {
     f2_mul_reg(r0, r1, a0, a1, g0, g1);
   }
+  st_f2(r, r0, r1);
+}
+
+// r = (conj ? conj(a) : a) * psi-constant idx (0: psi x, 1: psi y, 2: psi^2 x, a real constant)
+// -- the G2 endomorphisms of ark-bls12-381 g2.rs p_power_endomorphism / double_p_power_endomorphism
+B381_NOINL void f2_mul_psi(u4* r, const u4* a, int idx, int conj) {
+  Fp a0, a1, g0, g1, r0, r1;
+  ld_f2(a0, a1, a);
+  if (conj) { fp_neg(a1, a1); HOT_OFF(a1, a1); }
+  fp_const(g0, g_ct.psi[idx][0]);
+  fp_const(g1, g_ct.psi[idx][1]);
+  if (idx == 2) f2_mulfp_reg(r0, r1, a0, a1, g0);
+  else f2_mul_reg(r0, r1, a0, a1, g0, g1);
   st_f2(r, r0, r1);
 }
 

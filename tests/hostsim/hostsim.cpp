@@ -6,8 +6,10 @@
 // worst-case limb / column / magnitude bounds of the lazy arithmetic along the executed path.
 // It is NOT part of the product: libb381.so never links or loads it.
 #include <cstring>
+#include <vector>
 #include "../../plonky2-bls12-381-pairing_b200/csrc/programs.cuh"
 #include "../../plonky2-bls12-381-pairing_b200/csrc/helpers.cuh"
+#include "../../plonky2-bls12-381-pairing_b200/csrc/g1.cuh"
 
 using namespace b381;
 
@@ -155,14 +157,71 @@ int hs_g2_serialize(const uint32_t* g2, int inf, int compressed, uint8_t* out) {
 int hs_fp12_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f12_inv(cx, a, out); }
 int hs_fp6_inv_ext(const uint32_t* a, uint32_t* out) { Ctx cx = make_ctx(); return prog_f6_inv(cx, a, out); }
 
-int hs_subgroup_check(const uint32_t* pt, int is_g2, int inf, uint8_t* out) { Ctx cx = make_ctx(); return prog_subgroup_check(cx, pt, is_g2, inf, out); }
+int hs_subgroup_check(const uint32_t* pt, int is_g2, int inf, uint8_t* out) {
+  if (!is_g2) return prog_g1_in_subgroup(pt, inf, out);
+  Ctx cx = make_ctx();
+  return prog_g2_in_subgroup(cx, pt, inf, out);
+}
+
+int hs_clear_cofactor(const uint32_t* pt, int is_g2, int inf, uint32_t* out, uint8_t* out_inf) {
+  if (!is_g2) return prog_g1_clear_cofactor(pt, inf, out, out_inf);
+  Ctx cx = make_ctx();
+  return prog_g2_clear_cofactor(cx, pt, inf, out, out_inf);
+}
 
 int hs_scalar_mul(const uint32_t* pt, int is_g2, int inf, const uint32_t* k, uint32_t* out, uint8_t* out_inf) {
+  if (!is_g2) return prog_g1_scalar_mul(pt, inf, k, out, out_inf);
   Ctx cx = make_ctx();
   return prog_scalar_mul(cx, pt, is_g2, inf, k, out, out_inf);
 }
 
-int hs_point_sum(const uint32_t* packed, size_t cnt, int is_g2, uint32_t* out) { Ctx cx = make_ctx(); return prog_point_sum(cx, packed, cnt, is_g2, out); }
+int hs_g2_point_sum(const uint32_t* pts, const uint8_t* inf, size_t cnt, uint32_t* out, uint8_t* out_inf) {
+  Ctx cx = make_ctx();
+  return prog_g2_point_sum(cx, pts, inf, cnt, out, out_inf);
+}
+
+// the G1 bucket method exactly as the kernels of kernels.cu stage it (k_g1_to_raw, k_msm_digits x 2, k_msm_scan,
+// k_msm_bucket_sums, k_msm_chunks, k_g1_jac_sums, k_msm_final), run sequentially on the host
+int hs_g1_msm(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, size_t n, int c, int CH, uint32_t* out24, uint8_t* out_inf) {
+  int err = 0;
+  const int W = (256 + c - 1) / c;
+  const uint32_t B = 1u << c;
+  std::vector<uint32_t> raw(n * G1_RAW_AFF);
+  for (size_t i = 0; i < n; i++) { G1A p; err |= g1_load_ext(p, pts + 24 * i); g1_st_raw_aff(raw.data() + G1_RAW_AFF * i, p); }
+  const size_t m = (size_t)W * B;
+  std::vector<unsigned int> cnt(m, 0), start(m + 1, 0), cursor(m, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (inf && (inf[i] & 1)) continue;
+    for (int w = 0; w < W; w++) { uint32_t d = msm_digit(scalars + 8 * i, w, c); if (d) cnt[(size_t)w * B + d]++; }
+  }
+  for (size_t b = 0; b < m; b++) { start[b + 1] = start[b] + cnt[b]; cursor[b] = start[b]; }
+  std::vector<uint32_t> idx(start[m] ? start[m] : 1);
+  for (size_t i = 0; i < n; i++) {
+    if (inf && (inf[i] & 1)) continue;
+    for (int w = 0; w < W; w++) { uint32_t d = msm_digit(scalars + 8 * i, w, c); if (d) idx[cursor[(size_t)w * B + d]++] = (uint32_t)i; }
+  }
+  std::vector<uint32_t> buckets(m * G1_RAW_JAC);
+  for (size_t b = 0; b < m; b++) { G1J acc; msm_bucket_sum(acc, raw.data(), idx.data(), start[b], start[b + 1]); g1_st_raw_jac(buckets.data() + G1_RAW_JAC * b, acc); }
+  const uint32_t nchunk = (B + CH - 1) / CH;
+  std::vector<uint32_t> partial((size_t)W * nchunk * G1_RAW_JAC), sums((size_t)W * G1_RAW_JAC);
+  for (int w = 0; w < W; w++)
+    for (uint32_t j = 0; j < nchunk; j++) {
+      uint32_t lo = j * CH, hi = lo + CH < B ? lo + CH : B;
+      if (lo == 0) lo = 1;
+      G1J r;
+      if (lo < hi) msm_chunk_weighted(r, buckets.data() + (size_t)G1_RAW_JAC * w * B, lo, hi); else g1_set_identity(r);
+      g1_st_raw_jac(partial.data() + G1_RAW_JAC * ((size_t)w * nchunk + j), r);
+    }
+  for (int w = 0; w < W; w++) {
+    G1J acc; g1_set_identity(acc);
+    for (uint32_t j = 0; j < nchunk; j++) { G1J q; g1_ld_raw_jac(q, partial.data() + G1_RAW_JAC * ((size_t)w * nchunk + j)); g1_add(acc, acc, q); }
+    g1_st_raw_jac(sums.data() + G1_RAW_JAC * w, acc);
+  }
+  G1J r;
+  msm_combine_windows(r, sums.data(), W, c);
+  g1_store_jac_ext(out24, out_inf, r);
+  return err;
+}
 
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS

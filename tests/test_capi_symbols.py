@@ -43,7 +43,7 @@ def test_product_never_imports_the_oracle():
     pkg = os.path.join(util.ROOT, "plonky2-bls12-381-pairing_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".rs")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".rs")):
                 text = open(os.path.join(dp, f)).read()
                 for needle in ("b381_oracle", "b381_ref", "libb381_hostsim", "oracle/_build", "oracle/_ref"):
                     assert needle not in text, (f, needle)

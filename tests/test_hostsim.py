@@ -371,25 +371,50 @@ def test_scalar_mul(hs):
 
 
 def test_point_sum(hs):
-    """One level of the point-reduction tree (packed layout) against the oracle's group law: distinct
-    points, a repeated point (doubling case), P + (-P), identity flags."""
+    """One level of the G2 point-reduction tree against the oracle's group law: distinct points, a repeated
+    point (doubling case), P + (-P), identity flags."""
     r = util.rng(37)
-    pts = [o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER)) for _ in range(5)]
-    pts += [pts[0], (pts[1][0], (o.P - pts[1][1]) % o.P)]
-    packed = []
-    for i, p in enumerate(pts):
-        packed += o.g1_to_limbs32(p) + [1 if i == 2 else 0]
-    out = u(25)
-    assert hs.hs_point_sum(A(packed), ctypes.c_size_t(len(pts)), 0, out) == 0
+    pts = [o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER)) for _ in range(4)]
+    pts += [pts[0], (pts[1][0], o.f2_neg(pts[1][1]))]
+    words = sum((o.g2_to_limbs32(p) for p in pts), [])
+    inf = (ctypes.c_uint8 * len(pts))(*[1 if i == 2 else 0 for i in range(len(pts))])
+    out, f = u(48), (ctypes.c_uint8 * 1)()
+    assert hs.hs_g2_point_sum(A(words), inf, ctypes.c_size_t(len(pts)), out, f) == 0
     acc = None
     for i, p in enumerate(pts):
         if i != 2:
-            acc = o.g1_add(acc, p)
-    assert out[24] == 0 and list(out)[:24] == o.g1_to_limbs32(acc)
+            acc = o.g2_add(acc, p)
+    assert f[0] == 0 and list(out) == o.g2_to_limbs32(acc)
     q = o.g2_mul(o.G2_GEN, 5)
-    packed2 = o.g2_to_limbs32(q) + [0] + o.g2_to_limbs32((q[0], o.f2_neg(q[1]))) + [0]
-    out2 = u(49)
-    assert hs.hs_point_sum(A(packed2), ctypes.c_size_t(2), 1, out2) == 0 and out2[48] == 1
+    w2 = o.g2_to_limbs32(q) + o.g2_to_limbs32((q[0], o.f2_neg(q[1])))
+    assert hs.hs_g2_point_sum(A(w2), None, ctypes.c_size_t(2), out, f) == 0 and f[0] == 1
+
+
+def test_g1_bucket_msm(hs):
+    """the G1 bucket method staged as on the device (host simulation of every kernel), against the oracle:
+    random points and 256-bit scalars, repeated points (doubling inside a bucket), P and -P in one bucket,
+    identity flags, zero scalars, several window widths / chunk sizes."""
+    r = util.rng(38)
+    f = (ctypes.c_uint8 * 1)()
+    for n, c, ch in ((1, 4, 4), (9, 3, 2), (40, 5, 8), (40, 7, 32)):
+        ks = [r.randrange(0, 1 << 256) for _ in range(n)]
+        pts = [o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER)) for _ in range(n)]
+        inf = [0] * n
+        if n >= 9:
+            pts[3] = pts[2]; ks[3] = ks[2]                         # same point, same digits: doubling inside buckets
+            pts[5] = o.g1_neg(pts[4]); ks[5] = ks[4]               # P and -P with equal scalars: buckets cancel
+            ks[6] = 0
+            inf[7] = 1
+            ks[8] = (1 << 256) - 1
+        want = None
+        for p_, k_, i_ in zip(pts, ks, inf):
+            if not i_:
+                want = o.g1_add(want, o.g1_mul(p_, k_))
+        words = sum((o.g1_to_limbs32(p_) for p_ in pts), [])
+        sc = sum(([(k_ >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for k_ in ks), [])
+        out = u(24)
+        assert hs.hs_g1_msm(A(words), (ctypes.c_uint8 * n)(*inf), A(sc), ctypes.c_size_t(n), c, ch, out, f) == 0
+        assert (f[0] == 1 and want is None) or (f[0] == 0 and list(out) == o.g1_to_limbs32(want)), (n, c, ch)
 
 
 def test_literal_vertical_line_branch(hs):
@@ -438,3 +463,51 @@ def test_adversarial_operands(hs):
         if k < 3:
             assert hs.hs_final_exp(A(o.f12_to_limbs32(x)), o12) == 0
             assert o.f12_eq(o.f12_from_limbs32(list(o12)), o.ark_final_exponentiation(x))
+
+
+def _curve_points_outside_subgroups():
+    """curve points decompressed from small x: (almost surely) outside the prime-order subgroups"""
+    g1s, g2s = [], []
+    x = 1
+    while len(g1s) < 3:
+        res = o.g1_deserialize(bytes([0x80]) + x.to_bytes(47, "big"), True)
+        if res[0] == "ok":
+            g1s.append(res[1])
+        x += 1
+    x = 1
+    while len(g2s) < 2:
+        res = o.g2_deserialize(bytes([0x80]) + bytes(47) + x.to_bytes(48, "big"), True)
+        if res[0] == "ok":
+            g2s.append(res[1])
+        x += 1
+    return g1s, g2s
+
+
+def test_endomorphism_subgroup_checks_and_cofactor_clearing(hs):
+    """the endomorphism tests (G1: (BETA x, y) == -[x^2] P; G2: psi(P) == [x] P) agree with [r] P == identity, and
+    cofactor clearing equals multiplication by the RFC 9380 effective cofactors (oracle: g1/g2_clear_cofactor)."""
+    b = (ctypes.c_uint8 * 1)()
+    g1s, g2s = _curve_points_outside_subgroups()
+    r = util.rng(37)
+    g1s += [o.g1_mul(o.G1_GEN, r.randrange(1, o.R_ORDER)), o.G1_GEN]
+    g2s += [o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER))]
+    for P1 in g1s:
+        want = o.g1_mul(P1, o.R_ORDER) is None
+        assert o.g1_in_subgroup_fast(P1) == want
+        assert hs.hs_subgroup_check(A(o.g1_to_limbs32(P1)), 0, 0, b) == 0 and bool(b[0]) == want
+        out = u(24)
+        assert hs.hs_clear_cofactor(A(o.g1_to_limbs32(P1)), 0, 0, out, b) == 0
+        C = o.g1_clear_cofactor(P1)
+        assert C == o.g1_mul(P1, o.G1_H_EFF)
+        assert (b[0] == 1 and C is None) or (b[0] == 0 and list(out) == o.g1_to_limbs32(C))
+    for Q in g2s:
+        want = o.g2_mul(Q, o.R_ORDER) is None
+        assert o.g2_in_subgroup_fast(Q) == want
+        assert hs.hs_subgroup_check(A(o.g2_to_limbs32(Q)), 1, 0, b) == 0 and bool(b[0]) == want
+        out = u(48)
+        assert hs.hs_clear_cofactor(A(o.g2_to_limbs32(Q)), 1, 0, out, b) == 0
+        C = o.g2_clear_cofactor(Q)
+        assert C == o.g2_mul(Q, o.G2_H_EFF)
+        assert b[0] == 0 and list(out) == o.g2_to_limbs32(C)
+        assert o.g2_in_subgroup_fast(C)
+    assert hs.hs_clear_cofactor(A([0] * 24), 0, 1, u(24), b) == 0 and b[0] == 1
