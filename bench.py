@@ -233,6 +233,7 @@ def main():
     value = n * world * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
     del dout
+    torch.cuda.empty_cache()
 
     # ---- end to end through the host-pointer C ABI (pinned host memory) --------------------------
     h1 = torch.from_numpy(g1.view(np.int32)).pin_memory()
@@ -247,7 +248,7 @@ def main():
     step_host()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = args.steps
     for _ in range(e2e_steps):
         step_host()
     barrier()
@@ -280,6 +281,29 @@ def main():
         cfg5 = {"pairs": 2 * half * world, "seconds": dt, "pairs_per_s": 2 * half * world / dt,
                 "result_is_one": bool(np.array_equal(res, one)),
                 "exchange": "all_gather of one Fq12 (576 B) per rank, then b381_fp12_product + one final exp" if world > 1 else "single rank: no exchange"}
+
+    # ---- BASELINE config #4 as literally written: 2^20 pairs in TOTAL, sharded contiguously over the ranks (strong scaling) ----
+    strong = None
+    if not args.no_extras and n >= (1 << 20) // world:
+        ns = (1 << 20) // world
+        souts = torch.empty(ns * 144, dtype=torch.int32, device=dev)
+        def step_strong():
+            L.check(lib.b381_pairing_dev(d1.data_ptr(), d2.data_ptr(), None, souts.data_ptr(), ns, L.MODE_ARK, st))
+        step_strong()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(3):
+            step_strong()
+        s1.record(stream)
+        barrier()
+        sms = max_over_ranks(s0.elapsed_time(s1)) / 3
+        sms_n = torch.cuda.get_device_properties(dev).multi_processor_count
+        rounds = -(-ns // (sms_n * 256))
+        strong = {"pairs_total": 1 << 20, "pairs_per_gpu": ns, "ms": sms, "pairs_per_s": (1 << 20) / sms * 1e3,
+                  "rounds_per_gpu": rounds, "round_fill": ns / (rounds * sms_n * 256),
+                  "note": "a launch is one round of #SM x 256 pairs and a partly filled last round costs a full one: the ratio to N x the 1-GPU rate is bounded by round_fill"}
+        del souts
 
     if rank != 0:
         if world > 1:
@@ -318,7 +342,17 @@ def main():
     extras = {}
     if cfg5 is not None:
         extras["config5_multi_pairing_bls_shape"] = cfg5
+    if strong is not None:
+        extras["config4_strong_scaling_2p20_total"] = strong
     if not args.no_extras:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))           # GB/s: measured copy bandwidth of this pool, else the recipe's fallback
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
         def time_dev(fn, reps=3):
             fn(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,12 +362,16 @@ def main():
                 t = a.elapsed_time(b)
                 best = t if best is None else min(best, t)
             return best
+
+        def imad_frac(units_per_s, fp_muls_per_unit):
+            return units_per_s * fp_muls_per_unit * MACS_PER_FP_MUL / 1e9 / pk.value
+
         m = 1 << 16
         mout = torch.empty(m * 144, dtype=torch.int32, device=dev)
         t = time_dev(lambda: L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), m, 0, st)))
-        extras["config3_miller_loops_per_s_2p16"] = m / t * 1e3
+        extras["config3_miller_loops_2p16"] = {"per_s": m / t * 1e3, "imad_frac": imad_frac(m / t * 1e3, FP_MULS_MILLER)}
         t = time_dev(lambda: L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), n, 0, st)), reps=2)
-        extras["config5_multi_miller_pairs_per_s_2p20"] = n / t * 1e3
+        extras["config5_multi_miller_pairs_2p20"] = {"per_s": n / t * 1e3, "note": "two pairs per thread share the squarings; tree reduction included"}
         # G2Prepared stage: coefficients/s and Miller loops/s against prepared Q's, 2^16 pairs
         co = torch.empty(m * L.G2PREP_WORDS, dtype=torch.int32, device=dev)
         t = time_dev(lambda: L.check(lib.b381_g2_prepare_dev(d2.data_ptr(), co.data_ptr(), m, 0, st)), reps=2)
@@ -344,17 +382,80 @@ def main():
         L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mref.data_ptr(), m, 0, st))
         torch.cuda.synchronize()
         extras["miller_prepared_equals_unprepared"] = bool(torch.equal(mout, mref))
-        del co, mref
-        k = 1 << 22
-        fa = torch.from_numpy(np.tile(g1[:12], k).view(np.int32)).to(dev); fb = torch.from_numpy(np.tile(g1[12:24], k).view(np.int32)).to(dev)
-        fo = torch.empty(k * 12, dtype=torch.int32, device=dev)
-        t = time_dev(lambda: L.check(lib.b381_fp_mul_chain_dev(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k, 256, st)))
-        extras["config2_fp_mul_chain_G_per_s"] = k * 259 / t / 1e6
-        t = time_dev(lambda: L.check(lib.b381_fp_mul_dev(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k, st)))
-        extras["config2_fp_mul_stream_G_per_s"] = k / t / 1e6
-        extras["config2_fp_mul_stream_GBps"] = k * 144 / t / 1e6
+        del co, mref, mout
+
+        # ---- BASELINE config #2: Fp / Fp2 / Fp12 / MyFq12 products on 2^26 random elements (device-resident), each against
+        # the integer-multiply roofline AND the HBM roofline (algorithmic bytes = 3 x element size) ----
+        def rand_canon(count_fp):
+            x = torch.randint(-(1 << 31), (1 << 31) - 1, (count_fp, 12), dtype=torch.int32, device=dev)
+            x[:, 11] &= 0x0FFFFFFF                         # < 2^380 < p: canonical Montgomery limbs
+            return x.reshape(-1)
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        cfg2 = {}
+        for name, fn, fp_per_el, fpmuls in (("fp", lib.b381_fp_mul_dev, 1, 1), ("fp2", lib.b381_fp2_mul_dev, 2, 3),
+                                            ("fp12", lib.b381_fp12_mul_dev, 12, 54), ("myfq12_wbasis", lib.b381_fp12_mul_wbasis_dev, 12, 54)):
+            k = 1 << 26
+            while 3 * k * fp_per_el * 48 > 0.8 * free_b:
+                k >>= 1
+            fa, fb = rand_canon(k * fp_per_el), rand_canon(k * fp_per_el)
+            fo = torch.empty(k * fp_per_el * 12, dtype=torch.int32, device=dev)
+            t = time_dev(lambda: L.check(fn(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k, st)), reps=2)
+            per_s = k / t * 1e3
+            cfg2[name] = {"elements": k, "elements_per_s": per_s, "fp_mul_per_s": per_s * fpmuls,
+                          "imad_frac": imad_frac(per_s, fpmuls), "GBps": per_s * 3 * fp_per_el * 48 / 1e9,
+                          "hbm_frac": per_s * 3 * fp_per_el * 48 / 1e9 / hbm_peak}
+            if name == "fp":
+                k2 = 1 << 22
+                tc = time_dev(lambda: L.check(lib.b381_fp_mul_chain_dev(fa.data_ptr(), fb.data_ptr(), fo.data_ptr(), k2, 256, st)))
+                cfg2["fp_chain_register_resident"] = {"fp_mul_per_s": k2 * 259 / tc * 1e3, "imad_frac": imad_frac(k2 * 259 / tc * 1e3, 1) * 325 / 300,
+                                                      "note": "256 dependent 13-word products per element held in registers (325 IMAD.WIDE each)"}
+            del fa, fb, fo
+        cfg2["_notes"] = ("uniform random canonical elements generated on the device; MyFq12 = 144 Fp-mul schoolbook in the reference, computed in the "
+                          "tower (54) and permuted; hbm peak %.0f GB/s %s" % (hbm_peak, hbm_src))
+        extras["config2_field_products_2p26"] = cfg2
         L.check(lib.b381_check_dev(st))
-        # witness helpers, through the host-pointer API (H2D + kernel + D2H), 2^17 elements
+
+        # ---- SURVEY 8f ranks 2-4 on device-resident data (CUDA events; no host copies) ----
+        grp = {}
+        kp = 1 << 16
+        p1 = d1[:kp * 24]; p2 = d2[:kp * 48]
+        o1 = torch.empty(kp * 24, dtype=torch.int32, device=dev); o2 = torch.empty(kp * 48, dtype=torch.int32, device=dev)
+        f8 = torch.empty(kp, dtype=torch.uint8, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_g1_in_subgroup_dev(p1.data_ptr(), None, f8.data_ptr(), kp, st)), reps=2)
+        grp["g1_subgroup_checks_per_s"] = kp / t * 1e3
+        ok1 = bool(f8.all().item())
+        t = time_dev(lambda: L.check(lib.b381_g2_in_subgroup_dev(p2.data_ptr(), None, f8.data_ptr(), kp, st)), reps=2)
+        grp["g2_subgroup_checks_per_s"] = kp / t * 1e3
+        grp["subgroup_all_in"] = ok1 and bool(f8.all().item())
+        t = time_dev(lambda: L.check(lib.b381_g1_clear_cofactor_dev(p1.data_ptr(), None, o1.data_ptr(), f8.data_ptr(), kp, st)), reps=2)
+        grp["g1_clear_cofactor_per_s"] = kp / t * 1e3
+        t = time_dev(lambda: L.check(lib.b381_g2_clear_cofactor_dev(p2.data_ptr(), None, o2.data_ptr(), f8.data_ptr(), kp, st)), reps=2)
+        grp["g2_clear_cofactor_per_s"] = kp / t * 1e3
+        sc = torch.randint(-(1 << 31), (1 << 31) - 1, (n * 8,), dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_g1_scalar_mul_dev(p1.data_ptr(), None, sc.data_ptr(), o1.data_ptr(), f8.data_ptr(), kp, st)), reps=2)
+        grp["g1_scalar_muls_per_s"] = kp / t * 1e3
+        t = time_dev(lambda: L.check(lib.b381_g2_scalar_mul_dev(p2.data_ptr(), None, sc.data_ptr(), o2.data_ptr(), f8.data_ptr(), kp, st)), reps=2)
+        grp["g2_scalar_muls_per_s"] = kp / t * 1e3
+        r1 = torch.empty(24, dtype=torch.int32, device=dev); rf = torch.empty(1, dtype=torch.uint8, device=dev)
+        # distinct random points for the MSM: [s_i] P_i of the tiled fixture points, made on the device
+        mp = torch.empty(n * 24, dtype=torch.int32, device=dev); mf = torch.empty(n, dtype=torch.uint8, device=dev)
+        L.check(lib.b381_g1_scalar_mul_dev(d1.data_ptr(), None, sc.data_ptr(), mp.data_ptr(), mf.data_ptr(), n, st))
+        sc2 = torch.randint(-(1 << 31), (1 << 31) - 1, (n * 8,), dtype=torch.int32, device=dev)
+        for logn in (16, 20):
+            nn = 1 << logn
+            if nn > n:
+                continue
+            t = time_dev(lambda: L.check(lib.b381_g1_msm_dev(mp.data_ptr(), None, sc2.data_ptr(), r1.data_ptr(), rf.data_ptr(), nn, st)), reps=2)
+            # bucket method at window c: ceil(256 / c) mixed additions of 11 Fp-mul per point
+            c = 16 if logn >= 17 else 8; w = 256 // c
+            grp["g1_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": c, "imad_frac_bucket_additions": imad_frac(nn / t * 1e3, w * 11)}
+        t = time_dev(lambda: L.check(lib.b381_g1_sum_dev(mp.data_ptr(), None, r1.data_ptr(), rf.data_ptr(), n, st)), reps=2)
+        grp["g1_sum_points_per_s"] = n / t * 1e3
+        L.check(lib.b381_check_dev(st))
+        extras["groups_device_resident"] = grp
+        del o1, o2, f8, sc, sc2, mp, mf
+
+        # witness helpers and wire formats through the host-pointer API (H2D + kernel + D2H)
         import time as _t
         kh = 1 << 17
         ha = np.tile(g1[:12], kh).astype(np.uint32)
@@ -367,34 +468,26 @@ def main():
         def time_host(fn):
             fn()
             t0 = _t.perf_counter(); fn(); return _t.perf_counter() - t0
-        extras["helpers_fp_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_inv(L.u32(ha)[1], L.u32(ho)[1], kh)))
-        extras["helpers_fp2_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp2_inv(L.u32(h2)[1], L.u32(ho2)[1], kh)))
-        extras["helpers_fp12_inv_per_s"] = (1 << 13) / time_host(lambda: L.check(lib.b381_fp12_inv(L.u32(sq)[1], L.u32(so)[1], 1 << 13)))
+        hp = {}
+        hp["fp_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_inv(L.u32(ha)[1], L.u32(ho)[1], kh)))
+        hp["fp2_inv_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp2_inv(L.u32(h2)[1], L.u32(ho2)[1], kh)))
+        hp["fp12_inv_per_s"] = (1 << 13) / time_host(lambda: L.check(lib.b381_fp12_inv(L.u32(sq)[1], L.u32(so)[1], 1 << 13)))
         L.check(lib.b381_fp_inv(L.u32(ha)[1], L.u32(ho)[1], kh))
         hsq = np.zeros(kh * 12, dtype=np.uint32)
         L.check(lib.b381_fp_mul(L.u32(ho)[1], L.u32(ho)[1], L.u32(hsq)[1], kh))          # squares: always have a root
-        extras["helpers_fp_sqrt_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_sqrt(L.u32(hsq)[1], None, L.u32(ho)[1], kh)))
-        # wire formats, subgroup checks, scalar multiplication, MSM, host-pointer API, 2^15 points
+        hp["fp_sqrt_per_s"] = kh / time_host(lambda: L.check(lib.b381_fp_sqrt(L.u32(hsq)[1], None, L.u32(ho)[1], kh)))
         import ctypes as _c
         kp = 1 << 15
         u8p = lambda arr: arr.ctypes.data_as(_c.POINTER(_c.c_uint8))
-        p1 = np.ascontiguousarray(g1[:kp * 24]); p2 = np.ascontiguousarray(g2[:kp * 48])
+        q1 = np.ascontiguousarray(g1[:kp * 24]); q2 = np.ascontiguousarray(g2[:kp * 48])
         enc1 = np.zeros(kp * 48, dtype=np.uint8); enc2 = np.zeros(kp * 96, dtype=np.uint8)
-        extras["g1_compress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_serialize(L.u32(p1)[1], None, 1, u8p(enc1), kp)))
-        L.check(lib.b381_g2_serialize(L.u32(p2)[1], None, 1, u8p(enc2), kp))
+        hp["g1_compress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_serialize(L.u32(q1)[1], None, 1, u8p(enc1), kp)))
+        L.check(lib.b381_g2_serialize(L.u32(q2)[1], None, 1, u8p(enc2), kp))
         d1_ = np.zeros(kp * 24, dtype=np.uint32); d2_ = np.zeros(kp * 48, dtype=np.uint32); fi = np.zeros(kp, dtype=np.uint8)
-        extras["g1_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_deserialize(u8p(enc1), 1, L.u32(d1_)[1], u8p(fi), kp)))
-        extras["g2_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_deserialize(u8p(enc2), 1, L.u32(d2_)[1], u8p(fi), kp)))
-        extras["wire_roundtrip_ok"] = bool(np.array_equal(d1_, p1) and np.array_equal(d2_, p2))
-        sg = np.zeros(kp, dtype=np.uint8)
-        extras["g1_subgroup_checks_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_in_subgroup(L.u32(p1)[1], None, u8p(sg), kp)))
-        extras["g2_subgroup_checks_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_in_subgroup(L.u32(p2)[1], None, u8p(sg), kp)))
-        extras["subgroup_all_in"] = bool(sg.all())
-        sc_ = np.random.default_rng(7).integers(0, 1 << 32, size=kp * 8, dtype=np.uint64).astype(np.uint32)
-        extras["g1_scalar_muls_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_scalar_mul(L.u32(p1)[1], None, L.u32(sc_)[1], L.u32(d1_)[1], u8p(fi), kp)))
-        extras["g2_scalar_muls_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_scalar_mul(L.u32(p2)[1], None, L.u32(sc_)[1], L.u32(d2_)[1], u8p(fi), kp)))
-        m1 = np.zeros(24, dtype=np.uint32); f1 = np.zeros(1, dtype=np.uint8)
-        extras["g1_msm_points_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_msm(L.u32(p1)[1], None, L.u32(sc_)[1], L.u32(m1)[1], u8p(f1), kp)))
+        hp["g1_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g1_deserialize(u8p(enc1), 1, L.u32(d1_)[1], u8p(fi), kp)))
+        hp["g2_decompress_per_s"] = kp / time_host(lambda: L.check(lib.b381_g2_deserialize(u8p(enc2), 1, L.u32(d2_)[1], u8p(fi), kp)))
+        hp["wire_roundtrip_ok"] = bool(np.array_equal(d1_, q1) and np.array_equal(d2_, q2))
+        extras["helpers_and_wire_formats_host_pointer_api"] = hp
 
     line = {"metric": "pairings/sec (Miller loop + final exp)", "value": value, "unit": "pairings/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -307,18 +307,65 @@ __device__ __forceinline__ void store_canon(uint32_t* dst, Fp& x) {   // x in (-
   d4[2] = make_uint4(w[8], w[9], w[10], w[11]);
 }
 
+// Streaming element-wise kernels (BASELINE config #2): a warp handles 32 consecutive elements.  The 32 x W words of
+// a tile are contiguous in HBM: the warp moves them with fully coalesced 128-bit loads / stores (lane l takes the
+// uint4 groups l, l + 32, ...: 512 contiguous bytes per instruction) through a shared-memory tile; each thread then
+// picks up ITS element with 128-bit shared-memory loads.  Row strides of 12 and 28 words make those conflict-free
+// (a quarter-warp's eight 16-byte accesses fall into eight different groups of four banks).
+template <int W, int RS>
+__device__ __forceinline__ void tile_load(uint32_t* tile, const uint32_t* gsrc, int valid, int lane) {
+  const uint4* g4 = reinterpret_cast<const uint4*>(gsrc);
+#pragma unroll
+  for (int k = 0; k < W / 4; k++) {
+    const int idx = lane + 32 * k, e = (idx * 4) / W, w = (idx * 4) % W;
+    if (e < valid) *reinterpret_cast<uint4*>(tile + e * RS + w) = g4[idx];
+  }
+}
+template <int W, int RS>
+__device__ __forceinline__ void tile_store(uint32_t* gdst, const uint32_t* tile, int valid, int lane) {
+  uint4* g4 = reinterpret_cast<uint4*>(gdst);
+#pragma unroll
+  for (int k = 0; k < W / 4; k++) {
+    const int idx = lane + 32 * k, e = (idx * 4) / W, w = (idx * 4) % W;
+    if (e < valid) g4[idx] = *reinterpret_cast<const uint4*>(tile + e * RS + w);
+  }
+}
+__device__ __forceinline__ bool load_canon_s(Fp& x, const uint32_t* src) {       // 12 words from shared memory
+  uint32_t w[12];
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
+  w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+  w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+  fp_unpack32(x, w);
+  return fp_below_p(x);
+}
+
 __global__ void __launch_bounds__(256)
 k_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* err) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    Fp x, y, r;
-    bool ok = load_canon(x, a + 12 * i);
-    ok &= load_canon(y, b + 12 * i);
-    if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
-    Acc t;
-    acc_zero(t);
-    acc_mac(t, x, y);
-    acc_redc384(r, t);
-    store_canon(out + 12 * i, r);
+  constexpr int W = 12, RS = 12, WARPS = 8;
+  __shared__ __align__(16) uint32_t sm[WARPS][3][32 * RS];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const size_t ntiles = (n + 31) / 32, stride = (size_t)gridDim.x * WARPS;
+  for (size_t t = (size_t)blockIdx.x * WARPS + wi; t < ntiles; t += stride) {
+    const size_t e0 = t * 32;
+    const int valid = (int)(n - e0 < 32 ? n - e0 : 32);
+    tile_load<W, RS>(sm[wi][0], a + e0 * W, valid, lane);
+    tile_load<W, RS>(sm[wi][1], b + e0 * W, valid, lane);
+    __syncwarp();
+    if (lane < valid) {
+      Fp x, y, r;
+      bool ok = load_canon_s(x, sm[wi][0] + lane * RS);
+      ok &= load_canon_s(y, sm[wi][1] + lane * RS);
+      if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
+      Acc acc;
+      acc_zero(acc);
+      acc_mac(acc, x, y);
+      acc_redc384(r, acc);
+      store_canon(sm[wi][2] + lane * RS, r);
+    }
+    __syncwarp();
+    tile_store<W, RS>(out + e0 * W, sm[wi][2], valid, lane);
+    __syncwarp();
   }
 }
 
@@ -343,27 +390,41 @@ k_fp_mul_chain(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, in
 
 __global__ void __launch_bounds__(128)
 k_fp2_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int* err) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    Fp a0, a1, b0, b1, r0, r1;
-    bool ok = load_canon(a0, a + 24 * i);
-    ok &= load_canon(a1, a + 24 * i + 12);
-    ok &= load_canon(b0, b + 24 * i);
-    ok &= load_canon(b1, b + 24 * i + 12);
-    if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
-    Acc A, B, T;
-    acc_zero(A); acc_mac(A, a0, b0);
-    acc_zero(B); acc_mac(B, a1, b1);
-    acc_sub(T, A, B);
-    acc_redc384(r0, T);
-    Fp sa, sb;
-    fp_add(sa, a0, a1);
-    fp_add(sb, b0, b1);
-    acc_add(T, A, B);
-    acc_neg(T, T);
-    acc_mac(T, sa, sb);
-    acc_redc384(r1, T);
-    store_canon(out + 24 * i, r0);
-    store_canon(out + 24 * i + 12, r1);
+  constexpr int W = 24, RS = 28, WARPS = 4;
+  __shared__ __align__(16) uint32_t sm[WARPS][3][32 * RS];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const size_t ntiles = (n + 31) / 32, stride = (size_t)gridDim.x * WARPS;
+  for (size_t t = (size_t)blockIdx.x * WARPS + wi; t < ntiles; t += stride) {
+    const size_t e0 = t * 32;
+    const int valid = (int)(n - e0 < 32 ? n - e0 : 32);
+    tile_load<W, RS>(sm[wi][0], a + e0 * W, valid, lane);
+    tile_load<W, RS>(sm[wi][1], b + e0 * W, valid, lane);
+    __syncwarp();
+    if (lane < valid) {
+      Fp a0, a1, b0, b1, r0, r1;
+      bool ok = load_canon_s(a0, sm[wi][0] + lane * RS);
+      ok &= load_canon_s(a1, sm[wi][0] + lane * RS + 12);
+      ok &= load_canon_s(b0, sm[wi][1] + lane * RS);
+      ok &= load_canon_s(b1, sm[wi][1] + lane * RS + 12);
+      if (!ok) atomicOr(err, ERR_NOT_CANONICAL);
+      Acc A, B, T;
+      acc_zero(A); acc_mac(A, a0, b0);
+      acc_zero(B); acc_mac(B, a1, b1);
+      acc_sub(T, A, B);
+      acc_redc384(r0, T);
+      Fp sa, sb;
+      fp_add(sa, a0, a1);
+      fp_add(sb, b0, b1);
+      acc_add(T, A, B);
+      acc_neg(T, T);
+      acc_mac(T, sa, sb);
+      acc_redc384(r1, T);
+      store_canon(sm[wi][2] + lane * RS, r0);
+      store_canon(sm[wi][2] + lane * RS + 12, r1);
+    }
+    __syncwarp();
+    tile_store<W, RS>(out + e0 * W, sm[wi][2], valid, lane);
+    __syncwarp();
   }
 }
 

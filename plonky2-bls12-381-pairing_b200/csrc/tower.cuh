@@ -770,10 +770,39 @@ B381_NOINL bool f2_equal(const u4* a, const u4* b) {
 }
 
 // external (12 x u32 Montgomery R=2^384) <-> slot.  src = 24 words (c0, c1).  Returns validity.
-B381_NOINL bool f2_load_ext(u4* r, const uint32_t* src) {
-  uint32_t w0[12], w1[12];
+// External buffers are read / written with 128-bit accesses on the device (every Fq2 of the C-ABI layouts starts
+// on a 16-byte boundary when the buffer does: 24-word elements).
+B381_DEV B381_INL void ext_ld24(uint32_t (&w0)[12], uint32_t (&w1)[12], const uint32_t* src) {
+#if defined(__CUDA_ARCH__)
+  if ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    const uint4 v0 = s4[0], v1 = s4[1], v2 = s4[2], v3 = s4[3], v4 = s4[4], v5 = s4[5];
+    w0[0] = v0.x; w0[1] = v0.y; w0[2] = v0.z; w0[3] = v0.w; w0[4] = v1.x; w0[5] = v1.y; w0[6] = v1.z; w0[7] = v1.w;
+    w0[8] = v2.x; w0[9] = v2.y; w0[10] = v2.z; w0[11] = v2.w;
+    w1[0] = v3.x; w1[1] = v3.y; w1[2] = v3.z; w1[3] = v3.w; w1[4] = v4.x; w1[5] = v4.y; w1[6] = v4.z; w1[7] = v4.w;
+    w1[8] = v5.x; w1[9] = v5.y; w1[10] = v5.z; w1[11] = v5.w;
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < 12; i++) { w0[i] = src[i]; w1[i] = src[12 + i]; }
+}
+B381_DEV B381_INL void ext_st24(uint32_t* dst, const uint32_t (&w0)[12], const uint32_t (&w1)[12]) {
+#if defined(__CUDA_ARCH__)
+  if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(w0[0], w0[1], w0[2], w0[3]); d4[1] = make_uint4(w0[4], w0[5], w0[6], w0[7]); d4[2] = make_uint4(w0[8], w0[9], w0[10], w0[11]);
+    d4[3] = make_uint4(w1[0], w1[1], w1[2], w1[3]); d4[4] = make_uint4(w1[4], w1[5], w1[6], w1[7]); d4[5] = make_uint4(w1[8], w1[9], w1[10], w1[11]);
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 12; i++) { dst[i] = w0[i]; dst[12 + i] = w1[i]; }
+}
+
+B381_NOINL bool f2_load_ext(u4* r, const uint32_t* src) {
+  uint32_t w0[12], w1[12];
+  ext_ld24(w0, w1, src);
   Fp c0, c1;
   bool ok0 = fp_from_ext(c0, w0);
   bool ok1 = fp_from_ext(c1, w1);
@@ -787,8 +816,7 @@ B381_NOINL void f2_store_ext(uint32_t* dst, const u4* a) {
   uint32_t w0[12], w1[12];
   fp_to_ext(w0, c0);
   fp_to_ext(w1, c1);
-#pragma unroll
-  for (int i = 0; i < 12; i++) { dst[i] = w0[i]; dst[12 + i] = w1[i]; }
+  ext_st24(dst, w0, w1);
 }
 
 // ---------------------------------------------------------------------------------------------

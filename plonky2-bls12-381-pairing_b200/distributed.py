@@ -71,3 +71,90 @@ def one_fq12_words() -> np.ndarray:
     w = np.zeros(144, dtype=np.uint32)
     w[:12] = to_limbs32(1)
     return w
+
+
+# ---- one process, several GPUs: a context per device, a host thread per context --------------------------------
+class DeviceSet:
+    """One libb381 context per GPU (b381_ctx_create), driven by one host thread each: what a Rust host (SURVEY 8b
+    "Threading": one context per device, calls from several host threads) would do with a thread pool.  Independent
+    pairings are sharded contiguously over the devices, no data-path collective; the multi-pairing product combines
+    the per-device Fq12 partials on the first device."""
+
+    def __init__(self, devices):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.devices = list(devices)
+        self.ctxs = []
+        for d in self.devices:
+            c = ctypes.c_void_p()
+            _lib.check(self.lib.b381_ctx_create(int(d), ctypes.byref(c)))
+            self.ctxs.append(c)
+
+    def close(self):
+        for c in self.ctxs:
+            self.lib.b381_ctx_destroy(c)
+        self.ctxs = []
+
+    def _run(self, fn):
+        """fn(k) on a thread bound to context k, for every k; returns the list of results (first exception re-raised)"""
+        import threading
+        res, errs = [None] * len(self.ctxs), []
+
+        def work(k):
+            try:
+                self._lib.check(self.lib.b381_ctx_set_current(self.ctxs[k]))
+                res[k] = fn(k)
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+            finally:
+                self.lib.b381_ctx_set_current(None)
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(len(self.ctxs))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return res
+
+    def pairing(self, g1: np.ndarray, g2: np.ndarray, inf: Optional[np.ndarray], mode: int = 0) -> np.ndarray:
+        """out[i] = e(P_i, Q_i) for a host batch, sharded contiguously over the devices"""
+        L, lib = self._lib, self.lib
+        n = g1.size // 24
+        out = np.empty(n * 144, dtype=np.uint32)
+        w = len(self.ctxs)
+
+        def shard(k):
+            lo, hi = shard_bounds(n, k, w)
+            if hi > lo:
+                L.check(lib.b381_pairing(L.u32(g1[24 * lo:24 * hi])[1], L.u32(g2[48 * lo:48 * hi])[1],
+                                         L.u8(inf[lo:hi])[1] if inf is not None else None, L.u32(out[144 * lo:144 * hi])[1], hi - lo, mode))
+        self._run(shard)
+        return out
+
+    def multi_pairing(self, g1: np.ndarray, g2: np.ndarray, inf: Optional[np.ndarray], mode: int = 0) -> np.ndarray:
+        """final_exp(prod_i miller(P_i, Q_i)): per-device partial products, combined on the first device"""
+        L, lib = self._lib, self.lib
+        n = g1.size // 24
+        w = len(self.ctxs)
+        parts = np.tile(one_fq12_words(), (w, 1))
+
+        def shard(k):
+            lo, hi = shard_bounds(n, k, w)
+            if hi > lo:
+                L.check(lib.b381_multi_miller_loop(L.u32(g1[24 * lo:24 * hi])[1], L.u32(g2[48 * lo:48 * hi])[1],
+                                                   L.u8(inf[lo:hi])[1] if inf is not None else None, L.u32(parts[k])[1], hi - lo, mode))
+        self._run(shard)
+        out = np.zeros(144, dtype=np.uint32)
+
+        def combine(k):
+            if k == 0:
+                prod = np.zeros(144, dtype=np.uint32)
+                flat = np.ascontiguousarray(parts).reshape(-1)
+                L.check(lib.b381_fp12_product(L.u32(flat)[1], L.u32(prod)[1], w))
+                L.check(lib.b381_final_exp(L.u32(prod)[1], L.u32(out)[1], 1))
+        self._run(combine)
+        return out

@@ -351,3 +351,30 @@ def test_every_dev_entry_point(L, lib, z):
     L.check(lib.b381_multi_pairing(L.u32(g1)[1], L.u32(g2)[1], u8(inf), L.u32(h144)[1], m, L.MODE_ARK))
     L.check(lib.b381_multi_pairing_dev(dg1.data_ptr(), dg2.data_ptr(), dinf.data_ptr(), d144.data_ptr(), m, L.MODE_ARK, st)); L.check(lib.b381_check_dev(st))
     assert np.array_equal(back(d144, np.uint32), h144)
+
+
+def test_single_process_device_set(L, lib, z):
+    """distributed.DeviceSet: one process, one context per GPU (all visible GPUs; the same GPU twice on a 1-GPU box),
+    a host thread per context: sharded pairings and the multi-pairing product equal the fixture values."""
+    import torch
+    import b381
+    ng = torch.cuda.device_count()
+    devs = list(range(ng)) if ng > 1 else [0, 0]
+    ds = b381.distributed.DeviceSet(devs)
+    try:
+        n = 1000
+        idx = np.arange(n) % 256
+        g1 = np.ascontiguousarray(z["g1"][idx]).reshape(-1); g2 = np.ascontiguousarray(z["g2"][idx]).reshape(-1)
+        inf = np.zeros(n, dtype=np.uint8); inf[17] = 1
+        out = ds.pairing(g1, g2, inf, L.MODE_ARK).reshape(n, 144)
+        one = np.array(o.f12_to_limbs32(o.F12_ONE), dtype=np.uint32)
+        for i in (0, 16, 17, 499, 500, 999):
+            assert np.array_equal(out[i], one if inf[i] else z["pairing"][idx[i]]), i
+        m = 64
+        res = ds.multi_pairing(g1[:24 * m], g2[:48 * m], None, L.MODE_ARK)
+        pr = o.F12_ONE
+        for i in range(m):
+            pr = o.f12_mul(pr, o.f12_from_limbs32(z["miller_ark"][i].tolist()))
+        assert o.f12_eq(o.f12_from_limbs32(res.tolist()), o.ark_final_exponentiation(pr))
+    finally:
+        ds.close()
