@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
+
   for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
     __syncthreads();
     size_t i = base + threadIdx.x;
