@@ -20,13 +20,15 @@ constexpr int PP_A = 0, PP_B = 6, PP_L = 12, PP_T = 15, PP_R = 20, PP_Q = 23, PP
 // ... second pair of the shared-squaring two-pair loop and the running product of k_multi_miller
 constexpr int PP_R2 = 26, PP_Q2 = 29, PP_P2 = 31, PP_ACC = 32, PP_NSLOTS = 38;
 // final exponentiation: ACC (the value being squared) and the first scratch slots are hot.
-constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_F = 28, FE_Y0 = 28 /* f is dead once y0 is first written */, FE_Y1 = 34, FE_Y2 = 40, FE_R = 46, FE_NSLOTS = 52;
+// T = 12 scratch slots for the Fp12 products; the inversion of the easy part needs 15 and runs over into Y1, which is
+// not live yet.  48 slots: 29 of them in global memory = 105 MB of scratch for 148 CTAs, inside the 126 MB L2.
+constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_Y1 = 24, FE_Y2 = 30, FE_F = 36, FE_Y0 = 36 /* f is dead once y0 is first written */, FE_R = 42, FE_NSLOTS = 48;
 // literal loop
 constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
 // shared-squaring multi-Miller (two pairs per thread): second pair's R, Q, P and the running product
 constexpr int M2_R2 = 25, M2_Q2 = 28, M2_P2 = 30, M2_ACC = 32 /* = PP_ACC: one accumulator slot range for both modes */, M2_NSLOTS = 38;
 constexpr int M2_SCRATCH = 6;   // 14 scratch slots of the accumulating Fp12 product: dead line / scratch / bank-B slots of either plan
-constexpr int MAX_NSLOTS = 52;
+constexpr int MAX_NSLOTS = 48;
 // Stores under a per-thread `if (ident)` (miller_to_slots & co.) must never hit tensor memory (tcgen05.st is
 // .sync.aligned): the P / Q input slots live in the global-memory part of the arena, f in shared memory.
 static_assert(ML_Q >= NS + NT_MAX && ML_P >= NS + NT_MAX && M2_Q2 >= NS + NT_MAX && M2_P2 >= NS + NT_MAX, "P / Q slots must be global-memory slots");

@@ -402,14 +402,23 @@ B381_DEV B381_INL void f2_mul_ss(u4* r, const u4* a, const u4* a2, const u4* b, 
 // flags: SOP_XIk multiplies b_k by xi = 1 + u while it sits in registers, (b0 - b1 + 3 p, b0 + b1): b_k must be a
 // stored value with b0 < 3.4 p and b1 <= 3 p (tracker-asserted through the 12-word products); SOP_DBL doubles
 // the result in the double-width domain (2 a b of the Fp12 squaring).
-enum SopFlags { SOP_XI0 = 1, SOP_XI1 = 2, SOP_XI2 = 4, SOP_DBL = 8 };
+// Result post-operations (the Karatsuba recombinations of the Fp12 product / squaring, folded into the sum that
+// produces their first operand; p1 / p2 / r2 are extra slots):
+//   SOP_SUB2        r = S - p1 - p2                    weak-reduced
+//   SOP_HALFSUB     r = S - (p1 + p2) / 2              weak-reduced      (SOP_HALFSUB_XI: xi p2)
+//   SOP_ALSO_ADD    r = S  and  r2 = S + p1            r2 weak-reduced   (SOP_ALSO_XIADD: r2 = xi S + p1)
+enum SopFlags { SOP_XI0 = 1, SOP_XI1 = 2, SOP_XI2 = 4, SOP_DBL = 8, SOP_SUB2 = 16, SOP_HALFSUB = 32, SOP_HALFSUB_XI = 64, SOP_ALSO_ADD = 128, SOP_ALSO_XIADD = 256 };
 B381_DEV B381_INL void f2_xi_pos(Fp& b0, Fp& b1) {
   Fp d;
   fp_sub(d, b0, b1);
   fp_add(b1, b0, b1);
   fp_add_p3(b0, d);
 }
-B381_NOINL void f2_sop(u4* r, int flags, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
+// Two instances: the lean one (operand flags only) is the Miller loop's; the one with result post-operations is
+// used by the Fp12 product.  One function with everything cost the Miller loop 2.6 % (measured).
+template <bool POST>
+B381_DEV B381_INL void f2_sop_t(u4* r, int flags, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p,
+                                const u4* p1, const u4* p2, u4* r2) {
   Fp x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1;
   ld_f2(x0, x1, a0p); ld_f2(u0, u1, b0p);
   ld_f2(y0, y1, a1p); ld_f2(v0, v1, b1p);
@@ -432,7 +441,37 @@ B381_NOINL void f2_sop(u4* r, int flags, const u4* a0p, const u4* b0p, const u4*
   Fp r0, r1;
   acc_redc2(r0, P, r1, X);
   fp_add_p(r0, r0);
+  if (POST && (flags & (SOP_SUB2 | SOP_HALFSUB | SOP_HALFSUB_XI))) {
+    Fp x0, x1, y0, y1;
+    ld_f2(x0, x1, p1);
+    ld_f2(y0, y1, p2);
+    if (flags & SOP_SUB2) {
+      fp_sub(r0, r0, x0); fp_sub(r1, r1, x1);
+      fp_sub(r0, r0, y0); fp_sub(r1, r1, y1);
+    } else {
+      if (flags & SOP_HALFSUB_XI) f2_mulxi_reg(y0, y1, y0, y1);
+      fp_add(x0, x0, y0); fp_add(x1, x1, y1);
+      fp_half(x0, x0); fp_half(x1, x1);
+      fp_sub(r0, r0, x0); fp_sub(r1, r1, x1);
+    }
+    fp_wreduce(r0); fp_wreduce(r1);
+  }
   st_f2(r, r0, r1);
+  if (POST && (flags & (SOP_ALSO_ADD | SOP_ALSO_XIADD))) {
+    Fp x0, x1;
+    ld_f2(x0, x1, p1);
+    if (flags & SOP_ALSO_XIADD) f2_mulxi_reg(r0, r1, r0, r1);
+    fp_add(r0, r0, x0); fp_add(r1, r1, x1);
+    fp_wreduce(r0); fp_wreduce(r1);
+    st_f2(r2, r0, r1);
+  }
+}
+B381_NOINL void f2_sop(u4* r, int flags, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p) {
+  f2_sop_t<false>(r, flags, a0p, b0p, a1p, b1p, a2p, b2p, nullptr, nullptr, nullptr);
+}
+B381_NOINL void f2_sop_post(u4* r, int flags, const u4* a0p, const u4* b0p, const u4* a1p, const u4* b1p, const u4* a2p, const u4* b2p,
+                            const u4* p1, const u4* p2, u4* r2) {
+  f2_sop_t<true>(r, flags, a0p, b0p, a1p, b1p, a2p, b2p, p1, p2, r2);
 }
 
 // r = post( pre(a, a2)^2 )
@@ -830,9 +869,12 @@ B381_DEV B381_INL void mul_ss(const Ctx& cx, int r, int a, int a2, int b, int b2
   sync_point(cx);
   f2_mul_ss(S_(r), S_(a), a2 >= 0 ? S_(a2) : nullptr, S_(b), b2 >= 0 ? S_(b2) : nullptr);
 }
-B381_DEV B381_INL void sop3(const Ctx& cx, int r, int a0, int b0, int a1, int b1, int a2, int b2, int flags = 0) {
+B381_DEV B381_INL void sop3(const Ctx& cx, int r, int a0, int b0, int a1, int b1, int a2, int b2, int flags = 0, int p1 = -1, int p2 = -1, int r2 = -1) {
   sync_point(cx);
-  f2_sop(S_(r), flags, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2));
+  if (flags & (SOP_SUB2 | SOP_HALFSUB | SOP_HALFSUB_XI | SOP_ALSO_ADD | SOP_ALSO_XIADD))
+    f2_sop_post(S_(r), flags, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2), p1 >= 0 ? S_(p1) : nullptr, p2 >= 0 ? S_(p2) : nullptr, r2 >= 0 ? S_(r2) : nullptr);
+  else
+    f2_sop(S_(r), flags, S_(a0), S_(b0), S_(a1), S_(b1), S_(a2), S_(b2));
 }
 B381_DEV B381_INL void mul_ex(const Ctx& cx, int r, int a, int b, int b2, int pre_b, int post, int p1 = -1, int p2 = -1) {
   sync_point(cx);
@@ -864,11 +906,14 @@ B381_DEV B381_INL void f6_mul(const Ctx& cx, int r, int a, int b, int t) {
 
 // The same product with the two xi-multiplications folded into the operand loads of the sums (no scratch, no
 // linear passes); b1, b2 must satisfy the SOP_XI bounds (single stored values, or weak-reduced sums).  dbl: 2 a b.
-B381_DEV B381_INL void f6_mul_x(const Ctx& cx, int r, int a, int b, int dbl = 0) {
+struct SopPost { int flags, p1, p2, r2; };
+B381_DEV B381_INL void f6_mul_x(const Ctx& cx, int r, int a, int b, int dbl = 0, const SopPost* post = nullptr) {
   const int d = dbl ? SOP_DBL : 0;
-  sop3(cx, r, a, b, a + 1, b + 2, a + 2, b + 1, SOP_XI1 | SOP_XI2 | d);
-  sop3(cx, r + 1, a, b + 1, a + 1, b, a + 2, b + 2, SOP_XI2 | d);
-  sop3(cx, r + 2, a, b + 2, a + 1, b + 1, a + 2, b, d);
+  const SopPost none = {0, -1, -1, -1};
+  const SopPost& q0 = post ? post[0] : none; const SopPost& q1 = post ? post[1] : none; const SopPost& q2 = post ? post[2] : none;
+  sop3(cx, r, a, b, a + 1, b + 2, a + 2, b + 1, SOP_XI1 | SOP_XI2 | d | q0.flags, q0.p1, q0.p2, q0.r2);
+  sop3(cx, r + 1, a, b + 1, a + 1, b, a + 2, b + 2, SOP_XI2 | d | q1.flags, q1.p1, q1.p2, q1.r2);
+  sop3(cx, r + 2, a, b + 2, a + 1, b + 1, a + 2, b, d | q2.flags, q2.p1, q2.p2, q2.r2);
 }
 
 // Fp6 squaring via f6_mul-style Karatsuba with squarings (3 sqr + 3 mul)
@@ -891,17 +936,17 @@ B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
 // coefficients of sb that get multiplied by xi are weak-reduced sums.
 B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
   const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3;
-  f6_mul_x(cx, aa, a, b);
-  f6_mul_x(cx, bb, a + 3, b + 3);
   for (int i = 0; i < 3; i++) {
     lin(cx, sa + i, a + i, a + 3 + i, L_ADD);
     lin(cx, sb + i, b + i, b + 3 + i, i == 0 ? L_ADD : L_ADD_R);
   }
-  f6_mul_x(cx, r + 3, sa, sb);                    // (a0+a1)(b0+b1)   (a, b dead from here on)
-  for (int i = 0; i < 3; i++) kcomb(cx, r + 3 + i, r + 3 + i, aa + i, bb + i, -1, K_PLAIN);
-  lin(cx, r, aa, bb + 2, L_XIADD);                // c0 = aa + v bb ; v bb = (xi bb2, bb0, bb1)
-  lin(cx, r + 1, aa + 1, bb, L_ADD_R);
-  lin(cx, r + 2, aa + 2, bb + 1, L_ADD_R);
+  f6_mul_x(cx, aa, a, b);
+  // bb = a1 b1, and with it c0 = aa + v bb = (aa0 + xi bb2, aa1 + bb0, aa2 + bb1) straight into r (a0, b0 are dead)
+  const SopPost pb[3] = {{SOP_ALSO_ADD, aa + 1, -1, r + 1}, {SOP_ALSO_ADD, aa + 2, -1, r + 2}, {SOP_ALSO_XIADD, aa, -1, r}};
+  f6_mul_x(cx, bb, a + 3, b + 3, 0, pb);
+  // c1 = (a0 + a1)(b0 + b1) - aa - bb
+  const SopPost pc[3] = {{SOP_SUB2, aa, bb, -1}, {SOP_SUB2, aa + 1, bb + 1, -1}, {SOP_SUB2, aa + 2, bb + 2, -1}};
+  f6_mul_x(cx, r + 3, sa, sb, 0, pc);
 }
 
 // Fp12 complex squaring in place; fq12_target_tree.rs:143-155.  Scratch: t = 5 slots, s3 = 3 more
@@ -953,10 +998,17 @@ B381_DEV void f12_sqr_oop(const Ctx& cx, int d, int f, int t, int s3) {
   lin(cx, u + 1, f + 1, f + 3, L_ADD_R);
   lin(cx, u + 2, f + 2, f + 4, L_ADD_R);
   f6_mul_x(cx, d + 3, f + 3, f, 1);               // c1 = 2 a1 a0
+#ifdef B381_SQR_FOLD
+  // c0 = s u - (c1 + v c1) / 2 ; v c1 = (xi c12, c10, c11): the recombination rides on the sums that produce s u
+  const SopPost pc[3] = {{SOP_HALFSUB_XI, d + 3, d + 5, -1}, {SOP_HALFSUB, d + 4, d + 3, -1}, {SOP_HALFSUB, d + 5, d + 4, -1}};
+  f6_mul_x(cx, d, s, u, 0, pc);
+#else
+  // (folding these three recombinations into the sums, as f12_mul does, was measured: -2 % on k_miller)
   f6_mul_x(cx, d, s, u);                          // s u
   kcomb(cx, d, d, d + 3, d + 5, -1, K_HALFSUB_XI);     // c0 = s u - (c1 + v c1) / 2 ; v c1 = (xi c12, c10, c11)
   kcomb(cx, d + 1, d + 1, d + 4, d + 3, -1, K_HALFSUB);
   kcomb(cx, d + 2, d + 2, d + 5, d + 4, -1, K_HALFSUB);
+#endif
 }
 
 // sparse multiplication d = f * (c0 + c1 v + c4 v w) OUT OF PLACE, xi c1 and xi c4 formed in registers:
