@@ -716,4 +716,141 @@ B381_HD B381_INL void fp_to_ext(uint32_t (&w)[12], const Fp& a) {
   fp_pack32(w, o);
 }
 
+// ---------------------------------------------------------------------------------------------
+// modular inversion: Bernstein-Yang "safegcd" division steps (constant control flow, no multiplications
+// in the inner loop).  The stored value v = A R' is made canonical, then (f, g) = (p, v) runs through
+// batches of 30 division steps on the low words; each batch's 2 x 2 transition matrix is applied to the
+// full-length (f, g) and, modulo p, to (d, e) = (0, R'^2 mod p), so that d ends at +-v^-1 R'^2 = +-A^-1 R'.
+// Values are 13 signed limbs of 30 bits with 64-bit signed accumulators (the layout of the public
+// libsecp256k1 modinv32 code, written out for a 381-bit modulus).  Theorem 11.2 of Bernstein-Yang 2019
+// (delta starts at 1; f^2 + 4 g^2 <= 5 * 2^(2 * 381)) bounds the number of division steps by
+// floor((49 * 381 + 57) / 17) = 1101 <= 37 * 30.  On the device a warp leaves the loop as soon as every
+// active lane has g = 0 (random inputs: 26 - 28 batches), which is the fixed point of the iteration.
+// About 20 k ALU instructions + 4 k IMAD.WIDE against 183 k IMAD.WIDE for the Fermat power a^(p-2):
+// the same residue, a tenth of the time.  inverse(0) = 0 (as a^(p-2)).
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_N = 13;
+constexpr int SG_BATCHES = 37;
+constexpr uint32_t SG_M30 = 0x3fffffffu;
+
+B381_HD B381_INL void sg_divsteps30(uint32_t& eta, uint32_t f, uint32_t g, int32_t& tu, int32_t& tv, int32_t& tq, int32_t& tr) {
+  uint32_t u = 1, v = 0, q = 0, r = 1;
+#pragma unroll 6
+  for (int i = 0; i < 30; i++) {
+    uint32_t c1 = (uint32_t)((int32_t)eta >> 31);       // delta > 0
+    const uint32_t c2 = 0u - (g & 1u);                  // g odd
+    const uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+    g += x & c2; q += y & c2; r += z & c2;
+    c1 &= c2;                                           // swap
+    eta = (eta ^ c1) - (c1 + 1u);
+    f += g & c1; u += q & c1; v += r & c1;
+    g >>= 1; u <<= 1; v <<= 1;
+  }
+  tu = (int32_t)u; tv = (int32_t)v; tq = (int32_t)q; tr = (int32_t)r;
+}
+
+// (f, g) <- t (f, g) / 2^30 (exact)
+B381_HD B381_INL void sg_update_fg(int32_t (&f)[SG_N], int32_t (&g)[SG_N], int32_t u, int32_t v, int32_t q, int32_t r) {
+  int64_t cf = (int64_t)u * f[0] + (int64_t)v * g[0];
+  int64_t cg = (int64_t)q * f[0] + (int64_t)r * g[0];
+  cf >>= 30; cg >>= 30;
+#pragma unroll
+  for (int i = 1; i < SG_N; i++) {
+    cf += (int64_t)u * f[i] + (int64_t)v * g[i];
+    cg += (int64_t)q * f[i] + (int64_t)r * g[i];
+    f[i - 1] = (int32_t)((uint32_t)cf & SG_M30); cf >>= 30;
+    g[i - 1] = (int32_t)((uint32_t)cg & SG_M30); cg >>= 30;
+  }
+  f[SG_N - 1] = (int32_t)cf;
+  g[SG_N - 1] = (int32_t)cg;
+}
+
+// (d, e) <- t (d, e) / 2^30 mod p, both kept in (-2p, p)
+B381_HD B381_INL void sg_update_de(int32_t (&d)[SG_N], int32_t (&e)[SG_N], int32_t u, int32_t v, int32_t q, int32_t r) {
+  const int32_t pl[SG_N] = B381_SG_P30;
+  const int32_t sd = d[SG_N - 1] >> 31, se = e[SG_N - 1] >> 31;
+  int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+  int64_t cd = (int64_t)u * d[0] + (int64_t)v * e[0];
+  int64_t ce = (int64_t)q * d[0] + (int64_t)r * e[0];
+  md -= (int32_t)((B381_SG_PINV30 * (uint32_t)cd + (uint32_t)md) & SG_M30);
+  me -= (int32_t)((B381_SG_PINV30 * (uint32_t)ce + (uint32_t)me) & SG_M30);
+  cd += (int64_t)pl[0] * md;
+  ce += (int64_t)pl[0] * me;
+  cd >>= 30; ce >>= 30;
+#pragma unroll
+  for (int i = 1; i < SG_N; i++) {
+    cd += (int64_t)u * d[i] + (int64_t)v * e[i] + (int64_t)pl[i] * md;
+    ce += (int64_t)q * d[i] + (int64_t)r * e[i] + (int64_t)pl[i] * me;
+    d[i - 1] = (int32_t)((uint32_t)cd & SG_M30); cd >>= 30;
+    e[i - 1] = (int32_t)((uint32_t)ce & SG_M30); ce >>= 30;
+  }
+  d[SG_N - 1] = (int32_t)cd;
+  e[SG_N - 1] = (int32_t)ce;
+}
+
+// r = a^-1 (Montgomery domain R'), r in [0, p); a any stored value with |a| < 2^17 p
+B381_HD B381_INL void fp_inv_safegcd(Fp& r, const Fp& a) {
+  Fp c = a;
+  fp_canon(c);
+  int32_t f[SG_N] = B381_SG_P30, g[SG_N], d[SG_N], e[SG_N] = B381_SG_R2_30;
+#pragma unroll
+  for (int i = 0; i < SG_N; i++) {                      // limb i = bits 30 i .. 30 i + 29
+    const int k = (30 * i) >> 5, s = (30 * i) & 31;
+    uint32_t w = c.l[k] >> s;
+    if (s > 2 && k + 1 < NL) w |= c.l[k + 1] << (32 - s);
+    g[i] = (int32_t)(w & SG_M30);
+    d[i] = 0;
+  }
+  uint32_t eta = 0xffffffffu;                           // -delta, delta = 1
+  for (int it = 0; it < SG_BATCHES; it++) {
+    int32_t tu, tv, tq, tr;
+    sg_divsteps30(eta, (uint32_t)f[0] | ((uint32_t)f[1] << 30), (uint32_t)g[0] | ((uint32_t)g[1] << 30), tu, tv, tq, tr);
+    sg_update_de(d, e, tu, tv, tq, tr);
+    sg_update_fg(f, g, tu, tv, tq, tr);
+#if defined(__CUDA_ARCH__)
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < SG_N; i++) nz |= (uint32_t)g[i];
+    if (__all_sync(__activemask(), nz == 0)) break;
+#endif
+  }
+  // f = +-1 (or p when a = 0, with d = 0): d <- sign(f) d, as two's-complement words
+  const uint32_t fneg = (uint32_t)(f[SG_N - 1] >> 31);
+  Fp t;
+  {
+    // 13 limbs of 30 bits (top one signed) -> 13 words of 32 bits: word k = bits 32 k .. 32 k + 31
+    uint32_t dl[SG_N + 2];
+#pragma unroll
+    for (int i = 0; i < SG_N; i++) dl[i] = (uint32_t)d[i];
+    dl[SG_N] = dl[SG_N + 1] = (uint32_t)(d[SG_N - 1] >> 31);          // sign extension
+#pragma unroll
+    for (int k = 0; k < NL; k++) {
+      const int j = (32 * k) / 30, off = 32 * k - 30 * j;
+      // limbs below the top one are non-negative 30-bit values; the top limb (and the extension) is sign-extended
+      uint32_t w = dl[j] >> off;
+      if (j + 1 < SG_N + 2) w |= dl[j + 1] << (30 - off);
+      if (60 - off < 32 && j + 2 < SG_N + 2) w |= dl[j + 2] << (60 - off);
+      t.l[k] = w;
+    }
+    B381_SETRANGE(t, -2.0, 1.0);
+  }
+  Fp n;
+  fp_neg(n, t);
+#pragma unroll
+  for (int k = 0; k < NL; k++) t.l[k] = (n.l[k] & fneg) | (t.l[k] & ~fneg);
+  B381_SETRANGE(t, -2.0, 2.0);
+  {                                                     // (-2p, 2p) -> [0, 2p) -> [0, p)
+    const uint32_t p2[NL] = B381_P2;
+    const uint32_t neg = (uint32_t)((int32_t)t.l[NL - 1] >> 31);
+    B381_CC_DECL;
+    ADD_CC(t.l[0], t.l[0], p2[0] & neg);
+#pragma unroll
+    for (int k = 1; k < NL - 1; k++) ADDC_CC(t.l[k], t.l[k], p2[k] & neg);
+    ADDC(t.l[NL - 1], t.l[NL - 1], p2[NL - 1] & neg);
+    B381_SETRANGE(t, 0.0, 2.0 - 1e-9);
+  }
+  fp_canon_small(t);
+  r = t;
+}
+
 }  // namespace b381

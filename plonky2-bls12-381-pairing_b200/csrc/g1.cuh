@@ -177,7 +177,7 @@ B381_G1FN void g1_mul_x_abs_jac(G1J& r, const G1J& p) {
 B381_G1FN bool g1_to_affine(G1A& r, const G1J& p) {
   if (g1_is_identity(p)) return false;
   Fp zi, zi2;
-  fp_pow_words(zi, p.z, g_et.pm2, 12);
+  fp_inv_safegcd(zi, p.z);
   r1_sqr(zi2, zi);
   r1_mul(r.x, p.x, zi2);
   r1_mul(zi2, zi2, zi);

@@ -85,7 +85,7 @@ B381_DEV B381_INL int prog_fp_inv(const uint32_t* a, uint32_t* out) {
   uint32_t nz = 0;
   for (int j = 0; j < 12; j++) nz |= w[j];
   if (nz == 0) err |= HERR_ZERO_DIVISION;            // ark: inverse() of zero is None, the reference unwraps
-  fp_pow_words(r, x, g_et.pm2, 12);
+  fp_inv_safegcd(r, x);
   fp_to_ext(wo, r);
   for (int j = 0; j < 12; j++) out[j] = wo[j];
   return err;
@@ -149,7 +149,7 @@ B381_DEV B381_INL int prog_fp2_inv(const uint32_t* a, uint32_t* out) {
   acc_mul(T, a0, a0);
   acc_mac(T, a1, a1);
   acc_redc(n, T);                                    // norm a0^2 + a1^2
-  fp_pow_words(ni, n, g_et.pm2, 12);
+  fp_inv_safegcd(ni, n);
   fp_mul(r0, a0, ni);
   fp_neg_nn(t, a1);
   fp_mul(r1, t, ni);
@@ -193,7 +193,7 @@ B381_DEV B381_INL int prog_fp2_sqrt(const uint32_t* a, int sgn, uint32_t* out) {
     }
     c0 = t;
     fp_dbl(d, t);
-    fp_pow_words(ti, d, g_et.pm2, 12);               // 1 / (2 c0)
+    fp_inv_safegcd(ti, d);               // 1 / (2 c0)
     fp_mul(c1, a1, ti);
   }
   {                                                  // verify (c0 + c1 u)^2 == a
@@ -434,7 +434,7 @@ B381_DEV B381_INL bool f2_sqrt_any(Fp& c0, Fp& c1, const Fp& a0, const Fp& a1) {
     }
     c0 = t;
     fp_dbl(d, t);
-    fp_pow_words(ti, d, g_et.pm2, 12);
+    fp_inv_safegcd(ti, d);
     fp_mul(c1, a1, ti);
   }
   Fp q0, q1;

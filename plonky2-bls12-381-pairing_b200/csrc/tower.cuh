@@ -292,8 +292,9 @@ B381_DEV B381_INL void f2_mulxi_reg(Fp& r0, Fp& r1, const Fp& a0, const Fp& a1) 
   r0 = t0; r1 = t1;
 }
 
-// Fermat inversion a^(p-2), 4-bit fixed windows, table in registers is too large -> binary
-// square-and-multiply driven by the nibble table (uniform control flow across the warp).
+// Fp inversion: Bernstein-Yang division steps (fp32.cuh fp_inv_safegcd); the Fermat power a^(p-2) it replaces
+// cost 4 % of a pairing.  B381_FERMAT_INV selects the old square-and-multiply ladder (kept for measurements).
+#ifdef B381_FERMAT_INV
 #define FP_MUL_SMALL fp_mul12      // x and a are reduction outputs (at most 1.03 p): 12-word products
 B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
   Fp x;
@@ -312,6 +313,9 @@ B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) {
   }
   r = x;
 }
+#else
+B381_DEV B381_INL void fp_inv_reg(Fp& r, const Fp& a) { fp_inv_safegcd(r, a); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // noinline slot primitives

@@ -257,6 +257,26 @@ def test_witness_helpers(hs):
     assert hs.hs_fp6_inv_ext(A([0] * 72), o72) == 2
 
 
+def test_safegcd_inversion(hs):
+    """fp_inv_safegcd (Bernstein-Yang division steps, fp32.cuh) against the modular inverse: structured values
+    (powers of two and their neighbours, p - 2^k, values whose Montgomery form is all ones / sparse) and 400
+    random ones; inverse(0) = 0 with the zero-division flag."""
+    r = util.rng(977)
+    out = u(12)
+    vals = [1, 2, 3, o.P - 1, o.P - 2, o.P - 3, (o.P - 1) // 2, (o.P + 1) // 2]
+    vals += [v % o.P for k in range(1, 381, 13) for v in (1 << k, (1 << k) - 1, o.P - (1 << k))]
+    rinv = pow(1 << 384, -1, o.P)
+    vals += [(m * rinv) % o.P for m in ((1 << 381) - 1, (1 << 380) + 1, 0x5555555555555555 * (1 << 300), o.P - 1, 1)]
+    vals += [util.rfp(r) for _ in range(400)]
+    for a in vals:
+        if a == 0:
+            continue
+        assert hs.hs_fp_inv(A(o.fp_to_limbs32(a)), out) == 0
+        got = o.fp_from_limbs32(list(out))
+        assert got == pow(a, -1, o.P), hex(a)
+    assert hs.hs_fp_inv(A([0] * 12), out) == 2 and list(out) == [0] * 12
+
+
 def test_wire_formats(hs):
     """Witness digits (fq_target.rs:300-313, fq12_target.rs:408-416) and the ZCash / IETF point encodings
     against the oracle: round trips, both y signs, infinity, uncompressed, and every rejection path."""
