@@ -285,25 +285,36 @@ def main():
     # ---- BASELINE config #4 as literally written: 2^20 pairs in TOTAL, sharded contiguously over the ranks (strong scaling) ----
     strong = None
     if not args.no_extras and n >= (1 << 20) // world:
-        ns = (1 << 20) // world
-        souts = torch.empty(ns * 144, dtype=torch.int32, device=dev)
-        def step_strong():
-            L.check(lib.b381_pairing_dev(d1.data_ptr(), d2.data_ptr(), None, souts.data_ptr(), ns, L.MODE_ARK, st))
-        step_strong()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        for _ in range(3):
-            step_strong()
-        s1.record(stream)
-        barrier()
-        sms = max_over_ranks(s0.elapsed_time(s1)) / 3
         sms_n = torch.cuda.get_device_properties(dev).multi_processor_count
-        rounds = -(-ns // (sms_n * 256))
+
+        def time_shard(ns):
+            souts = torch.empty(ns * 144, dtype=torch.int32, device=dev)
+            def step_strong():
+                L.check(lib.b381_pairing_dev(d1.data_ptr(), d2.data_ptr(), None, souts.data_ptr(), ns, L.MODE_ARK, st))
+            step_strong()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(3):
+                step_strong()
+            s1.record(stream)
+            barrier()
+            return max_over_ranks(s0.elapsed_time(s1)) / 3
+
+        ns = (1 << 20) // world
+        sms = time_shard(ns)
+        full, tail = divmod(ns, sms_n * 256)
         strong = {"pairs_total": 1 << 20, "pairs_per_gpu": ns, "ms": sms, "pairs_per_s": (1 << 20) / sms * 1e3,
-                  "rounds_per_gpu": rounds, "round_fill": ns / (rounds * sms_n * 256),
-                  "note": "a launch is one round of #SM x 256 pairs and a partly filled last round costs a full one: the ratio to N x the 1-GPU rate is bounded by round_fill"}
-        del souts
+                  "full_rounds_per_gpu": full, "tail_pairs": tail,
+                  "tail_shape": "none" if tail == 0 else ("128-thread CTAs (0.55 round)" if tail <= sms_n * 128 else "full round"),
+                  "note": "a launch is one round of #SM x 256 pairs; the last, partly filled round runs as CTAs of 128 threads when it holds at most #SM x 128 pairs (host_api.inc pair_cfg)"}
+        if world == 1:
+            # the shard of each rank count, timed on this GPU: strong-scaling efficiency of the kernel path = t(2^20) / (N t(2^20 / N))
+            shard = {}
+            for N in (2, 4, 8):
+                t = time_shard((1 << 20) // N)
+                shard["N=%d" % N] = {"pairs_per_gpu": (1 << 20) // N, "ms": t, "efficiency_vs_1gpu": sms / (N * t)}
+            strong["shard_times_on_one_gpu"] = shard
 
     if rank != 0:
         if world > 1:

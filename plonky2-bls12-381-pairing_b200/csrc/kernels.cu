@@ -84,11 +84,14 @@ __device__ __forceinline__ void report(int e, int* err) {
 // ---- tower kernels (persistent, one CTA per SM) ---------------------------------------------------
 // Lock-step kernels: every thread of the CTA executes the same program (threads past the end of the
 // batch recompute the last element and drop the result), so sync_point() barriers are legal.
+// They run with 256 threads per CTA (two warps per SM sub-partition), or with 128 for the tail of a batch
+// (host_api.inc pair_cfg): the slot arena is indexed by threadIdx.x with a fixed stride of BLOCK, the barriers are
+// per group of 128 threads, and the tensor-memory columns of the second warp group simply stay unused.
 __global__ void __launch_bounds__(BLOCK, 1)
 k_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* out, size_t n, int mode, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_final_exp(const uint32_t* in, uint32_t* out, size_t n, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -119,7 +122,7 @@ k_pairing(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, uint32_t* 
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
 
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_g2_prepare(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, u4* garena, int* err, uint32_t* dump_coeffs) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_f12_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int wbasis, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(BLOCK, 1)
 k_tower_inv(const uint32_t* in, uint32_t* out, size_t n, int deg, u4* garena, int* err, uint32_t* dump) {
   Ctx cx = make_ctx(garena, B381_LOCKSTEP);
   const int w = deg == 12 ? 144 : 72;
-  for (size_t base = (size_t)blockIdx.x * BLOCK; base < n; base += (size_t)gridDim.x * BLOCK) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
     __syncthreads();
     size_t i = base + threadIdx.x;
     const bool active = i < n;

@@ -794,6 +794,22 @@ B381_NOINL void f2_override_if(u4* r, int cond, int one) {
   st_f2(r, c0, c1);
 }
 
+// r = cond ? a : r, executed by every thread of the warp (uniform loads / stores, per-thread selection): see above
+B381_NOINL void f2_select_if(u4* r, const u4* a, int cond) {
+  Fp c0, c1, k0, k1;
+  ld_f2(c0, c1, r);
+  ld_f2(k0, k1, a);
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    c0.l[i] = cond ? k0.l[i] : c0.l[i];
+    c1.l[i] = cond ? k1.l[i] : c1.l[i];
+  }
+#ifdef B381_TRACK_BOUNDS
+  if (cond) { c0.lb = k0.lb; c0.ub = k0.ub; c0.mag = k0.mag; c1.lb = k1.lb; c1.ub = k1.ub; c1.mag = k1.mag; }
+#endif
+  st_f2(r, c0, c1);
+}
+
 // canonical test a == 0 (full reduction; rare path)
 B381_NOINL bool f2_is_zero(const u4* a) {
   Fp a0, a1;
@@ -938,7 +954,7 @@ B381_DEV B381_INL void f6_sqr(const Ctx& cx, int r, int a, int t) {
 // r may alias a or b.  Scratch: t1 = 6 slots (aa, bb), t2 = 6 slots (sa, sb).  The xi-multiplications of the
 // Fp6 products are folded into the sums of products (f6_mul_x): b and a + 3.. are stored values, the two
 // coefficients of sb that get multiplied by xi are weak-reduced sums.
-B381_DEV void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
+B381_DEV B381_INL void f12_mul(const Ctx& cx, int r, int a, int b, int t1, int t2) {
   const int aa = t1, bb = t1 + 3, sa = t2, sb = t2 + 3;
   for (int i = 0; i < 3; i++) {
     lin(cx, sa + i, a + i, a + 3 + i, L_ADD);
@@ -1043,7 +1059,7 @@ B381_DEV B381_INL void f12_conj(const Ctx& cx, int f) {
 
 // Frobenius map f -> f^(p^k) in place, k in 1..3; fq12_target_tree.rs:92-128, fq6_target_tree.rs:129-169.
 // Slot f + 3 i + j holds the coefficient of w^(2j+i).
-B381_DEV void f12_frobenius(const Ctx& cx, int f, int k) {
+B381_DEV B381_INL void f12_frobenius(const Ctx& cx, int f, int k) {
   for (int i = 0; i < 2; i++)
     for (int j = 0; j < 3; j++) {
       const int tw = 2 * j + i;
@@ -1055,7 +1071,7 @@ B381_DEV void f12_frobenius(const Ctx& cx, int f, int k) {
 }
 
 // Fp6 inverse; fq6_target_tree.rs:59-89.  r may alias a.  t = 5 scratch slots.
-B381_DEV void f6_inv(const Ctx& cx, int r, int a, int t) {
+B381_DEV B381_INL void f6_inv(const Ctx& cx, int r, int a, int t) {
   const int c0 = t, c1 = t + 1, c2 = t + 2, x = t + 3, y = t + 4;
   sqr(cx, c0, a); mul(cx, x, a + 1, a + 2); kcomb(cx, c0, c0, -1, x, -1, K_XI_C);        // c0 = a0^2 - xi a1 a2
   sqr(cx, c1, a + 2); lin(cx, c1, c1, -1, L_MULXI); mul(cx, x, a, a + 1); lin(cx, c1, c1, x, L_SUB);   // c1 = xi a2^2 - a0 a1
@@ -1068,7 +1084,7 @@ B381_DEV void f6_inv(const Ctx& cx, int r, int a, int t) {
 }
 
 // Fp12 inverse in place; fq12_target_tree.rs:77-90.  t = 15 scratch slots.
-B381_DEV void f12_inv(const Ctx& cx, int f, int t) {
+B381_DEV B381_INL void f12_inv(const Ctx& cx, int f, int t) {
   const int u = t, v = t + 3, w = t + 6;          // w: up to 5 + 4
   f6_sqr(cx, u, f, w);
   f6_sqr(cx, v, f + 3, w);
@@ -1086,7 +1102,7 @@ B381_DEV void f12_inv(const Ctx& cx, int f, int t) {
 // /root/reference/src/fields_as_trees/miller_loop.rs:46-104.  With z0=c0.c0, z4=c0.c1, z3=c0.c2,
 // z2=c1.c0, z1=c1.c1, z5=c1.c2:  (z0',z1') from fp4(z0,z1); (z4',z5') from fp4(z2,z3);
 // (z2',z3') from fp4(z4,z5) with the xi twist.  Three fused primitive calls, no scratch.
-B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s, int reduce = 1) {
+B381_DEV B381_INL void f12_cyclotomic_square(const Ctx& cx, int d, int s, int reduce = 1) {
   const int z0 = 0, z4 = 1, z3 = 2, z2 = 3, z1 = 4, z5 = 5;
   sync_point(cx);
   f2_cyc_fp4(S_(d + z0), S_(d + z1), S_(s + z0), S_(s + z1), S_(s + z0), S_(s + z1), 0, reduce);
@@ -1096,21 +1112,124 @@ B381_DEV void f12_cyclotomic_square(const Ctx& cx, int d, int s, int reduce = 1)
   f2_cyc_fp4(S_(d + z2), S_(d + z3), S_(s + z4), S_(s + z5), S_(s + z2), S_(s + z3), 1, reduce);
 }
 
-// r = conj(a^|x|): ark Bls12::exp_by_x (x < 0).  The running value ping-pongs between the two
-// fixed slot ranges acc / acc2 (the hot end of the arena); r may alias a.  t = 16 scratch slots.
-B381_DEV void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int acc2, int t) {
+// r = conj(a^|x|): ark Bls12::exp_by_x (x < 0), plain left-to-right form over Granger-Scott squarings.  The running
+// value ping-pongs between the two fixed slot ranges acc / acc2; r may alias a.  t = 12 scratch slots.  Not used by
+// the kernels any more: the tests keep it as the cross-check of the compressed form below.
+B381_DEV B381_INL void f12_exp_by_x_gs(const Ctx& cx, int r, int a, int acc, int acc2, int t) {
   int cur = acc, nxt = acc2;
   const uint64_t xabs = B381_X_ABS;
-  int since = 0;                                  // squarings since the last weak reduction
   for (int b = 62; b >= 0; b--) {
-    const int red = (++since == 4) || b == 0;     // input magnitude <= ~30 -> 69 -> 147 -> 303 -> reduced (bound-tracked)
-    f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur, red);
-    if (red) since = 0;
+    f12_cyclotomic_square(cx, nxt, b == 62 ? a : cur);
     const int sw = cur; cur = nxt; nxt = sw;
-    if ((xabs >> b) & 1) { f12_mul(cx, cur, cur, a, t, t + 6); since = 0; }
+    if ((xabs >> b) & 1) f12_mul(cx, cur, cur, a, t, t + 6);
   }
   for (int i = 0; i < 3; i++) lin(cx, r + i, cur + i, -1, L_COPY);
   for (int i = 3; i < 6; i++) lin(cx, r + i, cur + i, -1, L_NEG);
+}
+
+// Karabina's compressed squaring (Squaring in cyclotomic subgroups, Math. Comp. 2013): the Granger-Scott formulas
+// for (z2, z3, z4, z5) do not involve (z0, z1), so a run of squarings carries four coefficients and costs two fused
+// Fp4 squarings instead of three.  d, s: Fp12 slot ranges of which only +1, +2, +3, +5 are touched.
+B381_DEV B381_INL void f12_cyclotomic_square_c(const Ctx& cx, int d, int s) {
+  const int z4 = 1, z3 = 2, z2 = 3, z5 = 5;
+  sync_point(cx);
+  f2_cyc_fp4(S_(d + z4), S_(d + z5), S_(s + z2), S_(s + z3), S_(s + z4), S_(s + z5), 0, 1);
+  sync_point(cx);
+  f2_cyc_fp4(S_(d + z2), S_(d + z3), S_(s + z4), S_(s + z5), S_(s + z2), S_(s + z3), 1, 1);
+}
+
+// n compressed squarings src -> ... -> last (n >= 1); intermediate values alternate p0, p1, p0, ...; the caller
+// picks them so that the one before the last is not `last` itself (the squaring is out of place)
+B381_DEV B381_INL void f12_csqr_run(const Ctx& cx, int last, int src, int n, int p0, int p1) {
+  int cur = src, nxt = p0, oth = p1;
+  for (int i = 1; i <= n; i++) {
+    const int dst = i == n ? last : nxt;
+    f12_cyclotomic_square_c(cx, dst, cur);
+    cur = dst;
+    const int sw = nxt; nxt = oth; oth = sw;
+  }
+}
+
+// r = conj(a^|x|), |x| = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16, right to left:  a^|x| is the product of a^(2^i) over
+// those six i.  The first 57 squarings run in compressed form; the three values needed in full (i = 16, 48, 57)
+//   z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2),   z0 = (2 z1^2 + z2 z5 - 3 z3 z4) xi + 1
+// share ONE Fp2 inversion (Montgomery's trick; the inversion itself is the division-step one, fp32.cuh); the last six
+// squarings are ordinary Granger-Scott ones.  132 + 18 fused Fp4 squarings instead of 189 per exponentiation, paid
+// with 6 sums of products, 9 Fp2 products and one inversion: the value is the same field element, so the output of
+// the final exponentiation is unchanged bit for bit.
+// z2 = 0: the relation a b = s c^2 + conj(b) between the Fp4 coefficients of a cyclotomic element (the t-coefficient
+// of the Granger-Scott identity) gives z1 = 2 z4 z5 / z3 there, and z2 = z3 = 0 only for the identity (z1 = 0, z0 = 1;
+// gcd(p^4 - 1, p^4 - p^2 + 1) = 1).  Those cases are patched by per-thread selections inside a WARP-uniform branch
+// that runs without the lock-step barriers, so the barrier sequence of the CTA does not depend on the data.
+// r must not alias a; acc, acc2: 6 slots each (hot); t: 12 scratch slots.
+B381_DEV B381_INL void f12_exp_by_x(const Ctx& cx, int r, int a, int acc, int acc2, int t) {
+  const int z0 = 0, z4 = 1, z3 = 2, z2 = 3, z1 = 4, z5 = 5;
+  f12_csqr_run(cx, r, a, 16, acc, acc2);                 // compressed a^(2^16) -> r
+  f12_csqr_run(cx, t, r, 32, acc, acc2);                 // compressed a^(2^48) -> t .. t + 5
+  f12_csqr_run(cx, acc, t, 9, acc, acc2);                // compressed a^(2^57) -> acc (the 8th lands in acc2)
+  const int B[3] = {r, t, acc};
+  const int u = t + 6, w = acc2;                         // 6 + 6 free slots
+  const int ZERO = u, ONE = u + 1, X = u + 2, Y = u + 3;
+  sync_point(cx); f2_set_small(S_(ZERO), 0);
+  sync_point(cx); f2_set_small(S_(ONE), 1);
+  bool zf[3], any = false;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int b = B[k];
+    sync_point(cx);
+    zf[k] = f2_is_zero(S_(b + z2));
+    any = any || zf[k];
+    lin(cx, X, b + z4, -1, L_TRIPLE);
+    sop3(cx, b + z1, b + z5, b + z5, b + z4, X, ZERO, ZERO, SOP_XI0 | SOP_SUB2, b + z3, b + z3);   // numerator
+    lin(cx, b + z0, b + z2, -1, L_MUL4);                                                            // denominator
+  }
+#if defined(__CUDA_ARCH__)
+  any = __any_sync(__activemask(), any);
+#endif
+  if (any) {                                             // z2 = 0 somewhere in this warp (the identity, mostly)
+    Ctx c2 = cx;
+    c2.sync = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int b = B[k];
+      mul(c2, X, b + z4, b + z5);
+      lin(c2, X, X, X, L_ADD_R);                         // 2 z4 z5
+      f2_select_if(slot(c2, b + z1), slot(c2, X), zf[k]);
+      f2_select_if(slot(c2, b + z0), slot(c2, b + z3), zf[k]);
+      const bool dz = f2_is_zero(slot(c2, b + z0));
+      f2_override_if(slot(c2, b + z0), dz, 1);           // the identity: numerator 0, denominator 1
+    }
+  }
+  mul(cx, w, B[0] + z0, B[1] + z0);                      // d0 d1
+  mul(cx, w + 1, w, B[2] + z0);                          // d0 d1 d2
+  sync_point(cx); f2_inv(S_(w + 1), S_(w + 1));
+  mul(cx, w + 2, w + 1, w);                              // 1 / d2
+  mul(cx, w + 1, w + 1, B[2] + z0);                      // 1 / (d0 d1)
+  mul(cx, w + 3, w + 1, B[0] + z0);                      // 1 / d1
+  mul(cx, w, w + 1, B[1] + z0);                          // 1 / d0
+  const int inv[3] = {w, w + 3, w + 2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int b = B[k];
+    mul(cx, b + z1, b + z1, inv[k]);
+    lin(cx, X, b + z4, -1, L_TRIPLE);
+    lin(cx, X, X, -1, L_NEG);                            // -3 z4
+    lin(cx, Y, b + z1, -1, L_DBL);                       // 2 z1
+    sop3(cx, b + z0, Y, b + z1, b + z2, b + z5, b + z3, X, SOP_XI0 | SOP_XI1 | SOP_XI2);   // xi goes on the undoubled factor (operand bounds)
+    lin(cx, b + z0, b + z0, ONE, L_ADD_R);
+  }
+  f12_mul(cx, r, r, t, w, u);                            // a^(2^16 + 2^48)
+  f12_mul(cx, r, r, acc, t, u);                          // ... + 2^57
+  f12_cyclotomic_square(cx, w, acc);
+  f12_cyclotomic_square(cx, acc, w);
+  f12_cyclotomic_square(cx, w, acc);                     // a^(2^60)
+  f12_mul(cx, r, r, w, t, u);
+  f12_cyclotomic_square(cx, acc, w);
+  f12_cyclotomic_square(cx, w, acc);                     // a^(2^62)
+  f12_mul(cx, r, r, w, t, u);
+  f12_cyclotomic_square(cx, acc, w);                     // a^(2^63)
+  f12_mul(cx, r, r, acc, t, u);
+  for (int i = 3; i < 6; i++) lin(cx, r + i, r + i, -1, L_NEG);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1385,7 +1504,7 @@ B381_DEV void zk_miller_loop_multi(const Ctx& cx, const MultiSlots& s, int k, co
 // ---------------------------------------------------------------------------------------------
 struct FexpSlots { int f, y0, y1, y2, r, acc, acc2, T; };
 
-B381_DEV void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
+B381_DEV B381_INL void final_exponentiation(const Ctx& cx, const FexpSlots& s) {
   const int f = s.f, y0 = s.y0, y1 = s.y1, y2 = s.y2, r = s.r, acc = s.acc, acc2 = s.acc2, T = s.T;
   // easy part: r = f^((p^6-1)(p^2+1))
   f12_copy(cx, r, f);

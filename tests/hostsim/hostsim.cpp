@@ -236,7 +236,26 @@ int hs_tracking(void) {
 extern "C" int hs_fp12_exp_by_x(const uint32_t* a, uint32_t* out) {
   Ctx cx = make_ctx();
   bool ok = f12_load_ext(cx, FE_F, a);
-  f12_exp_by_x(cx, FE_Y0, FE_F, FE_ACC, FE_ACC2, FE_T);
-  f12_store_ext(cx, out, FE_Y0);
+  f12_exp_by_x(cx, FE_Y1, FE_F, FE_ACC, FE_ACC2, FE_T);
+  f12_store_ext(cx, out, FE_Y1);
+  return ok ? 0 : 1;
+}
+
+// the plain (uncompressed, left-to-right) form: the fall-back of the compressed one
+extern "C" int hs_fp12_exp_by_x_plain(const uint32_t* a, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, FE_F, a);
+  f12_exp_by_x_gs(cx, FE_Y1, FE_F, FE_ACC, FE_ACC2, FE_T);
+  f12_store_ext(cx, out, FE_Y1);
+  return ok ? 0 : 1;
+}
+
+// n compressed (Karabina) squarings; only the coefficients +1, +2, +3, +5 of the output are meaningful
+extern "C" int hs_fp12_compressed_squarings(const uint32_t* a, int n, uint32_t* out) {
+  Ctx cx = make_ctx();
+  bool ok = f12_load_ext(cx, FE_F, a);
+  for (int i = 0; i < 6; i++) f2_set_small(slot(cx, FE_Y1 + i), 0);
+  f12_csqr_run(cx, FE_Y1, FE_F, n, FE_ACC, FE_ACC2);
+  f12_store_ext(cx, out, FE_Y1);
   return ok ? 0 : 1;
 }

@@ -139,6 +139,30 @@ def test_golden_fixture_ragged_sizes(L, lib, z, n):
     assert np.array_equal(out.reshape(n, 144), z["pairing"][:n])
 
 
+def test_tail_launch_shapes(L, lib, z):
+    """Batches around the launch-shape boundaries of the pair kernels (host_api.inc pair_cfg): up to #SM x 128 pairs
+    run as CTAs of 128 threads, more as a full round of 256-thread CTAs, and the last launch of a larger batch is a
+    tail of either shape.  Every output must equal the fixture value of its source pair."""
+    sm = ctypes.c_int(0)
+    L.check(lib.b381_device_info(ctypes.byref(sm), None, None, None))
+    half, full = sm.value * 128, sm.value * 256
+    for n in (half - 1, half, half + 1, full, full + 1, full + half, 2 * full + 77):
+        perm = np.random.default_rng(n).integers(0, 256, size=n)
+        g1, g2 = _pairs(z, perm)
+        out = np.zeros(n * 144, dtype=np.uint32)
+        L.check(lib.b381_pairing(util.p32(g1), util.p32(g2), None, util.p32(out), n, L.MODE_ARK))
+        assert np.array_equal(out.reshape(n, 144), z["pairing"][perm]), n
+    for n in (half, half + 1, full + 3):
+        perm = np.random.default_rng(n + 1).integers(0, 256, size=n)
+        g1, g2 = _pairs(z, perm)
+        out = np.zeros(n * 144, dtype=np.uint32)
+        L.check(lib.b381_miller_loop(util.p32(g1), util.p32(g2), None, util.p32(out), n, L.MODE_ARK))
+        assert np.array_equal(out.reshape(n, 144), z["miller_ark"][perm]), n
+        fin = np.ascontiguousarray(z["miller_ark"][perm]).reshape(-1)
+        L.check(lib.b381_final_exp(util.p32(fin), util.p32(out), n))
+        assert np.array_equal(out.reshape(n, 144), z["pairing"][perm]), n
+
+
 def test_zk_mode_batch(L, lib, z):
     n = 16
     g1, g2 = _pairs(z, list(range(n)))

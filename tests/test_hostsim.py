@@ -277,6 +277,30 @@ def test_safegcd_inversion(hs):
     assert hs.hs_fp_inv(A([0] * 12), out) == 2 and list(out) == [0] * 12
 
 
+def test_compressed_exp_by_x(hs):
+    """The final exponentiation's exp_by_x runs 57 of its 63 squarings in Karabina's compressed form and
+    decompresses three values with one shared inversion (tower.cuh f12_exp_by_x): same field element as the plain
+    Granger-Scott ladder and as the oracle, on cyclotomic elements; the identity (z2 = 0) takes the fall-back."""
+    z = util.pairs_256()
+    out, out2 = u(144), u(144)
+    for i in (0, 5, 77, 200, 255):
+        a = A(z["pairing"][i])
+        e = o.f12_from_limbs32(list(z["pairing"][i]))
+        assert hs.hs_fp12_exp_by_x(a, out) == 0 and hs.hs_fp12_exp_by_x_plain(a, out2) == 0
+        assert list(out) == list(out2) and o.f12_eq(o.f12_from_limbs32(list(out)), o.ark_exp_by_x(e))
+    one = A(o.f12_to_limbs32(o.F12_ONE))
+    assert hs.hs_fp12_exp_by_x(one, out) == 0 and list(out) == list(one)
+    # compressed squarings alone: coefficients z4, z3, z2, z5 (slots 1, 2, 3, 5) of a^(2^n)
+    e = o.f12_from_limbs32(list(z["pairing"][9]))
+    w = e
+    for n in range(1, 20):
+        w = o.f12_cyclotomic_square(w)
+        if n in (1, 2, 7, 19):
+            assert hs.hs_fp12_compressed_squarings(A(z["pairing"][9]), n, out) == 0
+            got = o.f12_from_limbs32(list(out))
+            assert (got[0][1], got[0][2], got[1][0], got[1][2]) == (w[0][1], w[0][2], w[1][0], w[1][2])
+
+
 def test_wire_formats(hs):
     """Witness digits (fq_target.rs:300-313, fq12_target.rs:408-416) and the ZCash / IETF point encodings
     against the oracle: round trips, both y signs, infinity, uncompressed, and every rejection path."""
