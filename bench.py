@@ -325,15 +325,20 @@ def main():
     # ---- roofline of the dominant (only) kernel of the step: k_pairing -----------------------------
     kernel_s = ms_per_step * 1e-3                       # the step is ceil(n / 37888) back-to-back k_pairing launches
     alg_ginst = n * FP_MULS_PAIRING * MACS_PER_FP_MUL / kernel_s / 1e9
-    traffic = None
+    traffic, executed = None, None
     tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile))
             traffic = tj.get("k_pairing_dram_bytes_per_step_2p20") if n == PAIRS_PER_GPU else None
+            executed = tj.get("k_pairing_wide_multiplies_executed_per_pairing")
         except Exception:
             traffic = None
     roofline = {"bound": "imad", "achieved": alg_ginst, "peak": pk.value, "unit": "G IMAD.WIDE/s", "frac": alg_ginst / pk.value,
+                "executed_frac": (n * executed / kernel_s / 1e9 / pk.value) if executed else None,
+                "executed_note": "share of the multiplier issue slots filled by the wide multiplies the kernel really executes (per-pairing count from the "
+                                 "ncu opcode table of this build, profiles/ncu_traffic.json): lower than `frac` because lazy reductions, compressed cyclotomic "
+                                 "squarings and safegcd inversions do less than the 14 627 x 300 textbook multiplies `frac` is defined on",
                 "traffic": traffic, "traffic_note": "DRAM bytes per step (28 launches) from profiles/ncu_traffic.json; algorithmic bytes per step = pairs x 864",
                 "note": "integer-multiply roofline (north_star): algorithmic work = pairs x %d Fp-mul x %d 32x32->64 MACs (1 IMAD.WIDE each); "
                         "peak = fused IMAD.WIDE.U32 rate measured live by b381_imad_peak (faster of two register allocations of the same "
