@@ -394,6 +394,49 @@ def main():
         extras["g2_prepare_points_per_s_2p16"] = m / t * 1e3
         t = time_dev(lambda: L.check(lib.b381_miller_loop_prepared_dev(d1.data_ptr(), co.data_ptr(), None, mout.data_ptr(), m, 0, 0, st)), reps=2)
         extras["miller_loops_prepared_per_s_2p16"] = m / t * 1e3
+        # the same stage in the packed (internal-format, tile-interleaved) layout: no conversions, coalesced reads
+        pkd = torch.empty(lib.b381_g2_packed_words(m), dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_g2_prepare_packed_dev(d2.data_ptr(), pkd.data_ptr(), m, 0, st)), reps=2)
+        extras["g2_prepare_packed_points_per_s_2p16"] = m / t * 1e3
+        mpk = torch.empty(m * 144, dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_miller_loop_packed_dev(d1.data_ptr(), pkd.data_ptr(), None, mpk.data_ptr(), m, 0, 0, st)), reps=2)
+        # per line: 2 Fp2-by-Fp products (4 Fp-mul) + six sums of three Fp2 products (54); per squaring 2 x 27 + ... = the oracle's
+        # count of the whole loop minus the curve steps: 6 952 - 63 x 25 - 5 x 37 = 5 192 Fp-mul
+        extras["miller_loops_packed_per_s_2p16"] = {"per_s": m / t * 1e3, "imad_frac": imad_frac(m / t * 1e3, FP_MULS_MILLER - 63 * 25 - 5 * 37),
+                                                    "coefficient_stream_GBps": m / t * 1e3 * 4 * L.G2PREP_WORDS / 1e9}
+        extras["miller_packed_equals_prepared"] = bool(torch.equal(mpk, mout))
+        del pkd, mpk
+        # whole rounds (2 x #SM x 256 pairs): the 2^16 of config #3 is 1.73 rounds and costs 2
+        sms_c = torch.cuda.get_device_properties(dev).multi_processor_count
+        mr = 2 * sms_c * 256
+        pkd = torch.empty(lib.b381_g2_packed_words(mr), dtype=torch.int32, device=dev)
+        mo = torch.empty(mr * 144, dtype=torch.int32, device=dev)
+        L.check(lib.b381_g2_prepare_packed_dev(d2.data_ptr(), pkd.data_ptr(), mr, 0, st))
+        wr = {}
+        for name, fn, fpm in (("miller_loops", lambda: lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mo.data_ptr(), mr, 0, st), FP_MULS_MILLER),
+                              ("miller_loops_packed", lambda: lib.b381_miller_loop_packed_dev(d1.data_ptr(), pkd.data_ptr(), None, mo.data_ptr(), mr, 0, 0, st), FP_MULS_MILLER - 63 * 25 - 5 * 37),
+                              ("pairings_packed", lambda: lib.b381_miller_loop_packed_dev(d1.data_ptr(), pkd.data_ptr(), None, mo.data_ptr(), mr, 0, 1, st), FP_MULS_PAIRING - 63 * 25 - 5 * 37)):
+            t = time_dev(lambda: L.check(fn()), reps=2)
+            wr[name] = {"per_s": mr / t * 1e3, "imad_frac": imad_frac(mr / t * 1e3, fpm)}
+        wr["pairs"] = mr
+        extras["whole_rounds_2x"] = wr
+        del pkd, mo
+        # config #5 against cached (packed) public keys: four pairs per thread share the squarings
+        nk = n
+        while nk * L.G2PREP_WORDS * 4 > 0.5 * torch.cuda.mem_get_info(dev)[0]:
+            nk //= 2
+        pkd = torch.empty(lib.b381_g2_packed_words(nk), dtype=torch.int32, device=dev)
+        L.check(lib.b381_g2_prepare_packed_dev(d2.data_ptr(), pkd.data_ptr(), nk, 0, st))
+        r144 = torch.empty(144, dtype=torch.int32, device=dev); r144b = torch.empty(144, dtype=torch.int32, device=dev)
+        t = time_dev(lambda: L.check(lib.b381_multi_miller_loop_packed_dev(d1.data_ptr(), pkd.data_ptr(), None, r144.data_ptr(), nk, 0, st)), reps=2)
+        L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, r144b.data_ptr(), nk, 0, st))
+        torch.cuda.synchronize()
+        # per pair: 68 lines x 43 Fp-mul + a quarter of the 63 squarings x 36 + a quarter of one Fq12 product
+        extras["config5_multi_miller_packed"] = {"pairs": nk, "per_s": nk / t * 1e3, "imad_frac": imad_frac(nk / t * 1e3, 68 * 43 + (63 * 36 + 54) / 4),
+                                                 "coefficient_stream_GBps": nk / t * 1e3 * 4 * L.G2PREP_WORDS / 1e9,
+                                                 "equals_unprepared_multi_miller": bool(torch.equal(r144, r144b)),
+                                                 "note": "lines from the packed G2Prepared stage (19.6 KB per pair, streamed from HBM), tree reduction included"}
+        del pkd
         mref = torch.empty(m * 144, dtype=torch.int32, device=dev)
         L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mref.data_ptr(), m, 0, st))
         torch.cuda.synchronize()
@@ -465,6 +508,18 @@ def main():
             # bucket method at window c: ceil(256 / c) mixed additions of 11 Fp-mul per point
             c = 16 if logn >= 17 else 8; w = 256 // c
             grp["g1_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": c, "imad_frac_bucket_additions": imad_frac(nn / t * 1e3, w * 11)}
+        # G2 bucket method on distinct points [s_i] Q_i (made on the device); window c: ceil(256 / c) general additions per point
+        n2 = min(n, 1 << 20)
+        mp2 = torch.empty(n2 * 48, dtype=torch.int32, device=dev); mf2 = torch.empty(n2, dtype=torch.uint8, device=dev)
+        L.check(lib.b381_g2_scalar_mul_dev(d2.data_ptr(), None, sc.data_ptr(), mp2.data_ptr(), mf2.data_ptr(), n2, st))
+        r2 = torch.empty(48, dtype=torch.int32, device=dev)
+        for logn in (16, 20):
+            nn = 1 << logn
+            if nn > n2:
+                continue
+            t = time_dev(lambda: L.check(lib.b381_g2_msm_dev(mp2.data_ptr(), None, sc2.data_ptr(), r2.data_ptr(), rf.data_ptr(), nn, st)), reps=2)
+            grp["g2_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": 16 if logn >= 17 else 8}
+        del mp2, mf2
         t = time_dev(lambda: L.check(lib.b381_g1_sum_dev(mp.data_ptr(), None, r1.data_ptr(), rf.data_ptr(), n, st)), reps=2)
         grp["g1_sum_points_per_s"] = n / t * 1e3
         L.check(lib.b381_check_dev(st))

@@ -82,6 +82,10 @@ SIGNATURES = {
     "b381_miller_loop_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_pairing_prepared": [_u32p, _u32p, _u8p, _u32p, ctypes.c_size_t, ctypes.c_int],
     "b381_g2_prepare_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
+    "b381_g2_packed_words": [ctypes.c_size_t],
+    "b381_g2_prepare_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
+    "b381_miller_loop_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
+    "b381_multi_miller_loop_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
     "b381_miller_loop_prepared_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_check_dev": [ctypes.c_void_p],
     "b381_ctx_create": [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)],
@@ -121,7 +125,7 @@ SIGNATURES = {
     "b381_imad_peak": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
 }
 G2PREP_WORDS = 68 * 72
-_RESTYPES = {"b381_last_error": ctypes.c_char_p, "b381_kernel_launches": ctypes.c_ulonglong}
+_RESTYPES = {"b381_last_error": ctypes.c_char_p, "b381_kernel_launches": ctypes.c_ulonglong, "b381_g2_packed_words": ctypes.c_size_t}
 
 
 def load():

@@ -165,6 +165,41 @@ k_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf
   B381_TMEM_END();
 }
 
+// G2Prepared in the packed layout (programs.cuh): `packed` is this launch's first tile; the launch offset is a multiple
+// of BLOCK, the CTA base a multiple of 128 (tail launches use CTAs of 128 threads), so point i of the launch sits at
+// g2pack_index(i).  Threads past the end of the batch work on the last point and write to a dump tile.
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_prepare_packed(const uint32_t* g2, u4* packed, size_t n, int mode, u4* garena, int* err, u4* dump_tile) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    const bool active = i < n;
+    u4* dst = active ? packed + g2pack_index(i) : dump_tile + threadIdx.x;
+    if (!active) i = n - 1;
+    int e = prog_g2_prepare_packed(cx, g2 + 48 * i, dst, mode);
+    if (active) report(e, err);
+  }
+  B381_TMEM_END();
+}
+
+// Miller loop (optionally + final exponentiation) of (P, packed prepared Q)
+__global__ void __launch_bounds__(BLOCK, 1)
+k_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, u4* garena, int* err, uint32_t* dump) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    int e = prog_miller_packed(cx, g1 + 24 * i, packed + g2pack_index(i), inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode, do_fe);
+    if (active) report(e, err);
+  }
+  B381_TMEM_END();
+}
+
 // every thread runs the Miller loops of TWO pairs per round with shared squarings, multiplies the
 // result into a private accumulator and dumps it (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
@@ -187,6 +222,40 @@ k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), M2_ACC);
   B381_TMEM_END();
 }
+
+// every thread runs the Miller loops of FOUR pairs per round against packed prepared Q's with shared squarings and
+// multiplies the result into its private accumulator (the partial products are reduced like k_multi_miller's).
+// A round covers PK_K consecutive tiles: thread t takes point t of each, so the line reads stay coalesced.
+__global__ void __launch_bounds__(BLOCK, 1)
+k_multi_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, size_t n, uint32_t* partial, int accumulate, u4* garena, int* err, const u4* one_tile) {
+  B381_TMEM_BEGIN();
+  Ctx cx = B381_TMEM_CTX(garena);
+  if (accumulate) f12_load_raw(cx, M2_ACC, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x));
+  else f12_set_one(cx, M2_ACC);
+  for (size_t base = (size_t)blockIdx.x * BLOCK * PK_K; base < n; base += (size_t)gridDim.x * BLOCK * PK_K) {
+    __syncthreads();
+    const uint32_t* pg1[PK_K];
+    const u4* ppk[PK_K];
+    int pinf[PK_K];
+    bool any = false;
+    for (int j = 0; j < PK_K; j++) {
+      size_t i = base + (size_t)j * BLOCK + threadIdx.x;
+      const bool act = i < n;
+      if (!act) i = n - 1;
+      pg1[j] = g1 + 24 * i;
+      ppk[j] = packed + g2pack_index(i);
+      pinf[j] = act ? (inf ? inf[i] : 0) : 3;
+      any = any || act;
+    }
+    int e = miller_pk_to_slots(cx, pg1, ppk, pinf, one_tile + threadIdx.x);
+    if (any) report(e, err);
+    f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);
+  }
+  f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), M2_ACC);
+  B381_TMEM_END();
+}
+
+__global__ void __launch_bounds__(BLOCK, 1) k_fill_one_line(u4* tile) { fill_one_line(tile + threadIdx.x); }
 
 // out[j] = product of in[j*K .. min((j+1)K, n_in))   (internal format; trip counts differ -> no lock step)
 __global__ void __launch_bounds__(BLOCK, 1)
@@ -280,6 +349,40 @@ k_g2_point_sum(const uint32_t* in, const uint8_t* in_inf, size_t n_in, uint32_t*
       report(prog_g2_point_sum(cx, in + lo * 48, in_inf ? in_inf + lo : nullptr, hi - lo, out + j * 48, out_inf + j), err);
     }
   }
+}
+
+// ---- G2 bucket method (programs.cuh): per-thread trip counts differ -> no lock step, no tensor memory ----------
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_msm_bucket_sums(const uint32_t* pts, const uint32_t* idx, const unsigned int* start, size_t m, uint32_t* buckets, u4* garena, int* err) {
+  Ctx cx = make_ctx(garena, 0);
+  for (size_t b = (size_t)blockIdx.x * BLOCK + threadIdx.x; b < m; b += (size_t)gridDim.x * BLOCK)
+    report(prog_g2_bucket_sum(cx, pts, idx, start[b], start[b + 1], buckets + (size_t)G2_RAW_JAC * b), err);
+}
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_msm_chunks(const uint32_t* buckets, int W, int c, int CH, uint32_t* partial, u4* garena) {
+  Ctx cx = make_ctx(garena, 0);
+  const uint32_t B = 1u << c, nchunk = (B + CH - 1) / CH;
+  const size_t total = (size_t)W * nchunk;
+  for (size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x; t < total; t += (size_t)gridDim.x * BLOCK) {
+    const uint32_t w = (uint32_t)(t / nchunk), j = (uint32_t)(t % nchunk);
+    uint32_t lo = j * CH, hi = lo + CH < B ? lo + CH : B;
+    if (lo == 0) lo = 1;                              // digit 0 contributes nothing
+    prog_g2_chunk_weighted(cx, buckets + (size_t)G2_RAW_JAC * w * B, lo, hi, partial + (size_t)G2_RAW_JAC * t);
+  }
+}
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_jac_sums(const uint32_t* in, size_t n_in, size_t per, uint32_t* sums, size_t n_out, u4* garena) {
+  Ctx cx = make_ctx(garena, 0);
+  for (size_t j = (size_t)blockIdx.x * BLOCK + threadIdx.x; j < n_out; j += (size_t)gridDim.x * BLOCK) {
+    const size_t lo = j * per, hi = lo + per < n_in ? lo + per : n_in;
+    prog_g2_jac_sum(cx, in, lo, hi, sums + (size_t)G2_RAW_JAC * j);
+  }
+}
+__global__ void __launch_bounds__(BLOCK, 1)
+k_g2_msm_final(const uint32_t* sums, int W, int c, uint32_t* out48, uint8_t* out_inf, u4* garena) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Ctx cx = make_ctx(garena, 0);
+  prog_g2_msm_final(cx, sums, W, c, out48, out_inf);
 }
 
 __global__ void k_fill_one_ext(uint32_t* out144) {

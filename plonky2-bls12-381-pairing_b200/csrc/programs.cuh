@@ -238,6 +238,184 @@ B381_DEV B381_INL int prog_miller_prepared(const Ctx& cx, const uint32_t* g1, co
   return err;
 }
 
+// ---- G2Prepared in the library's own layout ("packed": device memory only) ----------------------------
+// The same 68 triples per Q, but (1) in the INTERNAL number format -- the values the on-the-fly loop would hand from
+// its curve step to its line multiplication, so consuming a coefficient costs no conversion (the external format
+// costs six Fp multiplications per line) -- and (2) laid out exactly like a range of arena slots: points are grouped
+// in tiles of B381_GS (= the CTA size on the device, 1 on the host simulation); inside a tile, uint4 group g of
+// coefficient c of point j sits at (c * GPS + g) * B381_GS + j.  A warp therefore reads 512 contiguous bytes per
+// group, and a coefficient is addressed like a slot: the Miller loop multiplies straight out of the buffer.
+// ARK mode stores what ark_double_step_fused leaves, (i, 3j, h): the sign of h is applied by the consumer.
+constexpr int G2PACK_SLOTS = G2PREP_TRIPLES * 3;
+B381_DEV B381_INL size_t g2pack_u4_per_tile() { return (size_t)G2PACK_SLOTS * SLOT; }
+B381_DEV B381_INL size_t g2pack_index(size_t i) { return (i / B381_GS) * g2pack_u4_per_tile() + (i % B381_GS); }
+
+B381_DEV B381_INL void pack_triple(const Ctx& cx, u4* dst, int L) {
+  for (int k = 0; k < 3; k++) { sync_point_lin(cx); f2_lin(dst + k * SLOT, S_(L + k), nullptr, L_COPY); }
+}
+B381_DEV B381_INL void prefetch_triple(const u4* src) {
+#if defined(__CUDA_ARCH__)
+  for (int g = 0; g < 3 * GPS; g++) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + g * B381_GS));
+#else
+  (void)src;
+#endif
+}
+
+// pk = this point's first group (buffer + g2pack_index(i))
+B381_DEV B381_INL int prog_g2_prepare_packed(const Ctx& cx, const uint32_t* g2, u4* pk, int mode) {
+  int err = 0;
+  const int sQ = mode == MODE_ZK ? ML_Q : PP_Q, sR = mode == MODE_ZK ? ML_R : PP_R;
+  if (!f2_load_ext(S_(sQ), g2)) err |= ERR_NOT_CANONICAL;
+  if (!f2_load_ext(S_(sQ + 1), g2 + 24)) err |= ERR_NOT_CANONICAL;
+  lin(cx, sR, sQ, -1, L_COPY);
+  lin(cx, sR + 1, sQ + 1, -1, L_COPY);
+  f2_set_small(S_(sR + 2), 1);
+  int idx = 0;
+  if (mode == MODE_ZK) {
+    const uint64_t xh = B381_X_ABS >> 1;
+    bool found_one = false;
+    for (int b = 63; b >= 0; b--) {
+      bool bit = (xh >> b) & 1;
+      if (!found_one) { found_one = bit; continue; }
+      zk_double_step(cx, ML_R, ML_L, ML_T); pack_triple(cx, pk + (size_t)3 * SLOT * idx++, ML_L);
+      if (bit) { zk_add_step(cx, ML_R, ML_Q, ML_L, ML_T); pack_triple(cx, pk + (size_t)3 * SLOT * idx++, ML_L); }
+    }
+    zk_double_step(cx, ML_R, ML_L, ML_T); pack_triple(cx, pk + (size_t)3 * SLOT * idx++, ML_L);
+  } else {
+    const uint64_t xabs = B381_X_ABS;
+    for (int b = 62; b >= 0; b--) {
+      ark_double_step_fused(cx, PP_R, PP_L, PP_T); pack_triple(cx, pk + (size_t)3 * SLOT * idx++, PP_L);
+      if ((xabs >> b) & 1) { ark_add_step(cx, PP_R, PP_Q, PP_L, PP_T); pack_triple(cx, pk + (size_t)3 * SLOT * idx++, PP_L); }
+    }
+  }
+  return err;
+}
+
+// Miller loop of (P, packed Q) -> slots ML_F..; same values as miller_to_slots on (P, Q)
+B381_DEV B381_INL int miller_packed_to_slots(const Ctx& cx, const uint32_t* g1, const u4* pk, int inf, int mode) {
+  int err = 0;
+  const bool ident = (inf & 3) != 0;
+  const int sP = mode == MODE_ZK ? ML_P : PP_P;
+  if (ident) f2_set_small(S_(sP), 0);
+  else if (!f2_load_ext(S_(sP), g1)) err |= ERR_NOT_CANONICAL;
+  int idx = 0;
+  prefetch_triple(pk);
+  if (mode == MODE_ZK) {
+    f12_set_one(cx, ML_F);
+    const uint64_t xh = B381_X_ABS >> 1;
+    bool found_one = false;
+    auto line = [&]() {
+      const u4* src = pk + (size_t)3 * SLOT * idx++;
+      if (idx < G2PREP_TRIPLES) prefetch_triple(src + 3 * SLOT);
+      for (int k = 0; k < 3; k++) { sync_point_lin(cx); f2_lin(S_(ML_L + k), src + k * SLOT, nullptr, L_COPY); }
+      zk_ell(cx, ML_F, ML_L, ML_P, ML_T);
+    };
+    for (int b = 63; b >= 0; b--) {
+      bool bit = (xh >> b) & 1;
+      if (!found_one) { found_one = bit; continue; }
+      line();
+      if (bit) line();
+      f12_sqr(cx, ML_F, ML_T, ML_L);
+    }
+    line();
+  } else {
+    const uint64_t xabs = B381_X_ABS;
+    // static bank roles as in miller_prepared_to_slots: squaring A -> B, doubling line B -> A, addition line A -> B + copy back
+    for (int b = 62; b >= 0; b--) {
+      if (b != 62) f12_sqr_oop(cx, PP_B, PP_A, PP_T, PP_L);
+      else f12_set_one(cx, PP_B);
+      const u4* src = pk + (size_t)3 * SLOT * idx++;
+      if (idx < G2PREP_TRIPLES) prefetch_triple(src + 3 * SLOT);
+      ark_ell_oop_ext(cx, PP_A, PP_B, src, PP_L, PP_P, 1);
+      if ((xabs >> b) & 1) {
+        src = pk + (size_t)3 * SLOT * idx++;
+        if (idx < G2PREP_TRIPLES) prefetch_triple(src + 3 * SLOT);
+        ark_ell_oop_ext(cx, PP_B, PP_A, src, PP_L, PP_P, 0);
+        f12_copy(cx, PP_A, PP_B);
+      }
+    }
+  }
+  f12_conj(cx, ML_F);
+  if (ident) f12_set_one(cx, ML_F);
+  return err;
+}
+
+B381_DEV B381_INL int prog_miller_packed(const Ctx& cx, const uint32_t* g1, const u4* pk, int inf, uint32_t* out, int mode, int do_fe) {
+  int err = miller_packed_to_slots(cx, g1, pk, inf, mode);
+  if (do_fe) { err |= final_exp_slots(cx, ML_F); f12_store_ext(cx, out, FE_F); }
+  else f12_store_ext(cx, out, ML_F);
+  return err;
+}
+
+// ---- multi-Miller loop over packed prepared Q's: K pairs per thread share every squaring ----------------------
+// (ark squares f once per bit for the whole batch; with the curve steps cached the per-thread state of a
+// pair is just P, so four pairs fit where the on-the-fly loop holds two).  ARK mode.  Pair j reads its lines at
+// line[j] + 3 * SLOT * (triple index); a pair that contributes 1 (identity, or past the end of the batch) points at a
+// constant line (1, 0, 0) instead, so control flow stays uniform.  Result in bank A (= ML_F).
+constexpr int PK_K = 4;
+struct MillerSlotsPK { int A, B, L, T; int P[PK_K]; };
+constexpr int PK_P0 = PP_P, PK_P1 = PP_P2, PK_P2 = PP_R2, PK_P3 = PP_Q2;   // global-memory slots (written under `if (ident)`)
+static_assert(PK_P2 >= NS + NT_MAX && PK_P3 >= NS + NT_MAX, "P slots must be global-memory slots");
+
+template <int K>
+B381_DEV B381_INL void ark_bit_pk(const Ctx& cx, const MillerSlotsPK& s, int cur, int oth, bool square, bool add, const u4* const* line, const size_t* stride, int& idx) {
+  static_assert((K & 1) == 0, "even K: the bank after a bit does not depend on the bit");
+  if (square) {
+    f12_sqr_oop(cx, oth, cur, s.T, s.L);
+    const int sw = cur; cur = oth; oth = sw;
+  }
+  for (int pass = 0; pass < (add ? 2 : 1); pass++) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const u4* src = line[j] + stride[j] * idx;
+      if (idx + 1 < G2PREP_TRIPLES) prefetch_triple(src + stride[j]);
+      ark_ell_oop_ext(cx, oth, cur, src, s.L, s.P[j], pass == 0);
+      const int sw = cur; cur = oth; oth = sw;
+    }
+    idx++;
+  }
+}
+
+template <int K>
+B381_DEV void ark_miller_loop_pk(const Ctx& cx, const MillerSlotsPK& s, const u4* const* line, const size_t* stride) {
+  const uint64_t xabs = B381_X_ABS;
+  int idx = 0;
+  f12_set_one(cx, s.A);
+  ark_bit_pk<K>(cx, s, s.A, s.B, false, (xabs >> 62) & 1, line, stride, idx);        // no squaring of f = 1: the bank is kept
+  for (int b = 61; b >= 0; b -= 2) {
+    ark_bit_pk<K>(cx, s, s.A, s.B, true, (xabs >> b) & 1, line, stride, idx);
+    ark_bit_pk<K>(cx, s, s.B, s.A, true, (xabs >> (b - 1)) & 1, line, stride, idx);
+  }
+  f12_conj(cx, s.A);
+}
+
+// g1[j]: 24 words; pk[j]: first group of pair j's packed lines; inf[j] != 0: the pair contributes 1; one_line: this
+// thread's view of the constant line (1, 0, 0).  Leaves the product of the K Miller values in ML_F.
+B381_DEV B381_INL int miller_pk_to_slots(const Ctx& cx, const uint32_t* const* g1, const u4* const* pk, const int* inf, const u4* one_line) {
+  int err = 0;
+  MillerSlotsPK s;
+  s.A = PP_A; s.B = PP_B; s.L = PP_L; s.T = PP_T;
+  s.P[0] = PK_P0; s.P[1] = PK_P1; s.P[2] = PK_P2; s.P[3] = PK_P3;
+  const u4* line[PK_K];
+  size_t stride[PK_K];                             // uint4 distance between consecutive triples: 0 for the constant line
+  for (int j = 0; j < PK_K; j++) {
+    const bool ident = (inf[j] & 3) != 0;
+    if (ident) f2_set_small(S_(s.P[j]), 0);
+    else if (!f2_load_ext(S_(s.P[j]), g1[j])) err |= ERR_NOT_CANONICAL;
+    line[j] = ident ? one_line : pk[j];
+    stride[j] = ident ? 0 : (size_t)3 * SLOT;
+  }
+  ark_miller_loop_pk<PK_K>(cx, s, line, stride);
+  return err;
+}
+
+// the constant line (1, 0, 0) for this thread (stride 0: every triple index reads the same three slots)
+B381_DEV B381_INL void fill_one_line(u4* tile_lane) {
+  f2_set_small(tile_lane, 1);
+  f2_set_small(tile_lane + SLOT, 0);
+  f2_set_small(tile_lane + 2 * SLOT, 0);
+}
+
 // Fq12 / Fq6 inverse (witness helpers): /root/reference/src/fields/fq12_target.rs:340-374,
 // fq6_target.rs:384-418 run x.inverse() natively; formulas fq12_target_tree.rs:77-90, fq6_target_tree.rs:59-89
 B381_DEV B381_INL int prog_f12_inv(const Ctx& cx, const uint32_t* in, uint32_t* out) {
@@ -458,6 +636,91 @@ B381_DEV B381_INL int prog_g2_point_sum(const Ctx& cx, const uint32_t* in, const
   }
   jac_store_affine(cx, R, ZI, 1, out, out_inf);
   return err;
+}
+
+// ---- G2 bucket method (Pippenger) over the slot arena -----------------------------------------------------------
+// Same stages as the G1 pipeline (g1_kernels.cu; the digit histogram / scan / scatter kernels are shared, they never
+// look at a point): one thread per bucket sums its points, one thread per chunk of buckets forms the weighted chunk
+// sum by running sums, two levels of plain sums per window, Horner over the windows.  Intermediate points travel as
+// raw Jacobian triples: 3 slots x 24 words in the internal format.  Slot plan: Q 0..2, R 3..5, T 6..14 (jac_add's nine
+// scratch slots), R2 15..17, R3 18..20.
+constexpr int G2_RAW_JAC = 72;
+constexpr int GM_Q = 0, GM_R = 3, GM_T = 6, GM_R2 = 15, GM_R3 = 18;
+
+B381_DEV B381_INL void jac_store_raw(const Ctx& cx, uint32_t* dst, int R) {
+  for (int i = 0; i < 3; i++) {
+    Fp c0, c1;
+    ld_f2(c0, c1, S_(R + i));
+    B381_CHECK(c0.mag <= 4.2 && c1.mag <= 4.2, "raw Jacobian store: coordinate above the bound jac_load_raw claims");
+    for (int k = 0; k < SW; k++) { dst[24 * i + k] = (uint32_t)c0.l[k]; dst[24 * i + SW + k] = (uint32_t)c1.l[k]; }
+  }
+}
+B381_DEV B381_INL void jac_load_raw(const Ctx& cx, int R, const uint32_t* src) {
+  for (int i = 0; i < 3; i++) {
+    Fp c0, c1;
+    fp_zero(c0); fp_zero(c1);
+    for (int k = 0; k < SW; k++) { c0.l[k] = (limb_t)src[24 * i + k]; c1.l[k] = (limb_t)src[24 * i + SW + k]; }
+    B381_SETRANGE(c0, 0.0, 4.2); B381_SETRANGE(c1, 0.0, 4.2);     // outputs of jac_add / jac_double: Z = 2 Y Z < 4.2 p (checked at the store)
+    st_f2(S_(R + i), c0, c1);
+  }
+}
+B381_DEV B381_INL void jac_set_identity(const Ctx& cx, int R) {     // (1, 1, 0), ark-ec 0.4
+  f2_set_small(S_(R), 1); f2_set_small(S_(R + 1), 1); f2_set_small(S_(R + 2), 0);
+}
+
+// sum of the affine points pts[idx[lo .. hi)] (C-ABI layout, 48 words) -> raw Jacobian
+B381_DEV B381_INL int prog_g2_bucket_sum(const Ctx& cx, const uint32_t* pts, const uint32_t* idx, size_t lo, size_t hi, uint32_t* dst) {
+  int err = 0;
+  jac_set_identity(cx, GM_R);
+  for (size_t t = lo; t < hi; t++) {
+    err |= load_affine_point(cx, GM_Q, pts + (size_t)48 * idx[t], 1);
+    jac_add(cx, GM_R, GM_Q, GM_T);
+  }
+  jac_store_raw(cx, dst, GM_R);
+  return err;
+}
+
+// chunk [lo, hi) of one window's buckets: sum_{d in chunk} d B_d = running sums + (lo - 1) x (sum of the chunk)
+B381_DEV B381_INL void prog_g2_chunk_weighted(const Ctx& cx, const uint32_t* buckets, uint32_t lo, uint32_t hi, uint32_t* dst) {
+  jac_set_identity(cx, GM_R);                       // running sum
+  jac_set_identity(cx, GM_R2);                      // accumulated
+  for (uint32_t d = hi; d-- > lo;) {
+    jac_load_raw(cx, GM_Q, buckets + (size_t)G2_RAW_JAC * d);
+    jac_add(cx, GM_R, GM_Q, GM_T);
+    jac_add(cx, GM_R2, GM_R, GM_T);
+  }
+  const uint32_t m = lo - 1;
+  if (m != 0 && lo < hi) {
+    jac_set_identity(cx, GM_R3);
+    bool started = false;
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) jac_double(cx, GM_R3, GM_T);
+      if ((m >> bit) & 1u) { jac_add(cx, GM_R3, GM_R, GM_T); started = true; }
+    }
+    jac_add(cx, GM_R2, GM_R3, GM_T);
+  }
+  jac_store_raw(cx, dst, GM_R2);
+}
+
+// sum of the raw Jacobian points in[lo .. hi)
+B381_DEV B381_INL void prog_g2_jac_sum(const Ctx& cx, const uint32_t* in, size_t lo, size_t hi, uint32_t* dst) {
+  jac_set_identity(cx, GM_R);
+  for (size_t t = lo; t < hi; t++) {
+    jac_load_raw(cx, GM_Q, in + (size_t)G2_RAW_JAC * t);
+    jac_add(cx, GM_R, GM_Q, GM_T);
+  }
+  jac_store_raw(cx, dst, GM_R);
+}
+
+// Horner over the W window sums (c doublings per window) and conversion to affine
+B381_DEV B381_INL void prog_g2_msm_final(const Ctx& cx, const uint32_t* sums, int W, int c, uint32_t* out48, uint8_t* out_inf) {
+  jac_load_raw(cx, GM_R, sums + (size_t)G2_RAW_JAC * (W - 1));
+  for (int w = W - 2; w >= 0; w--) {
+    for (int i = 0; i < c; i++) jac_double(cx, GM_R, GM_T);
+    jac_load_raw(cx, GM_Q, sums + (size_t)G2_RAW_JAC * w);
+    jac_add(cx, GM_R, GM_Q, GM_T);
+  }
+  jac_store_affine(cx, GM_R, GM_R2, 1, out48, out_inf);
 }
 
 // ark g2.rs clear_cofactor (Budroni-Pintore, eprint 2017/419 section 4.1):

@@ -1309,6 +1309,22 @@ B381_DEV B381_INL void ark_ell_oop(const Ctx& cx, int d, int f, int L, int Pt, i
   f12_mul_by_014_oop(cx, d, f, L, L + 1, L + 2);
 }
 
+// The same against a line held OUTSIDE the arena (packed G2Prepared, programs.cuh): `line` points at three consecutive
+// slot-shaped values (i, 3j, h).  c1 / c2 are scaled by px / py on their way into the arena slots L + 1, L + 2; c0 is
+// read in place by the six sums of products (one cold read, then L1 / L2 hits).
+B381_DEV B381_INL void ark_ell_oop_ext(const Ctx& cx, int d, int f, const u4* line, int L, int Pt, int neg2) {
+  sync_point(cx);
+  f2_mulfp(S_(L + 2), line + 2 * SLOT, S_(Pt), 1, neg2);
+  f2_mulfp(S_(L + 1), line + SLOT, S_(Pt), 0);
+  const int a0 = f, a1 = f + 1, a2 = f + 2, b0 = f + 3, b1 = f + 4, b2 = f + 5, c1 = L + 1, c4 = L + 2;
+  sync_point(cx); f2_sop(S_(d + 0), SOP_XI1 | SOP_XI2, S_(a0), line, S_(a2), S_(c1), S_(b1), S_(c4));
+  sync_point(cx); f2_sop(S_(d + 1), SOP_XI2, S_(a0), S_(c1), S_(a1), line, S_(b2), S_(c4));
+  sync_point(cx); f2_sop(S_(d + 2), 0, S_(a1), S_(c1), S_(a2), line, S_(b0), S_(c4));
+  sync_point(cx); f2_sop(S_(d + 3), SOP_XI1 | SOP_XI2, S_(b0), line, S_(b2), S_(c1), S_(a2), S_(c4));
+  sync_point(cx); f2_sop(S_(d + 4), 0, S_(b0), S_(c1), S_(b1), line, S_(a0), S_(c4));
+  sync_point(cx); f2_sop(S_(d + 5), 0, S_(b1), S_(c1), S_(b2), line, S_(a1), S_(c4));
+}
+
 // slot plan shared by the Miller-loop kernels
 struct MillerSlots { int f, L, T, R, Q, P; };
 // Ping-pong plan of the ARK loops: f alternates between the banks A and B (every squaring and every line

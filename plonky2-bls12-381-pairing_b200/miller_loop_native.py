@@ -138,3 +138,49 @@ def pairing_prepared_batch(terms: Sequence[Tuple[G1Affine, G2Prepared]]) -> List
     lib = _lib.lib()
     _lib.check(lib.b381_pairing_prepared(_lib.u32(g1)[1], _lib.u32(co)[1], _lib.u8(inf)[1], _lib.u32(out)[1], n, mode))
     return [Fq12.from_limbs(out[144 * i:144 * i + 144]) for i in range(n)]
+
+
+class G2PreparedBatch:
+    """A batch of prepared Q's kept ON THE DEVICE in the library's packed layout (include/b381.h
+    b381_g2_prepare_packed_dev): the cached stage for callers that pair many P's against the same Q's.
+    Opaque: valid for this library build, this mode and this GPU context only."""
+
+    def __init__(self, qs: Sequence[G2Affine], mode: int = MODE_ARK):
+        import torch
+        n = len(qs)
+        if n == 0:
+            raise ValueError("empty batch")
+        self.n, self.mode = n, mode
+        self.q_infinity = np.array([2 if q.infinity else 0 for q in qs], dtype=np.uint8)
+        gen = G2Affine.generator().limbs()
+        g2 = np.array([gen if q.infinity else q.limbs() for q in qs], dtype=np.uint32).reshape(-1)
+        lib = _lib.lib()
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+        d2 = torch.from_numpy(g2.view(np.int32)).to(self._dev)
+        self.packed = torch.empty(lib.b381_g2_packed_words(n), dtype=torch.int32, device=self._dev)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.b381_g2_prepare_packed_dev(d2.data_ptr(), self.packed.data_ptr(), n, mode, st))
+        _lib.check(lib.b381_check_dev(st))
+
+    def _run(self, ps: Sequence[G1Affine], final_exp: int) -> np.ndarray:
+        import torch
+        if len(ps) != self.n:
+            raise ValueError("one P per prepared Q")
+        lib = _lib.lib()
+        g1 = np.array([p.limbs() for p in ps], dtype=np.uint32).reshape(-1)
+        inf = self.q_infinity | np.array([1 if p.infinity else 0 for p in ps], dtype=np.uint8)
+        d1 = torch.from_numpy(g1.view(np.int32)).to(self._dev)
+        dinf = torch.from_numpy(inf).to(self._dev)
+        out = torch.empty(self.n * 144, dtype=torch.int32, device=self._dev)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.b381_miller_loop_packed_dev(d1.data_ptr(), self.packed.data_ptr(), dinf.data_ptr(), out.data_ptr(), self.n, self.mode, final_exp, st))
+        _lib.check(lib.b381_check_dev(st))
+        return out.cpu().numpy().view(np.uint32)
+
+    def miller_loop(self, ps: Sequence[G1Affine]) -> List[MillerLoopResult]:
+        out = self._run(ps, 0)
+        return [MillerLoopResult(Fq12.from_limbs(out[144 * i:144 * i + 144])) for i in range(self.n)]
+
+    def pairing(self, ps: Sequence[G1Affine]) -> List[Fq12]:
+        out = self._run(ps, 1)
+        return [Fq12.from_limbs(out[144 * i:144 * i + 144]) for i in range(self.n)]

@@ -140,6 +140,37 @@ int hs_miller_prepared(const uint32_t* g1, const uint32_t* coeffs, int inf, uint
   return prog_miller_prepared(cx, g1, coeffs, inf, out, mode, do_fe);
 }
 
+// packed G2Prepared (internal format; on the host a tile is one point: 68 x 3 slots of 6 uint4 = 4896 words)
+int hs_g2_prepare_packed(const uint32_t* g2, uint32_t* packed, int mode) { Ctx cx = make_ctx(); return prog_g2_prepare_packed(cx, g2, reinterpret_cast<u4*>(packed), mode); }
+int hs_miller_packed(const uint32_t* g1, const uint32_t* packed, int inf, uint32_t* out, int mode, int do_fe) {
+  Ctx cx = make_ctx();
+  return prog_miller_packed(cx, g1, reinterpret_cast<const u4*>(packed), inf, out, mode, do_fe);
+}
+
+// product of n Miller values against packed prepared Q's, four pairs at a time (the k_multi_miller_packed path);
+// packed: n host tiles of 4896 words
+int hs_multi_miller_packed(const uint32_t* g1, const uint32_t* packed, const uint8_t* inf, size_t n, uint32_t* out) {
+  Ctx cx = make_ctx();
+  alignas(16) static u4 one_line[3 * GPS];
+  fill_one_line(one_line);
+  int err = 0;
+  f12_set_one(cx, M2_ACC);
+  for (size_t i = 0; i < n; i += PK_K) {
+    const uint32_t* pg1[PK_K]; const u4* ppk[PK_K]; int pinf[PK_K];
+    for (int j = 0; j < PK_K; j++) {
+      const bool act = i + j < n;
+      const size_t k = act ? i + j : n - 1;
+      pg1[j] = g1 + 24 * k;
+      ppk[j] = reinterpret_cast<const u4*>(packed) + g2pack_index(k);
+      pinf[j] = act ? (inf ? inf[k] : 0) : 3;
+    }
+    err |= miller_pk_to_slots(cx, pg1, ppk, pinf, one_line);
+    f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);
+  }
+  f12_store_ext(cx, out, M2_ACC);
+  return err;
+}
+
 int hs_fp_inv(const uint32_t* a, uint32_t* out) { return prog_fp_inv(a, out); }
 int hs_fp_pow(const uint32_t* a, const uint32_t* e, int nwords, uint32_t* out) { return prog_fp_pow(a, e, nwords, out); }
 int hs_fp_is_square(const uint32_t* a, uint8_t* out) { return prog_fp_is_square(a, out); }
@@ -220,6 +251,40 @@ int hs_g1_msm(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, 
   G1J r;
   msm_combine_windows(r, sums.data(), W, c);
   g1_store_jac_ext(out24, out_inf, r);
+  return err;
+}
+
+// the G2 bucket method exactly as the kernels stage it (k_msm_digits x 2, k_msm_scan, k_g2_msm_bucket_sums, k_g2_msm_chunks,
+// k_g2_jac_sums, k_g2_msm_final), run sequentially on the host
+int hs_g2_msm(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, size_t n, int c, int CH, uint32_t* out48, uint8_t* out_inf) {
+  Ctx cx = make_ctx();
+  int err = 0;
+  const int W = (256 + c - 1) / c;
+  const uint32_t B = 1u << c;
+  const size_t m = (size_t)W * B;
+  std::vector<unsigned int> cnt(m, 0), start(m + 1, 0), cursor(m, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (inf && (inf[i] & 1)) continue;
+    for (int w = 0; w < W; w++) { uint32_t d = msm_digit(scalars + 8 * i, w, c); if (d) cnt[(size_t)w * B + d]++; }
+  }
+  for (size_t b = 0; b < m; b++) { start[b + 1] = start[b] + cnt[b]; cursor[b] = start[b]; }
+  std::vector<uint32_t> idx(start[m] ? start[m] : 1);
+  for (size_t i = 0; i < n; i++) {
+    if (inf && (inf[i] & 1)) continue;
+    for (int w = 0; w < W; w++) { uint32_t d = msm_digit(scalars + 8 * i, w, c); if (d) idx[cursor[(size_t)w * B + d]++] = (uint32_t)i; }
+  }
+  std::vector<uint32_t> buckets(m * G2_RAW_JAC);
+  for (size_t b = 0; b < m; b++) err |= prog_g2_bucket_sum(cx, pts, idx.data(), start[b], start[b + 1], buckets.data() + G2_RAW_JAC * b);
+  const uint32_t nchunk = (B + CH - 1) / CH;
+  std::vector<uint32_t> partial((size_t)W * nchunk * G2_RAW_JAC), sums((size_t)W * G2_RAW_JAC);
+  for (int w = 0; w < W; w++)
+    for (uint32_t j = 0; j < nchunk; j++) {
+      uint32_t lo = j * CH, hi = lo + CH < B ? lo + CH : B;
+      if (lo == 0) lo = 1;
+      prog_g2_chunk_weighted(cx, buckets.data() + (size_t)G2_RAW_JAC * w * B, lo, hi, partial.data() + G2_RAW_JAC * ((size_t)w * nchunk + j));
+    }
+  for (int w = 0; w < W; w++) prog_g2_jac_sum(cx, partial.data(), (size_t)w * nchunk, (size_t)(w + 1) * nchunk, sums.data() + G2_RAW_JAC * w);
+  prog_g2_msm_final(cx, sums.data(), W, c, out48, out_inf);
   return err;
 }
 

@@ -93,6 +93,17 @@ def test_distinct_pairs_2p16_full_compare(L, lib):
     o2 = np.zeros(m * 144, dtype=np.uint32)
     L.check(lib.b381_miller_loop_prepared(L.u32(p[:24 * m])[1], L.u32(co)[1], None, L.u32(o2)[1], m, L.MODE_ARK))
     assert np.array_equal(o2, out[:144 * m])
+    # packed (internal-format) prepared stage on ALL 2^16 distinct pairs, device-resident
+    import torch
+    dev = torch.device("cuda:0"); st = torch.cuda.current_stream().cuda_stream
+    dp = torch.from_numpy(p.view(np.int32)).to(dev); dq = torch.from_numpy(q.view(np.int32)).to(dev)
+    pk = torch.empty(lib.b381_g2_packed_words(n), dtype=torch.int32, device=dev)
+    dout = torch.empty(n * 144, dtype=torch.int32, device=dev)
+    L.check(lib.b381_g2_prepare_packed_dev(dq.data_ptr(), pk.data_ptr(), n, L.MODE_ARK, st))
+    L.check(lib.b381_miller_loop_packed_dev(dp.data_ptr(), pk.data_ptr(), None, dout.data_ptr(), n, L.MODE_ARK, 0, st))
+    L.check(lib.b381_check_dev(st))
+    assert np.array_equal(dout.cpu().numpy().view(np.uint32), out), "packed prepared Miller loop differs from the unprepared one"
+    del dp, dq, pk, dout
     o144 = np.zeros(144, dtype=np.uint32); c144 = np.zeros(144, dtype=np.uint32)
     L.check(lib.b381_multi_miller_loop(L.u32(p)[1], L.u32(q)[1], None, L.u32(o144)[1], n, L.MODE_ARK))
     assert ref.ref_multi_miller_loop(util.p32(p), util.p32(q), None, util.p32(c144), n, threads) == 0

@@ -176,6 +176,37 @@ def test_g2_sum_and_msm(L, lib, z):
     assert f[0] == 1
 
 
+@pytest.mark.parametrize("logn", [8, 12, 17])
+def test_g2_bucket_msm_against_identity(L, lib, logn):
+    """G2 bucket method (n >= 256; window 4 / 8 / 16 bits): sum_i [k_i] (a_i G2) == [sum a_i k_i mod r] G2 with DISTINCT
+    device-generated points and random 256-bit scalars; identity flags and zero scalars drop out; repeated points and
+    P, -P with equal scalars meet inside buckets."""
+    n = 1 << logn
+    rng = np.random.default_rng(0xA00 + logn)
+    a = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    a[:, 7] &= 0x3FFFFFFF; a[:, 0] |= 1
+    a[11] = a[10]                                                  # the same point twice ...
+    g2 = np.tile(np.array(o.g2_to_limbs32(o.G2_GEN), dtype=np.uint32), n)
+    p = np.zeros(n * 48, dtype=np.uint32); f = np.zeros(n, dtype=np.uint8)
+    L.check(lib.b381_g2_scalar_mul(L.u32(g2)[1], None, L.u32(a.reshape(-1))[1], L.u32(p)[1], u8(f), n))
+    assert f.sum() == 0
+    k = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    k[11] = k[10]                                                  # ... with the same scalar: doubling inside every bucket it hits
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[3] = 1
+    k[5] = 0
+    ai, ki = _ints(a), _ints(k)
+    ai[21] = o.R_ORDER - ai[20]                                    # P_21 = -P_20 with equal scalars: the buckets cancel
+    pm = p.reshape(n, 48)
+    q20 = (util.f2_from_words(pm[20][:24].tolist()), util.f2_from_words(pm[20][24:].tolist()))
+    pm[21] = np.array(o.g2_to_limbs32(o.g2_neg(q20)), dtype=np.uint32)
+    k[21] = k[20]; ki[21] = ki[20]
+    tot = sum(x * y for i, (x, y) in enumerate(zip(ai, ki)) if i != 3) % o.R_ORDER
+    out = np.zeros(48, dtype=np.uint32); fo = np.zeros(1, dtype=np.uint8)
+    L.check(lib.b381_g2_msm(L.u32(p)[1], u8(inf), L.u32(k.reshape(-1))[1], L.u32(out)[1], u8(fo), n))
+    assert fo[0] == 0 and out.tolist() == o.g2_to_limbs32(o.g2_mul(o.G2_GEN, tot))
+
+
 def test_two_contexts_from_two_threads(L, lib, z):
     """b381_ctx_create / b381_ctx_set_current: two contexts (on the same GPU here: the box has one) driven by two
     host threads at the same time give the fixture values; the default context stays usable."""

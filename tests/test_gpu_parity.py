@@ -377,6 +377,10 @@ def test_python_host_api(L):
     qp = G2Prepared.from_affine(Q)
     assert miller_loop_prepared_batch([(P, qp)])[0].f == res.f
     assert pairing_prepared_batch([(P, qp), (G1Affine.identity(), qp)]) == [res.final_exponentiation(), Fq12.one()]
+    from b381.miller_loop_native import G2PreparedBatch
+    qb = G2PreparedBatch([Q, Q])
+    assert qb.miller_loop([P, P])[1].f == res.f
+    assert qb.pairing([P, G1Affine.identity()]) == [res.final_exponentiation(), Fq12.one()]
     from b381.fields import helpers as H
     from b381.fields.types import Fq, Fq2
     xs = [Fq(3), Fq(4), Fq(o.P - 1)]
@@ -679,3 +683,99 @@ def test_point_sum_and_msm(L, lib, z):
     sc2 = np.array([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for v in (k, o.R_ORDER - k)], dtype=np.uint32).reshape(-1)
     L.check(lib.b381_g1_msm(L.u32(g1[:48])[1], None, L.u32(sc2)[1], L.u32(o1)[1], u8(f), 2))
     assert f[0] == 1
+
+
+@pytest.mark.gpu
+def test_g2_packed_stage(L, lib, z):
+    """b381_g2_prepare_packed_dev / b381_miller_loop_packed_dev (G2Prepared in the internal, tile-interleaved layout):
+    values equal the golden fixture of the unprepared path bit for bit, at ragged sizes around the tile (256), the
+    half-round (148 x 128) and the round (148 x 256) boundaries, in both modes, with identity flags, with final exp."""
+    import torch
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(77)
+    assert lib.b381_g2_packed_words(1) == 256 * L.G2PREP_WORDS and lib.b381_g2_packed_words(257) == 512 * L.G2PREP_WORDS
+    for n in (1, 255, 257, sm * 128 + 3, sm * 256 + 129):
+        idx = rng.integers(0, 256, size=n)
+        g1 = torch.from_numpy(np.ascontiguousarray(z["g1"][idx]).reshape(-1).view(np.int32)).to(dev)
+        g2 = torch.from_numpy(np.ascontiguousarray(z["g2"][idx]).reshape(-1).view(np.int32)).to(dev)
+        pk = torch.empty(lib.b381_g2_packed_words(n), dtype=torch.int32, device=dev)
+        out = torch.empty(n * 144, dtype=torch.int32, device=dev)
+        for mode in ((L.MODE_ARK, L.MODE_ZK) if n < 1000 else (L.MODE_ARK,)):
+            L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr(), n, mode, st))
+            L.check(lib.b381_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), None, out.data_ptr(), n, mode, 0, st))
+            L.check(lib.b381_check_dev(st))
+            got = out.cpu().numpy().view(np.uint32).reshape(n, 144)
+            if mode == L.MODE_ARK:
+                assert np.array_equal(got, z["miller_ark"][idx]), n
+            else:
+                ref = torch.empty_like(out)
+                L.check(lib.b381_miller_loop_dev(g1.data_ptr(), g2.data_ptr(), None, ref.data_ptr(), n, mode, st))
+                L.check(lib.b381_check_dev(st))
+                assert torch.equal(out, ref), n
+            L.check(lib.b381_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), None, out.data_ptr(), n, mode, 1, st))
+            L.check(lib.b381_check_dev(st))
+            assert np.array_equal(out.cpu().numpy().view(np.uint32).reshape(n, 144), z["pairing"][idx]), (n, mode)
+        if n == 257:
+            inf = rng.integers(0, 4, size=n).astype(np.uint8)
+            dinf = torch.from_numpy(inf).to(dev)
+            L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr(), n, L.MODE_ARK, st))     # pk held the ZK-mode lines
+            L.check(lib.b381_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), dinf.data_ptr(), out.data_ptr(), n, L.MODE_ARK, 1, st))
+            L.check(lib.b381_check_dev(st))
+            got = out.cpu().numpy().view(np.uint32).reshape(n, 144)
+            one = np.array(o.f12_to_limbs32(o.F12_ONE), dtype=np.uint32)
+            for i in range(n):
+                assert np.array_equal(got[i], one if inf[i] else z["pairing"][idx[i]]), i
+    # argument checks: null / misaligned buffer, LITERAL mode
+    assert lib.b381_g2_prepare_packed_dev(g2.data_ptr(), None, 1, L.MODE_ARK, st) == -2
+    assert lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr() + 4, 1, L.MODE_ARK, st) == -2
+    assert lib.b381_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), None, out.data_ptr(), 1, L.MODE_LITERAL, 0, st) == -2
+
+
+@pytest.mark.gpu
+def test_multi_miller_packed(L, lib, z):
+    """b381_multi_miller_loop_packed_dev (four pairs per thread, shared squarings, lines from the packed stage) equals
+    b381_multi_miller_loop_dev on the same pairs: ragged sizes (partly filled groups of four tiles, several launches with
+    accumulation), identity flags; with the final exponentiation a batch made of (P_i, Q_i), (-P_i, Q_i) gives one."""
+    import torch
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(78)
+    for n in (1, 3, 257, 1025, 4 * sm * 256 + 777):
+        idx = rng.integers(0, 256, size=n)
+        g1 = torch.from_numpy(np.ascontiguousarray(z["g1"][idx]).reshape(-1).view(np.int32)).to(dev)
+        g2 = torch.from_numpy(np.ascontiguousarray(z["g2"][idx]).reshape(-1).view(np.int32)).to(dev)
+        pk = torch.empty(lib.b381_g2_packed_words(n), dtype=torch.int32, device=dev)
+        L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr(), n, L.MODE_ARK, st))
+        a = torch.empty(144, dtype=torch.int32, device=dev); b = torch.empty(144, dtype=torch.int32, device=dev)
+        for inf in (None, rng.integers(0, 4, size=n).astype(np.uint8) * (rng.integers(0, 3, size=n) == 0)):
+            dinf = None if inf is None else torch.from_numpy(inf.astype(np.uint8)).to(dev)
+            ip = None if inf is None else dinf.data_ptr()
+            L.check(lib.b381_multi_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), ip, a.data_ptr(), n, 0, st))
+            L.check(lib.b381_multi_miller_loop_dev(g1.data_ptr(), g2.data_ptr(), ip, b.data_ptr(), n, L.MODE_ARK, st))
+            L.check(lib.b381_check_dev(st))
+            assert torch.equal(a, b), (n, inf is None)
+            if n == 3 and inf is None:
+                want = o.F12_ONE
+                for i in idx:
+                    want = o.f12_mul(want, o.f12_from_limbs32(z["miller_ark"][i]))
+                assert o.f12_eq(o.f12_from_limbs32(a.cpu().numpy().view(np.uint32).tolist()), want)
+    # BLS shape: product of e(P_i, Q_i) e(-P_i, Q_i) = 1
+    n = 2048
+    idx = rng.integers(0, 256, size=n // 2)
+    h1 = np.ascontiguousarray(z["g1"][idx]).copy()
+    neg = h1.copy()
+    for i in range(n // 2):
+        y = o.fp_from_limbs32(h1[i][12:].tolist())
+        neg[i][12:] = o.fp_to_limbs32((o.P - y) % o.P)
+    g1 = torch.from_numpy(np.concatenate([h1, neg]).reshape(-1).view(np.int32)).to(dev)
+    g2 = torch.from_numpy(np.ascontiguousarray(np.concatenate([z["g2"][idx], z["g2"][idx]])).reshape(-1).view(np.int32)).to(dev)
+    pk = torch.empty(lib.b381_g2_packed_words(n), dtype=torch.int32, device=dev)
+    L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr(), n, L.MODE_ARK, st))
+    a = torch.empty(144, dtype=torch.int32, device=dev)
+    L.check(lib.b381_multi_miller_loop_packed_dev(g1.data_ptr(), pk.data_ptr(), None, a.data_ptr(), n, 1, st))
+    L.check(lib.b381_check_dev(st))
+    assert a.cpu().numpy().view(np.uint32).tolist() == o.f12_to_limbs32(o.F12_ONE)
+    assert lib.b381_multi_miller_loop_packed_dev(g1.data_ptr(), None, None, a.data_ptr(), n, 1, st) == -2

@@ -163,6 +163,56 @@ def test_multi_miller_and_literal(hs):
     assert hs.hs_literal(A(g1p), A(sum((util.f2_words(x) for x in qinf), [])), out) == 2
 
 
+def test_g2_packed_stage(hs):
+    """G2Prepared in the packed (internal-format) layout: the Miller loop / pairing over it equals the on-the-fly
+    loop and the golden fixture; identity flags give one."""
+    import numpy as np
+    z = util.pairs_256()
+    for i in (0, 11):
+        g1, g2 = A(z["g1"][i]), A(z["g2"][i])
+        for mode in (0, 1):
+            buf = np.zeros(68 * 72 + 4, dtype=np.uint32)
+            off = (-buf.ctypes.data // 4) % 4                   # 16-byte alignment of the uint4 view
+            pk = buf[off:off + 68 * 72]
+            pkp = pk.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+            assert hs.hs_g2_prepare_packed(g2, pkp, mode) == 0
+            out, ref = u(144), u(144)
+            assert hs.hs_miller_packed(g1, pkp, 0, out, mode, 0) == 0
+            assert hs.hs_miller_loop(g1, g2, 0, ref, mode) == 0
+            assert list(out) == list(ref), (i, mode)
+            if mode == 0:
+                assert list(out) == list(z["miller_ark"][i])
+            assert hs.hs_miller_packed(g1, pkp, 0, out, mode, 1) == 0 and list(out) == list(z["pairing"][i])
+            one = o.f12_to_limbs32(o.F12_ONE)
+            for inf in (1, 2, 3):
+                assert hs.hs_miller_packed(g1, pkp, inf, out, mode, 0) == 0 and list(out) == one
+
+
+def test_multi_miller_packed(hs):
+    """four pairs per thread against packed prepared Q's with shared squarings: the product equals the product of the
+    golden Miller values; identity flags and a count that is not a multiple of four (padding pairs contribute 1)."""
+    import numpy as np
+    z = util.pairs_256()
+    n = 6
+    buf = np.zeros(n * 68 * 72 + 4, dtype=np.uint32)
+    off = (-buf.ctypes.data // 4) % 4
+    pk = buf[off:off + n * 68 * 72]
+    for i in range(n):
+        pki = pk[68 * 72 * i:].ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        assert hs.hs_g2_prepare_packed(A(z["g2"][i]), pki, 0) == 0
+    pkp = pk.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    g1 = A(np.ascontiguousarray(z["g1"][:n]).reshape(-1))
+    out = u(144)
+    for inf in (None, (0, 1, 2, 0, 3, 0)):
+        want = o.F12_ONE
+        for i in range(n):
+            if inf is None or inf[i] == 0:
+                want = o.f12_mul(want, o.f12_from_limbs32(z["miller_ark"][i]))
+        cinf = None if inf is None else (ctypes.c_uint8 * n)(*inf)
+        assert hs.hs_multi_miller_packed(g1, pkp, cinf, ctypes.c_size_t(n), out) == 0
+        assert o.f12_eq(o.f12_from_limbs32(list(out)), want), inf
+
+
 def _triples_words(co):
     return sum((util.f2_words(c) for t in co for c in t), [])
 
@@ -459,6 +509,31 @@ def test_g1_bucket_msm(hs):
         out = u(24)
         assert hs.hs_g1_msm(A(words), (ctypes.c_uint8 * n)(*inf), A(sc), ctypes.c_size_t(n), c, ch, out, f) == 0
         assert (f[0] == 1 and want is None) or (f[0] == 0 and list(out) == o.g1_to_limbs32(want)), (n, c, ch)
+
+
+def test_g2_bucket_msm(hs):
+    """the G2 bucket method staged as on the device, against the oracle: the cases of test_g1_bucket_msm over Fq2."""
+    r = util.rng(39)
+    f = (ctypes.c_uint8 * 1)()
+    for n, c, ch in ((1, 4, 4), (9, 3, 2), (24, 5, 8)):
+        ks = [r.randrange(0, 1 << 256) for _ in range(n)]
+        pts = [o.g2_mul(o.G2_GEN, r.randrange(1, o.R_ORDER)) for _ in range(n)]
+        inf = [0] * n
+        if n >= 9:
+            pts[3] = pts[2]; ks[3] = ks[2]
+            pts[5] = o.g2_neg(pts[4]); ks[5] = ks[4]
+            ks[6] = 0
+            inf[7] = 1
+            ks[8] = (1 << 256) - 1
+        want = None
+        for p_, k_, i_ in zip(pts, ks, inf):
+            if not i_:
+                want = o.g2_add(want, o.g2_mul(p_, k_))
+        words = sum((o.g2_to_limbs32(p_) for p_ in pts), [])
+        sc = sum(([(k_ >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for k_ in ks), [])
+        out = u(48)
+        assert hs.hs_g2_msm(A(words), (ctypes.c_uint8 * n)(*inf), A(sc), ctypes.c_size_t(n), c, ch, out, f) == 0
+        assert (f[0] == 1 and want is None) or (f[0] == 0 and list(out) == o.g2_to_limbs32(want)), (n, c, ch)
 
 
 def test_literal_vertical_line_branch(hs):
