@@ -31,6 +31,15 @@ if what in ("all", "miller"):
     L.check(lib.b381_g2_prepare_dev(d2.data_ptr(), co.data_ptr(), n, 0, st))
     L.check(lib.b381_miller_loop_prepared_dev(d1.data_ptr(), co.data_ptr(), None, dout.data_ptr(), n, 0, 0, st))
     L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, dout.data_ptr(), 2 * n, 0, st))
+if what in ("all", "packed"):
+    n4 = 4 * n // 2                                  # one round of the four-pairs-per-thread multi loop
+    pk = torch.empty(lib.b381_g2_packed_words(n4), dtype=torch.int32, device="cuda")
+    L.check(lib.b381_g2_prepare_packed_dev(d2.data_ptr(), pk.data_ptr(), n4, 0, st))
+    L.check(lib.b381_miller_loop_packed_dev(d1.data_ptr(), pk.data_ptr(), None, dout.data_ptr(), n, 0, 0, st))
+    L.check(lib.b381_multi_miller_loop_packed_dev(d1.data_ptr(), pk.data_ptr(), None, dout.data_ptr(), n4, 0, st))
+    sc = torch.randint(-(1 << 31), (1 << 31) - 1, ((1 << 20) * 8,), dtype=torch.int32, device="cuda")
+    r2 = torch.empty(48, dtype=torch.int32, device="cuda"); rf2 = torch.empty(1, dtype=torch.uint8, device="cuda")
+    L.check(lib.b381_g2_msm_dev(d2.data_ptr(), None, sc.data_ptr(), r2.data_ptr(), rf2.data_ptr(), 1 << 20, st))
 if what in ("all", "groups"):
     nn = 1 << 20
     sc = torch.randint(-(1 << 31), (1 << 31) - 1, (nn * 8,), dtype=torch.int32, device="cuda")
