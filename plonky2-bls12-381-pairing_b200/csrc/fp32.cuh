@@ -716,6 +716,26 @@ B381_HD B381_INL void fp_to_ext(uint32_t (&w)[12], const Fp& a) {
   fp_pack32(w, o);
 }
 
+// The external words taken AS the stored value (no multiplication): the element is then off by the fixed factor
+// 2^-32 (R = 2^384 against R' = 2^416).  For a bilinear map of two such operands the result is off by 2^-64 and
+// fp_to_ext_unscale puts it right with ONE multiplication: stored x~ -> x~ * 2^448 / R' = x~ * 2^32 ... applied to the
+// stored product (a 2^-32)(b 2^-32) R' = a b 2^352 it gives a b 2^384 = the external form of a b.
+B381_HD B381_INL bool fp_from_ext_asis(Fp& r, const uint32_t (&w)[12]) {
+  fp_unpack32(r, w);
+  const bool ok = fp_below_p(r);
+  B381_SETRANGE(r, 0.0, 1.0);
+  return ok;
+}
+B381_HD B381_INL void fp_to_ext_unscale(uint32_t (&w)[12], const Fp& a) {
+  const uint32_t cin[NL] = B381_CIN;              // 2^448 mod p
+  Fp c, o;
+  fp_set(c, cin);
+  B381_CHECK(a.mag < MUL_MAG_MAX, "fp_to_ext_unscale: magnitude");
+  fp_mul(o, a, c);
+  fp_canon_small(o);
+  fp_pack32(w, o);
+}
+
 // ---------------------------------------------------------------------------------------------
 // modular inversion: Bernstein-Yang "safegcd" division steps (constant control flow, no multiplications
 // in the inner loop).  The stored value v = A R' is made canonical, then (f, g) = (p, v) runs through

@@ -467,47 +467,39 @@ B381_DEV B381_INL void prog_f12_product_raw(const Ctx& cx, const uint32_t* in, s
   f12_store_raw(cx, out, 0);
 }
 
-// tower-order Fp12 multiply on external buffers (config #2 microbench, b381_fp12_mul)
+// tower-order Fp12 multiply on external buffers (config #2 microbench, b381_fp12_mul).  The operands are used as
+// they are and the product is put right on the way out (fp32.cuh fp_from_ext_asis): 12 conversions instead of 36.
 B381_DEV B381_INL int prog_f12_mul(const Ctx& cx, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   int err = 0;
-  if (!f12_load_ext(cx, 0, a)) err |= ERR_NOT_CANONICAL;
-  if (!f12_load_ext(cx, 6, b)) err |= ERR_NOT_CANONICAL;
+  for (int i = 0; i < 6; i++) {
+    if (!f2_load_asis2(S_(i), a + 24 * i, a + 24 * i + 12)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_asis2(S_(6 + i), b + 24 * i, b + 24 * i + 12)) err |= ERR_NOT_CANONICAL;
+  }
   f12_mul(cx, 0, 0, 6, 12, 18);
-  f12_store_ext(cx, out, 0);
+  for (int i = 0; i < 6; i++) f2_store_unscale2(out + 24 * i, out + 24 * i + 12, S_(i));
   return err;
 }
 
 // MyFq12 (w-basis) multiply: /root/reference/src/fields/helpers.rs:90-152.  The reference's
 // schoolbook formula and the tower product are the same field element (its own test
-// helpers.rs:248-267 asserts it), so the product is computed in the tower and permuted with the
-// coefficient map of helpers.rs:39-41: wbasis index -> (tower slot, half).
-B381_DEV B381_INL void wbasis_map(int idx, int& slot_i, int& half) {
-  // coeffs = [c000,c100,c010,c110,c020,c120, c001,c101,c011,c111,c021,c121]; c_ijk: i = Fp6 half, j = Fp2 idx, k = u
-  const int w = idx % 6;          // power of w: i = w & 1, j = w >> 1
-  half = idx / 6;
-  slot_i = 3 * (w & 1) + (w >> 1);
-}
-
+// helpers.rs:248-267 asserts it), so the product is computed in the tower; the coefficient map of
+// helpers.rs:39-41 only decides where each half of a tower slot is read and written:
+// coeffs = [c000,c100,c010,c110,c020,c120, c001,c101,c011,c111,c021,c121]; c_ijk: i = Fp6 half, j = Fp2 idx, k = u,
+// so tower slot 3 i + j has its two halves at w-basis indices 2 j + i and 6 + 2 j + i.
 B381_DEV B381_INL int prog_wbasis_mul(const Ctx& cx, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   int err = 0;
-  uint32_t ta[144], tb[144];
-  for (int idx = 0; idx < 12; idx++) {
-    int s, h;
-    wbasis_map(idx, s, h);
-    for (int k = 0; k < 12; k++) {
-      ta[24 * s + 12 * h + k] = a[12 * idx + k];
-      tb[24 * s + 12 * h + k] = b[12 * idx + k];
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++) {
+      const int s = 3 * i + j, w = 2 * j + i;
+      if (!f2_load_asis2(S_(s), a + 12 * w, a + 12 * (6 + w))) err |= ERR_NOT_CANONICAL;
+      if (!f2_load_asis2(S_(6 + s), b + 12 * w, b + 12 * (6 + w))) err |= ERR_NOT_CANONICAL;
     }
-  }
-  if (!f12_load_ext(cx, 0, ta)) err |= ERR_NOT_CANONICAL;
-  if (!f12_load_ext(cx, 6, tb)) err |= ERR_NOT_CANONICAL;
   f12_mul(cx, 0, 0, 6, 12, 18);
-  f12_store_ext(cx, ta, 0);
-  for (int idx = 0; idx < 12; idx++) {
-    int s, h;
-    wbasis_map(idx, s, h);
-    for (int k = 0; k < 12; k++) out[12 * idx + k] = ta[24 * s + 12 * h + k];
-  }
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++) {
+      const int s = 3 * i + j, w = 2 * j + i;
+      f2_store_unscale2(out + 12 * w, out + 12 * (6 + w), S_(s));
+    }
   return err;
 }
 
@@ -673,8 +665,10 @@ B381_DEV B381_INL int prog_g2_bucket_sum(const Ctx& cx, const uint32_t* pts, con
   int err = 0;
   jac_set_identity(cx, GM_R);
   for (size_t t = lo; t < hi; t++) {
-    err |= load_affine_point(cx, GM_Q, pts + (size_t)48 * idx[t], 1);
-    jac_add(cx, GM_R, GM_Q, GM_T);
+    const uint32_t* pt = pts + (size_t)48 * idx[t];
+    if (!f2_load_ext(S_(GM_Q), pt)) err |= ERR_NOT_CANONICAL;
+    if (!f2_load_ext(S_(GM_Q + 1), pt + 24)) err |= ERR_NOT_CANONICAL;
+    jac_add_mixed(cx, GM_R, GM_Q, GM_T);
   }
   jac_store_raw(cx, dst, GM_R);
   return err;

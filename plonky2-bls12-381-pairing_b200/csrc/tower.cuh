@@ -878,6 +878,51 @@ B381_NOINL void f2_store_ext(uint32_t* dst, const u4* a) {
   ext_st24(dst, w0, w1);
 }
 
+// Streaming products (config #2): operands taken as they are (see fp_from_ext_asis), the two halves from separate
+// places (tower order: s1 = s0 + 12; w-basis order: wherever the coefficient map puts them), and the matching store
+// that removes the 2^-64 of a product of two such operands.
+B381_DEV B381_INL void ext_ld12(uint32_t (&w)[12], const uint32_t* src) {
+#if defined(__CUDA_ARCH__)
+  if ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    const uint4 v0 = s4[0], v1 = s4[1], v2 = s4[2];
+    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+    w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 12; i++) w[i] = src[i];
+}
+B381_DEV B381_INL void ext_st12(uint32_t* dst, const uint32_t (&w)[12]) {
+#if defined(__CUDA_ARCH__)
+  if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(w[0], w[1], w[2], w[3]); d4[1] = make_uint4(w[4], w[5], w[6], w[7]); d4[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 12; i++) dst[i] = w[i];
+}
+B381_NOINL bool f2_load_asis2(u4* r, const uint32_t* s0, const uint32_t* s1) {
+  uint32_t w0[12], w1[12];
+  ext_ld12(w0, s0); ext_ld12(w1, s1);
+  Fp c0, c1;
+  const bool ok0 = fp_from_ext_asis(c0, w0);
+  const bool ok1 = fp_from_ext_asis(c1, w1);
+  st_f2(r, c0, c1);
+  return ok0 && ok1;
+}
+B381_NOINL void f2_store_unscale2(uint32_t* d0, uint32_t* d1, const u4* a) {
+  Fp c0, c1;
+  ld_f2(c0, c1, a);
+  uint32_t w0[12], w1[12];
+  fp_to_ext_unscale(w0, c0);
+  fp_to_ext_unscale(w1, c1);
+  ext_st12(d0, w0); ext_st12(d1, w1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // orchestration helpers (slot indices)
 // ---------------------------------------------------------------------------------------------
@@ -1597,6 +1642,33 @@ B381_DEV void jac_add(const Ctx& cx, int R1, int R2, int t) {
   lin(cx, u1, u1, X1, L_SUB); mul(cx, u1, s2, u1);                 // r (V - X3)
   mul(cx, s1, s1, j); lin(cx, s1, s1, -1, L_DBL);                  // 2 S1 J
   lin(cx, Y1, u1, s1, L_SUB);
+}
+
+// R1 += Q with Q affine in slots (Q, Q + 1) (madd-2007-bl: 7 products + 4 squarings instead of 11 + 5); the same
+// group element as jac_add on (Q, 1), a different Jacobian representative.  t = 9 scratch.  Bucket sums only: results
+// leave through a canonical affine conversion.
+B381_DEV void jac_add_mixed(const Ctx& cx, int R1, int Q, int t) {
+  const int X1 = R1, Y1 = R1 + 1, Z1 = R1 + 2, X2 = Q, Y2 = Q + 1;
+  const int z1z1 = t, u2 = t + 1, s2 = t + 2, h = t + 3, hh = t + 4, i = t + 5, j = t + 6, v = t + 7;
+  if (f2_is_zero(S_(Z1))) {
+    lin(cx, X1, X2, -1, L_COPY); lin(cx, Y1, Y2, -1, L_COPY); f2_set_small(S_(Z1), 1);
+    return;
+  }
+  sqr(cx, z1z1, Z1);
+  mul(cx, u2, X2, z1z1);
+  mul(cx, s2, Y2, Z1); mul(cx, s2, s2, z1z1);
+  if (f2_equal(S_(u2), S_(X1)) && f2_equal(S_(s2), S_(Y1))) { jac_double(cx, R1, t); return; }
+  lin(cx, h, u2, X1, L_SUB);
+  sqr(cx, hh, h);
+  lin(cx, i, hh, -1, L_MUL4);                                      // I = 4 H^2
+  mul(cx, j, h, i);
+  lin(cx, s2, s2, Y1, L_SUB); lin(cx, s2, s2, -1, L_DBL);          // r = 2 (S2 - Y1)
+  mul(cx, v, X1, i);                                               // V = X1 I
+  sqr_s(cx, Z1, Z1, h); kcomb(cx, Z1, Z1, z1z1, hh, -1, K_PLAIN);  // Z3 = (Z1 + H)^2 - Z1Z1 - HH
+  sqr(cx, X1, s2); kcomb(cx, X1, X1, j, v, -1, K_PLAIN); lin(cx, X1, X1, v, L_SUB);   // X3 = r^2 - J - 2 V
+  lin(cx, v, v, X1, L_SUB); mul(cx, v, s2, v);                     // r (V - X3)
+  mul(cx, j, Y1, j); lin(cx, j, j, -1, L_DBL);                     // 2 Y1 J
+  lin(cx, Y1, v, j, L_SUB);
 }
 
 // optimized_line_function (:8-78): (n, d) for the line through Q1, Q2 at P.  t = 6 scratch
