@@ -388,7 +388,7 @@ def main():
         t = time_dev(lambda: L.check(lib.b381_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), m, 0, st)))
         extras["config3_miller_loops_2p16"] = {"per_s": m / t * 1e3, "imad_frac": imad_frac(m / t * 1e3, FP_MULS_MILLER)}
         t = time_dev(lambda: L.check(lib.b381_multi_miller_loop_dev(d1.data_ptr(), d2.data_ptr(), None, mout.data_ptr(), n, 0, st)), reps=2)
-        extras["config5_multi_miller_pairs_2p20"] = {"per_s": n / t * 1e3, "note": "two pairs per thread share the squarings; tree reduction included"}
+        extras["config5_multi_miller_pairs_2p20"] = {"per_s": n / t * 1e3, "note": "four pairs per thread share the squarings; tree reduction included"}
         # G2Prepared stage: coefficients/s and Miller loops/s against prepared Q's, 2^16 pairs
         co = torch.empty(m * L.G2PREP_WORDS, dtype=torch.int32, device=dev)
         t = time_dev(lambda: L.check(lib.b381_g2_prepare_dev(d2.data_ptr(), co.data_ptr(), m, 0, st)), reps=2)

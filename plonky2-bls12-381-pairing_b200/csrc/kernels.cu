@@ -200,7 +200,7 @@ k_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, uint32
   B381_TMEM_END();
 }
 
-// every thread runs the Miller loops of TWO pairs per round with shared squarings, multiplies the
+// every thread runs the Miller loops of MK = FOUR pairs per round with shared squarings, multiplies the
 // result into a private accumulator and dumps it (internal format) to partial[global thread id]
 __global__ void __launch_bounds__(BLOCK, 1)
 k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, int mode, uint32_t* partial, int accumulate, u4* garena, int* err) {
@@ -208,15 +208,23 @@ k_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_
   Ctx cx = B381_TMEM_CTX(garena);
   if (accumulate) f12_load_raw(cx, M2_ACC, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x));
   else f12_set_one(cx, M2_ACC);
-  for (size_t base = (size_t)blockIdx.x * BLOCK * 2; base < n; base += (size_t)gridDim.x * BLOCK * 2) {
+  for (size_t base = (size_t)blockIdx.x * BLOCK * MK; base < n; base += (size_t)gridDim.x * BLOCK * MK) {
     __syncthreads();
-    size_t i0 = base + 2 * (size_t)threadIdx.x, i1 = i0 + 1;
-    const bool act0 = i0 < n, act1 = i1 < n;        // inactive slots contribute 1
-    if (!act0) i0 = n - 1;
-    if (!act1) i1 = n - 1;
-    int e = miller2_to_slots(cx, g1 + 24 * i0, g2 + 48 * i0, act0 ? (inf ? inf[i0] : 0) : 3,
-                             g1 + 24 * i1, g2 + 48 * i1, act1 ? (inf ? inf[i1] : 0) : 3, mode);
-    if (act0) report(e, err);
+    const uint32_t* pg1[MK];
+    const uint32_t* pg2[MK];
+    int pinf[MK];
+    bool any = false;
+    for (int j = 0; j < MK; j++) {
+      size_t i = base + MK * (size_t)threadIdx.x + j;
+      const bool act = i < n;                        // inactive slots contribute 1
+      if (!act) i = n - 1;
+      pg1[j] = g1 + 24 * i;
+      pg2[j] = g2 + 48 * i;
+      pinf[j] = act ? (inf ? inf[i] : 0) : 3;
+      any = any || act;
+    }
+    int e = miller_multi_to_slots(cx, pg1, pg2, pinf, mode);
+    if (any) report(e, err);
     f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);   // scratch: slots that are dead once the loop has left f in ML_F
   }
   f12_store_raw(cx, partial + (size_t)RAW_WORDS * ((size_t)blockIdx.x * BLOCK + threadIdx.x), M2_ACC);

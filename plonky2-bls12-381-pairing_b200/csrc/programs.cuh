@@ -17,7 +17,7 @@ enum ErrBits { ERR_NOT_CANONICAL = 1, ERR_ZERO_DIVISION = 2 };
 constexpr int ML_F = 0, ML_L = 6, ML_T = 9, ML_R = 19, ML_Q = 22, ML_P = 24, ML_ACC = 25, ML_NSLOTS = 31;
 // ARK Miller loop, ping-pong plan (tower.cuh ark_miller_loop_pp): banks A (= ML_F) and B, line, 5 scratch slots
 constexpr int PP_A = 0, PP_B = 6, PP_L = 12, PP_T = 15, PP_R = 20, PP_Q = 23, PP_P = 25;
-// ... second pair of the shared-squaring two-pair loop and the running product of k_multi_miller
+// ... second pair of the shared-squaring multi-pair loop and the running product of k_multi_miller (pairs 3, 4: M4_*)
 constexpr int PP_R2 = 26, PP_Q2 = 29, PP_P2 = 31, PP_ACC = 32, PP_NSLOTS = 38;
 // final exponentiation: ACC (the value being squared) and the first scratch slots are hot.
 // T = 12 scratch slots for the Fp12 products; the inversion of the easy part needs 15 and runs over into Y1, which is
@@ -25,16 +25,19 @@ constexpr int PP_R2 = 26, PP_Q2 = 29, PP_P2 = 31, PP_ACC = 32, PP_NSLOTS = 38;
 constexpr int FE_ACC = 0, FE_ACC2 = 6, FE_T = 12, FE_Y1 = 24, FE_Y2 = 30, FE_F = 36, FE_Y0 = 36 /* f is dead once y0 is first written */, FE_R = 42, FE_NSLOTS = 48;
 // literal loop
 constexpr int LT_R = 0, LT_Q = 3, LT_P = 6, LT_FN = 9, LT_FD = 10, LT_N = 11, LT_D = 12, LT_T = 13, LT_OUT = 22, LT_NSLOTS = 23;
-// shared-squaring multi-Miller (two pairs per thread): second pair's R, Q, P and the running product
+// shared-squaring multi-Miller, ZK plan: second pair's R, Q, P and the running product
 constexpr int M2_R2 = 25, M2_Q2 = 28, M2_P2 = 30, M2_ACC = 32 /* = PP_ACC: one accumulator slot range for both modes */, M2_NSLOTS = 38;
 constexpr int M2_SCRATCH = 6;   // 14 scratch slots of the accumulating Fp12 product: dead line / scratch / bank-B slots of either plan
-constexpr int MAX_NSLOTS = 48;
+// pairs three and four of the shared-squaring multi-Miller loop (either plan): R (3 slots), Q (2), P (1) each
+constexpr int MK = 4;                 // pairs per thread of the on-the-fly multi-Miller loop
+constexpr int M4_R3 = 38, M4_Q3 = 41, M4_P3 = 43, M4_R4 = 44, M4_Q4 = 47, M4_P4 = 49, M4_NSLOTS = 50;
+constexpr int MAX_NSLOTS = 50;
 // Stores under a per-thread `if (ident)` (miller_to_slots & co.) must never hit tensor memory (tcgen05.st is
 // .sync.aligned): the P / Q input slots live in the global-memory part of the arena, f in shared memory.
 static_assert(ML_Q >= NS + NT_MAX && ML_P >= NS + NT_MAX && M2_Q2 >= NS + NT_MAX && M2_P2 >= NS + NT_MAX, "P / Q slots must be global-memory slots");
 static_assert(ML_F + 5 < NS, "f must be a shared-memory slot range");
 static_assert(PP_Q >= NS + NT_MAX && PP_P >= NS + NT_MAX && PP_A == ML_F, "ping-pong plan: P / Q in global memory, result where ML_F is");
-static_assert(PP_NSLOTS <= MAX_NSLOTS && M2_NSLOTS <= MAX_NSLOTS && PP_ACC == M2_ACC, "arena size / shared accumulator");
+static_assert(PP_NSLOTS <= MAX_NSLOTS && M2_NSLOTS <= MAX_NSLOTS && M4_NSLOTS <= MAX_NSLOTS && PP_ACC == M2_ACC && M4_R3 >= PP_ACC + 6, "arena size / shared accumulator");
 
 #define S_(i) slot(cx, (i))
 
@@ -92,16 +95,16 @@ B381_DEV B381_INL int miller_to_slots(const Ctx& cx, const uint32_t* g1, const u
   return err;
 }
 
-// Miller loops of TWO pairs with shared squarings into slots ML_F.. ; identity pairs contribute 1.
-B381_DEV B381_INL int miller2_to_slots(const Ctx& cx, const uint32_t* g1a, const uint32_t* g2a, int infa,
-                                       const uint32_t* g1b, const uint32_t* g2b, int infb, int mode) {
+// Miller loops of MK = FOUR pairs with shared squarings into slots ML_F.. ; identity pairs contribute 1.
+B381_DEV B381_INL int miller_multi_to_slots(const Ctx& cx, const uint32_t* const* g1, const uint32_t* const* g2, const int* inf, int mode) {
   int err = 0;
-  bool ident[2] = {(infa & 3) != 0, (infb & 3) != 0};
+  bool ident[MK];
   const bool zk = mode == MODE_ZK;
-  const int Pj[2] = {zk ? ML_P : PP_P, zk ? M2_P2 : PP_P2}, Qj[2] = {zk ? ML_Q : PP_Q, zk ? M2_Q2 : PP_Q2};
-  const uint32_t* g1[2] = {g1a, g1b};
-  const uint32_t* g2[2] = {g2a, g2b};
-  for (int j = 0; j < 2; j++) {
+  const int Rj[MK] = {zk ? ML_R : PP_R, zk ? M2_R2 : PP_R2, M4_R3, M4_R4};
+  const int Qj[MK] = {zk ? ML_Q : PP_Q, zk ? M2_Q2 : PP_Q2, M4_Q3, M4_Q4};
+  const int Pj[MK] = {zk ? ML_P : PP_P, zk ? M2_P2 : PP_P2, M4_P3, M4_P4};
+  for (int j = 0; j < MK; j++) {
+    ident[j] = (inf[j] & 3) != 0;
     if (ident[j]) {
       f2_set_small(S_(Pj[j]), 0); f2_set_small(S_(Qj[j]), 0); f2_set_small(S_(Qj[j] + 1), 0);
     } else {
@@ -113,15 +116,13 @@ B381_DEV B381_INL int miller2_to_slots(const Ctx& cx, const uint32_t* g1a, const
   if (zk) {
     MultiSlots s;
     s.f = ML_F; s.L = ML_L; s.T = ML_T;
-    s.R[0] = ML_R; s.Q[0] = ML_Q; s.P[0] = ML_P;
-    s.R[1] = M2_R2; s.Q[1] = M2_Q2; s.P[1] = M2_P2;
-    zk_miller_loop_multi(cx, s, 2, ident);
+    for (int j = 0; j < MK; j++) { s.R[j] = Rj[j]; s.Q[j] = Qj[j]; s.P[j] = Pj[j]; }
+    zk_miller_loop_multi(cx, s, MK, ident);
   } else {
     MillerSlotsPP s;
     s.A = PP_A; s.B = PP_B; s.L = PP_L; s.T = PP_T;
-    s.R[0] = PP_R; s.Q[0] = PP_Q; s.P[0] = PP_P;
-    s.R[1] = PP_R2; s.Q[1] = PP_Q2; s.P[1] = PP_P2;
-    ark_miller_loop_pp<2>(cx, s, ident);
+    for (int j = 0; j < MK; j++) { s.R[j] = Rj[j]; s.Q[j] = Qj[j]; s.P[j] = Pj[j]; }
+    ark_miller_loop_pp<MK>(cx, s, ident);
   }
   return err;
 }

@@ -1439,7 +1439,7 @@ B381_DEV void ark_miller_loop_pp(const Ctx& cx, const MillerSlotsPP& s, const bo
 }
 
 // slot plan of the ZK-mode two-pair loop (in-place primitives)
-struct MultiSlots { int f, L, T; int R[2], Q[2], P[2]; };
+struct MultiSlots { int f, L, T; int R[KPP], Q[KPP], P[KPP]; };
 
 // ---------------------------------------------------------------------------------------------
 // ZK mode: /root/reference/src/miller_loop_native.rs:27-116 with ell (:139-152) wired in.

@@ -119,15 +119,20 @@ int hs_final_exp(const uint32_t* in, uint32_t* out) { Ctx cx = make_ctx(); retur
 int hs_pairing(const uint32_t* g1, const uint32_t* g2, int inf, uint32_t* out, int mode) { Ctx cx = make_ctx(); return prog_pairing(cx, g1, g2, inf, out, mode); }
 int hs_literal(const uint32_t* g1p, const uint32_t* g2p, uint32_t* out) { Ctx cx = make_ctx(); return prog_literal(cx, g1p, g2p, out); }
 
-// product of n Miller values, two pairs at a time with shared squarings (the k_multi_miller path)
+// product of n Miller values, MK = four pairs at a time with shared squarings (the k_multi_miller path)
 int hs_multi_miller(const uint32_t* g1, const uint32_t* g2, const uint8_t* inf, size_t n, uint32_t* out, int mode) {
   Ctx cx = make_ctx();
   int err = 0;
   f12_set_one(cx, M2_ACC);
-  for (size_t i = 0; i < n; i += 2) {
-    const bool has1 = i + 1 < n;
-    size_t j = has1 ? i + 1 : i;
-    err |= miller2_to_slots(cx, g1 + 24 * i, g2 + 48 * i, inf ? inf[i] : 0, g1 + 24 * j, g2 + 48 * j, has1 ? (inf ? inf[j] : 0) : 3, mode);
+  for (size_t i = 0; i < n; i += MK) {
+    const uint32_t* pg1[MK]; const uint32_t* pg2[MK]; int pinf[MK];
+    for (int j = 0; j < MK; j++) {
+      const bool act = i + j < n;
+      const size_t k = act ? i + j : n - 1;
+      pg1[j] = g1 + 24 * k; pg2[j] = g2 + 48 * k;
+      pinf[j] = act ? (inf ? inf[k] : 0) : 3;
+    }
+    err |= miller_multi_to_slots(cx, pg1, pg2, pinf, mode);
     f12_mul(cx, M2_ACC, M2_ACC, ML_F, M2_SCRATCH, M2_SCRATCH + 6);   // scratch: slots that are dead once the loop has left f in ML_F
   }
   f12_store_ext(cx, out, M2_ACC);

@@ -779,3 +779,21 @@ def test_multi_miller_packed(L, lib, z):
     L.check(lib.b381_check_dev(st))
     assert a.cpu().numpy().view(np.uint32).tolist() == o.f12_to_limbs32(o.F12_ONE)
     assert lib.b381_multi_miller_loop_packed_dev(g1.data_ptr(), None, None, a.data_ptr(), n, 1, st) == -2
+
+
+@pytest.mark.gpu
+def test_multi_miller_ragged_counts_both_modes(L, lib, z):
+    """the four-pairs-per-thread multi-Miller loop at every residue of the batch size mod 4 (padding pairs contribute 1),
+    ARK and ZK modes, with identity flags: equals the product (b381_fp12_product) of the individual Miller values."""
+    rng = np.random.default_rng(79)
+    for mode in (L.MODE_ARK, L.MODE_ZK):
+        for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 1023):
+            idx = rng.integers(0, 256, size=n)
+            g1, g2 = _pairs(z, idx)
+            inf = (rng.integers(0, 4, size=n) * (rng.integers(0, 4, size=n) == 0)).astype(np.uint8)
+            each = np.zeros(n * 144, dtype=np.uint32)
+            L.check(lib.b381_miller_loop(util.p32(g1), util.p32(g2), util.p8(inf), util.p32(each), n, mode))
+            want = np.zeros(144, dtype=np.uint32); got = np.zeros(144, dtype=np.uint32)
+            L.check(lib.b381_fp12_product(util.p32(each), util.p32(want), n))
+            L.check(lib.b381_multi_miller_loop(util.p32(g1), util.p32(g2), util.p8(inf), util.p32(got), n, mode))
+            assert np.array_equal(got, want), (mode, n)
