@@ -192,7 +192,8 @@ int b381_fp2_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t
 int b381_fp12_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream);
 int b381_g2_prepare_dev(const uint32_t* g2, uint32_t* coeffs, size_t n, int mode, void* stream);
 int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream);
-/* G2Prepared in the library's own ("packed") layout: the same 68 triples per Q, kept in the internal number format and
+/* G2Prepared in the library's own ("packed") layout (the cached stage of src/miller_loop_target.rs:23-76 /
+   ark-ec G2Prepared again, consumed by the loop of src/miller_loop_native.rs:154-212): the same 68 triples per Q, kept in the internal number format and
    interleaved over tiles of 256 points so that a warp reads 512 contiguous bytes per access; the Miller loop multiplies
    straight out of the buffer (no conversion per line, no copy).  Device memory only, 16-byte aligned,
    b381_g2_packed_words(n) 32-bit words (n rounded up to a tile); opaque -- valid for this library build and `mode`.
@@ -200,7 +201,12 @@ int b381_miller_loop_prepared_dev(const uint32_t* g1, const uint32_t* coeffs, co
 size_t b381_g2_packed_words(size_t n);
 int b381_g2_prepare_packed_dev(const uint32_t* g2, uint32_t* packed, size_t n, int mode, void* stream);
 int b381_miller_loop_packed_dev(const uint32_t* g1, const uint32_t* packed, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream);
-/* out144 = product over i of miller_loop(P_i, packed Q_i) (ARK mode: `packed` must come from b381_g2_prepare_packed_dev with
+/* ONE cached Q against n points P_i: out[i] = miller_loop(P_i, Q) (final_exp: the pairing), Q = point 0 of `packed_one`
+   (b381_g2_prepare_packed_dev with n = 1).  Every thread reads the same lines (broadcast loads): no per-pair coefficient
+   memory, any batch size.  inf[i] bit0 = P_i is the identity. */
+int b381_miller_loop_packed_one_dev(const uint32_t* g1, const uint32_t* packed_one, const uint8_t* inf, uint32_t* out, size_t n, int mode, int final_exp, void* stream);
+/* multi_miller_loop (src/miller_loop_native.rs:154-212; ark Bls12::multi_miller_loop) against cached Q's:
+   out144 = product over i of miller_loop(P_i, packed Q_i) (ARK mode: `packed` must come from b381_g2_prepare_packed_dev with
    B381_MODE_ARK), optionally followed by the final exponentiation: the BLS batch-verify shape against cached public keys.
    Four pairs per thread share every squaring of f.  Same value as b381_multi_miller_loop / b381_multi_pairing. */
 int b381_multi_miller_loop_packed_dev(const uint32_t* g1, const uint32_t* packed, const uint8_t* inf, uint32_t* out144, size_t n, int final_exp, void* stream);

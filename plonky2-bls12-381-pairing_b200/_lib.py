@@ -86,6 +86,7 @@ SIGNATURES = {
     "b381_g2_prepare_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
     "b381_miller_loop_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_multi_miller_loop_packed_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
+    "b381_miller_loop_packed_one_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_miller_loop_prepared_dev": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p],
     "b381_check_dev": [ctypes.c_void_p],
     "b381_ctx_create": [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)],

@@ -186,7 +186,7 @@ k_g2_prepare_packed(const uint32_t* g2, u4* packed, size_t n, int mode, u4* gare
 
 // Miller loop (optionally + final exponentiation) of (P, packed prepared Q)
 __global__ void __launch_bounds__(BLOCK, 1)
-k_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, u4* garena, int* err, uint32_t* dump) {
+k_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, uint32_t* out, size_t n, int mode, int do_fe, int one_q, u4* garena, int* err, uint32_t* dump) {
   B381_TMEM_BEGIN();
   Ctx cx = B381_TMEM_CTX(garena);
   for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {
@@ -194,7 +194,8 @@ k_miller_packed(const uint32_t* g1, const u4* packed, const uint8_t* inf, uint32
     size_t i = base + threadIdx.x;
     const bool active = i < n;
     if (!active) i = n - 1;
-    int e = prog_miller_packed(cx, g1 + 24 * i, packed + g2pack_index(i), inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode, do_fe);
+    // one_q: every pair reads point 0 of the buffer (one cached Q against many P): warp-uniform addresses, broadcast loads
+    int e = prog_miller_packed(cx, g1 + 24 * i, one_q ? packed : packed + g2pack_index(i), inf ? inf[i] : 0, active ? out + 144 * i : dump + 144 * threadIdx.x, mode, do_fe);
     if (active) report(e, err);
   }
   B381_TMEM_END();

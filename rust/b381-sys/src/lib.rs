@@ -80,6 +80,7 @@ extern "C" {
     pub fn b381_g2_prepare_packed_dev(g2: *const u32, packed: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_miller_loop_packed_dev(g1: *const u32, packed: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, final_exp: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_multi_miller_loop_packed_dev(g1: *const u32, packed: *const u32, inf: *const u8, out144: *mut u32, n: usize, final_exp: c_int, stream: *mut c_void) -> c_int;
+    pub fn b381_miller_loop_packed_one_dev(g1: *const u32, packed_one: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, final_exp: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_g2_prepare_dev(g2: *const u32, coeffs: *mut u32, n: usize, mode: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_miller_loop_prepared_dev(g1: *const u32, coeffs: *const u32, inf: *const u8, out: *mut u32, n: usize, mode: c_int, final_exp: c_int, stream: *mut c_void) -> c_int;
     pub fn b381_check_dev(stream: *mut c_void) -> c_int;

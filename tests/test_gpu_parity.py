@@ -797,3 +797,36 @@ def test_multi_miller_ragged_counts_both_modes(L, lib, z):
             L.check(lib.b381_fp12_product(util.p32(each), util.p32(want), n))
             L.check(lib.b381_multi_miller_loop(util.p32(g1), util.p32(g2), util.p8(inf), util.p32(got), n, mode))
             assert np.array_equal(got, want), (mode, n)
+
+
+@pytest.mark.gpu
+def test_one_cached_q_against_many_p(L, lib, z):
+    """b381_miller_loop_packed_one_dev: one packed prepared Q, n points P_i (broadcast line reads): equals the pairing /
+    Miller loop of (P_i, Q) computed the ordinary way, across a round boundary, with identity flags on P."""
+    import torch
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    n = sm * 256 + 300
+    rng = np.random.default_rng(80)
+    idx = rng.integers(0, 256, size=n)
+    q = np.ascontiguousarray(z["g2"][17])
+    g1 = torch.from_numpy(np.ascontiguousarray(z["g1"][idx]).reshape(-1).view(np.int32)).to(dev)
+    g2 = torch.from_numpy(np.tile(q, n).view(np.int32)).to(dev)
+    pk = torch.empty(lib.b381_g2_packed_words(1), dtype=torch.int32, device=dev)
+    L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr(), 1, L.MODE_ARK, st))
+    inf = (rng.integers(0, 8, size=n) == 0).astype(np.uint8)
+    dinf = torch.from_numpy(inf).to(dev)
+    a = torch.empty(n * 144, dtype=torch.int32, device=dev); b = torch.empty(n * 144, dtype=torch.int32, device=dev)
+    for fe in (0, 1):
+        L.check(lib.b381_miller_loop_packed_one_dev(g1.data_ptr(), pk.data_ptr(), dinf.data_ptr(), a.data_ptr(), n, L.MODE_ARK, fe, st))
+        if fe:
+            L.check(lib.b381_pairing_dev(g1.data_ptr(), g2.data_ptr(), dinf.data_ptr(), b.data_ptr(), n, L.MODE_ARK, st))
+        else:
+            L.check(lib.b381_miller_loop_dev(g1.data_ptr(), g2.data_ptr(), dinf.data_ptr(), b.data_ptr(), n, L.MODE_ARK, st))
+        L.check(lib.b381_check_dev(st))
+        assert torch.equal(a, b), fe
+    P = (o.fp_from_limbs32(z["g1"][idx[1]][:12].tolist()), o.fp_from_limbs32(z["g1"][idx[1]][12:].tolist()))
+    Q = (util.f2_from_words(q[:24].tolist()), util.f2_from_words(q[24:].tolist()))
+    if not inf[1]:
+        assert o.f12_eq(o.f12_from_limbs32(a[144:288].cpu().numpy().view(np.uint32).tolist()), o.ark_pairing(P, Q))
