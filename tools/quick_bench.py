@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """quick_bench.py -- A/B timing of experiment builds of libb381.so on one GPU.
 
-    python tools/quick_bench.py build/v/lib_a.so build/v/lib_b.so ...        (run under gpurun)
+    python tools/quick_bench.py _variants/lib_a.so _variants/lib_b.so ...        (run under gpurun)
 
 Each library is loaded in its own subprocess (B381_LIB), checked against the golden fixture on 1024 tiled
 pairs (pairing, Miller loop), then timed with CUDA events on device-resident buffers: full pairings
@@ -25,6 +25,7 @@ def child(path):
     lib = L.init(0)
     z = np.load(os.path.join(ROOT, "tests", "golden", "pairs_256.npz"))
     res = {"lib": os.path.basename(path)}
+    path = path.partition("@")[0]
     n0 = 1024
     perm = np.random.default_rng(3).integers(0, 256, size=n0)
     g1 = np.ascontiguousarray(z["g1"][perm]).reshape(-1); g2 = np.ascontiguousarray(z["g2"][perm]).reshape(-1)
@@ -78,9 +79,14 @@ def child(path):
 def main():
     if len(sys.argv) >= 3 and sys.argv[1] == "--child":
         return child(sys.argv[2])
-    for path in sys.argv[1:]:
+    for spec in sys.argv[1:]:
+        # lib.so or lib.so@VAR=value[,VAR=value...] (environment of the child: run-time experiment switches)
+        path, _, extra = spec.partition("@")
         env = dict(os.environ, B381_LIB=os.path.abspath(path))
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", path], env=env, capture_output=True, text=True)
+        for kv in filter(None, extra.split(",")):
+            k, _, v = kv.partition("=")
+            env[k] = v
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", spec], env=env, capture_output=True, text=True)
         sys.stdout.write(r.stdout)
         if r.returncode != 0:
             print(json.dumps({"lib": os.path.basename(path), "error": r.stderr[-600:]}))
