@@ -87,10 +87,43 @@ k_msm_scan(const unsigned int* cnt, unsigned int* start, unsigned int* cursor, s
   if (threadIdx.x == 0) start[m] = s_carry;
 }
 
-// one thread per bucket (w, d), d >= 1: sum of its points -> buckets[(w * B + d)] (raw Jacobian)
+// Buckets ordered by decreasing size (counting sort over min(size, 255)): the threads of a warp then sum buckets of
+// (nearly) equal size instead of waiting for the fullest of 32 random ones (sizes are Poisson: mean 16 at 2^20 points
+// and 16-bit windows, the maximum of 32 is about 27).  mode 0: hist[size]++; mode 1: order[cursor[size]++] = bucket.
+// Per-block histograms in shared memory keep the global atomics at 256 per block.
+__global__ void __launch_bounds__(256)
+k_msm_size_sort(const unsigned int* start, size_t m, unsigned int* hist_or_cursor, uint32_t* order, int mode) {
+  __shared__ unsigned int s_cnt[256], s_base[256];
+  const size_t per = (m + gridDim.x - 1) / gridDim.x, lo = (size_t)blockIdx.x * per, hi = lo + per < m ? lo + per : m;
+  s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (size_t b = lo + threadIdx.x; b < hi; b += blockDim.x) {
+    const unsigned int sz = start[b + 1] - start[b];
+    atomicAdd(&s_cnt[sz < 255u ? sz : 255u], 1u);
+  }
+  __syncthreads();
+  if (s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&hist_or_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  if (mode == 0) return;
+  __syncthreads();
+  s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (size_t b = lo + threadIdx.x; b < hi; b += blockDim.x) {
+    const unsigned int sz = start[b + 1] - start[b], bin = sz < 255u ? sz : 255u;
+    order[s_base[bin] + atomicAdd(&s_cnt[bin], 1u)] = (uint32_t)b;
+  }
+}
+// hist (256 bins) -> first rank of every size, largest sizes first
+__global__ void k_msm_size_offsets(unsigned int* hist) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned int off = 0;
+  for (int c = 255; c >= 0; c--) { const unsigned int t = hist[c]; hist[c] = off; off += t; }
+}
+
+// one thread per bucket (w, d), taken in the order of decreasing size: sum of its points -> buckets[(w * B + d)] (raw Jacobian)
 __global__ void __launch_bounds__(128)
-k_msm_bucket_sums(const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, size_t m, uint32_t* buckets) {
-  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < m; b += (size_t)gridDim.x * blockDim.x) {
+k_msm_bucket_sums(const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, const uint32_t* order, size_t m, uint32_t* buckets) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = order[t];
     G1J acc;
     msm_bucket_sum(acc, pts_raw, idx, start[b], start[b + 1]);
     g1_st_raw_jac(buckets + (size_t)G1_RAW_JAC * b, acc);
@@ -176,8 +209,15 @@ int g1l_msm_scan(cudaStream_t s, const unsigned int* cnt, unsigned int* start, u
   k_msm_scan<<<1, 1024, 0, s>>>(cnt, start, cursor, m);
   return 1;
 }
-int g1l_msm_bucket_sums(int grid, cudaStream_t s, const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, size_t m, uint32_t* buckets) {
-  k_msm_bucket_sums<<<grid, 128, 0, s>>>(pts_raw, idx, start, m, buckets);
+int g1l_msm_size_order(int grid, cudaStream_t s, const unsigned int* start, size_t m, unsigned int* hist256, uint32_t* order) {
+  cudaMemsetAsync(hist256, 0, 256 * sizeof(unsigned int), s);
+  k_msm_size_sort<<<grid, 256, 0, s>>>(start, m, hist256, order, 0);
+  k_msm_size_offsets<<<1, 32, 0, s>>>(hist256);
+  k_msm_size_sort<<<grid, 256, 0, s>>>(start, m, hist256, order, 1);
+  return 3;
+}
+int g1l_msm_bucket_sums(int grid, cudaStream_t s, const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, const uint32_t* order, size_t m, uint32_t* buckets) {
+  k_msm_bucket_sums<<<grid, 128, 0, s>>>(pts_raw, idx, start, order, m, buckets);
   return 1;
 }
 int g1l_msm_chunks(int grid, cudaStream_t s, const uint32_t* buckets, int W, int c, int CH, uint32_t* partial) {

@@ -362,10 +362,12 @@ k_g2_point_sum(const uint32_t* in, const uint8_t* in_inf, size_t n_in, uint32_t*
 
 // ---- G2 bucket method (programs.cuh): per-thread trip counts differ -> no lock step, no tensor memory ----------
 __global__ void __launch_bounds__(BLOCK, 1)
-k_g2_msm_bucket_sums(const uint32_t* pts, const uint32_t* idx, const unsigned int* start, size_t m, uint32_t* buckets, u4* garena, int* err) {
+k_g2_msm_bucket_sums(const uint32_t* pts, const uint32_t* idx, const unsigned int* start, const uint32_t* order, size_t m, uint32_t* buckets, u4* garena, int* err) {
   Ctx cx = make_ctx(garena, 0);
-  for (size_t b = (size_t)blockIdx.x * BLOCK + threadIdx.x; b < m; b += (size_t)gridDim.x * BLOCK)
+  for (size_t t = (size_t)blockIdx.x * BLOCK + threadIdx.x; t < m; t += (size_t)gridDim.x * BLOCK) {
+    const size_t b = order[t];                      // buckets by decreasing size: a warp's 32 buckets are equally full
     report(prog_g2_bucket_sum(cx, pts, idx, start[b], start[b + 1], buckets + (size_t)G2_RAW_JAC * b), err);
+  }
 }
 __global__ void __launch_bounds__(BLOCK, 1)
 k_g2_msm_chunks(const uint32_t* buckets, int W, int c, int CH, uint32_t* partial, u4* garena) {
