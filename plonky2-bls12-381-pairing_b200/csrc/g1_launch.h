@@ -15,7 +15,8 @@ constexpr int G1L_RAW_AFF = 24, G1L_RAW_JAC = 36;      // words of a raw affine 
 int g1l_point_op(int grid, cudaStream_t s, int op, const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, uint32_t* out, uint8_t* out8, size_t n, int* err);
 int g1l_to_raw(int grid, cudaStream_t s, const uint32_t* pts, uint32_t* raw, size_t n, int* err);
 int g1l_msm_digits(int grid, cudaStream_t s, const uint32_t* scalars, const uint8_t* inf, size_t n, int W, int c, unsigned int* cnt_or_cursor, uint32_t* idx, int mode);
-int g1l_msm_scan(cudaStream_t s, const unsigned int* cnt, unsigned int* start, unsigned int* cursor, size_t m);
+// scratch: 3 x (ceil(m / 1024) + 1) words (used when m > 16384)
+int g1l_msm_scan(cudaStream_t s, const unsigned int* cnt, unsigned int* start, unsigned int* cursor, size_t m, unsigned int* scratch);
 // order[0 .. m) = the buckets by decreasing size (hist256: 256 words of scratch); shared by the G1 and G2 bucket sums
 int g1l_msm_size_order(int grid, cudaStream_t s, const unsigned int* start, size_t m, unsigned int* hist256, uint32_t* order);
 int g1l_msm_bucket_sums(int grid, cudaStream_t s, const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, const uint32_t* order, size_t m, uint32_t* buckets);
