@@ -191,6 +191,47 @@ k_g1_jac_sums(const uint32_t* in, size_t n_in, size_t per, uint32_t* sums, size_
   }
 }
 
+// sums[w] = sum of the nchunk chunk results of window w: one block per window; every thread adds its strided share,
+// then a shuffle tree inside the warps and one across them: 8 + 5 + 3 sequential additions for 2048 chunks instead of
+// the 32 + 64 of two levels of one-thread sums
+__device__ __forceinline__ void g1_shfl_down(G1J& r, const G1J& p, int delta) {
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    r.x.l[k] = __shfl_down_sync(0xffffffffu, p.x.l[k], delta);
+    r.y.l[k] = __shfl_down_sync(0xffffffffu, p.y.l[k], delta);
+    r.z.l[k] = __shfl_down_sync(0xffffffffu, p.z.l[k], delta);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_g1_window_tree(const uint32_t* partial, size_t nchunk, uint32_t* sums) {
+  __shared__ uint32_t s_w[8][G1_RAW_JAC];
+  const uint32_t* in = partial + (size_t)G1_RAW_JAC * blockIdx.x * nchunk;
+  G1J acc;
+  g1_set_identity(acc);
+  for (size_t t = threadIdx.x; t < nchunk; t += 256) {
+    G1J q;
+    g1_ld_raw_jac(q, in + (size_t)G1_RAW_JAC * t);
+    g1_add(acc, acc, q);
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    G1J q;
+    g1_shfl_down(q, acc, d);
+    g1_add(acc, acc, q);
+  }
+  if ((threadIdx.x & 31) == 0) g1_st_raw_jac(s_w[threadIdx.x >> 5], acc);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x < 8) g1_ld_raw_jac(acc, s_w[threadIdx.x]);
+    else g1_set_identity(acc);
+    for (int d = 4; d >= 1; d >>= 1) {
+      G1J q;
+      g1_shfl_down(q, acc, d);
+      g1_add(acc, acc, q);
+    }
+    if (threadIdx.x == 0) g1_st_raw_jac(sums + (size_t)G1_RAW_JAC * blockIdx.x, acc);
+  }
+}
+
 // Horner over the W window sums (c doublings per window) and conversion to affine; W = 1, c = 0: plain conversion
 __global__ void k_msm_final(const uint32_t* sums, int W, int c, uint32_t* out24, uint8_t* out_inf) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -265,6 +306,10 @@ int g1l_msm_chunks(int grid, cudaStream_t s, const uint32_t* buckets, int W, int
 }
 int g1l_jac_sums(int grid, cudaStream_t s, const uint32_t* in, size_t n_in, size_t per, uint32_t* sums, size_t n_out) {
   k_g1_jac_sums<<<grid, 128, 0, s>>>(in, n_in, per, sums, n_out);
+  return 1;
+}
+int g1l_window_tree(cudaStream_t s, const uint32_t* partial, int W, size_t nchunk, uint32_t* sums) {
+  k_g1_window_tree<<<W, 256, 0, s>>>(partial, nchunk, sums);
   return 1;
 }
 int g1l_msm_final(cudaStream_t s, const uint32_t* sums, int W, int c, uint32_t* out24, uint8_t* out_inf) {

@@ -22,6 +22,7 @@ int g1l_msm_size_order(int grid, cudaStream_t s, const unsigned int* start, size
 int g1l_msm_bucket_sums(int grid, cudaStream_t s, const uint32_t* pts_raw, const uint32_t* idx, const unsigned int* start, const uint32_t* order, size_t m, uint32_t* buckets);
 int g1l_msm_chunks(int grid, cudaStream_t s, const uint32_t* buckets, int W, int c, int CH, uint32_t* partial);
 int g1l_jac_sums(int grid, cudaStream_t s, const uint32_t* in, size_t n_in, size_t per, uint32_t* sums, size_t n_out);
+int g1l_window_tree(cudaStream_t s, const uint32_t* partial, int W, size_t nchunk, uint32_t* sums);
 int g1l_msm_final(cudaStream_t s, const uint32_t* sums, int W, int c, uint32_t* out24, uint8_t* out_inf);
 int g1l_sum_strided(int grid, cudaStream_t s, const uint32_t* pts, const uint8_t* inf, size_t n, uint32_t* partial, size_t T, int* err);
 

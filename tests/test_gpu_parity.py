@@ -727,6 +727,21 @@ def test_g2_packed_stage(L, lib, z):
             one = np.array(o.f12_to_limbs32(o.F12_ONE), dtype=np.uint32)
             for i in range(n):
                 assert np.array_equal(got[i], one if inf[i] else z["pairing"][idx[i]]), i
+    # a coordinate that is not canonical (all-ones words >= p) is reported through the context's error word; a Q flagged
+    # as the identity is never read
+    bad2 = torch.full((48,), -1, dtype=torch.int32, device=dev)
+    pk1 = torch.empty(lib.b381_g2_packed_words(1), dtype=torch.int32, device=dev)
+    L.check(lib.b381_g2_prepare_packed_dev(bad2.data_ptr(), pk1.data_ptr(), 1, L.MODE_ARK, st))
+    assert lib.b381_check_dev(st) == -3
+    bad1 = torch.full((24,), -1, dtype=torch.int32, device=dev)
+    L.check(lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk1.data_ptr(), 1, L.MODE_ARK, st))
+    o1 = torch.empty(144, dtype=torch.int32, device=dev)
+    L.check(lib.b381_miller_loop_packed_dev(bad1.data_ptr(), pk1.data_ptr(), None, o1.data_ptr(), 1, L.MODE_ARK, 0, st))
+    assert lib.b381_check_dev(st) == -3
+    f2 = torch.tensor([1], dtype=torch.uint8, device=dev)             # P flagged as the identity: its words are ignored
+    L.check(lib.b381_miller_loop_packed_dev(bad1.data_ptr(), pk1.data_ptr(), f2.data_ptr(), o1.data_ptr(), 1, L.MODE_ARK, 0, st))
+    assert lib.b381_check_dev(st) == 0
+    assert o1.cpu().numpy().view(np.uint32).tolist() == o.f12_to_limbs32(o.F12_ONE)
     # argument checks: null / misaligned buffer, LITERAL mode
     assert lib.b381_g2_prepare_packed_dev(g2.data_ptr(), None, 1, L.MODE_ARK, st) == -2
     assert lib.b381_g2_prepare_packed_dev(g2.data_ptr(), pk.data_ptr() + 4, 1, L.MODE_ARK, st) == -2
