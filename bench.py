@@ -509,7 +509,7 @@ def main():
                 continue
             t = time_dev(lambda: L.check(lib.b381_g1_msm_dev(mp.data_ptr(), None, sc2.data_ptr(), r1.data_ptr(), rf.data_ptr(), nn, st)), reps=2)
             # bucket method at window c: ceil(256 / c) mixed additions of 11 Fp-mul per point
-            c = 16 if logn >= 17 else 8; w = 256 // c
+            c = 16 if logn >= 16 else 8; w = 256 // c
             grp["g1_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": c, "imad_frac_bucket_additions": imad_frac(nn / t * 1e3, w * 11)}
         # G2 bucket method on distinct points [s_i] Q_i (made on the device); window c: ceil(256 / c) general additions per point
         n2 = min(n, 1 << 20)
@@ -521,7 +521,7 @@ def main():
             if nn > n2:
                 continue
             t = time_dev(lambda: L.check(lib.b381_g2_msm_dev(mp2.data_ptr(), None, sc2.data_ptr(), r2.data_ptr(), rf.data_ptr(), nn, st)), reps=2)
-            grp["g2_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": 16 if logn >= 17 else 8}
+            grp["g2_msm_2p%d" % logn] = {"points_per_s": nn / t * 1e3, "window_bits": 16 if logn >= 16 else 8}
         del mp2, mf2
         t = time_dev(lambda: L.check(lib.b381_g1_sum_dev(mp.data_ptr(), None, r1.data_ptr(), rf.data_ptr(), n, st)), reps=2)
         grp["g1_sum_points_per_s"] = n / t * 1e3
