@@ -464,7 +464,8 @@ B381_HD B381_INL void acc_neg(Acc& r, const Acc& a) {
     MADC_LO_CC(A[6], m_, (uint32_t)B381_Q6);  MADC_HI_CC(A[7], m_, (uint32_t)B381_Q6);                  \
     MADC_LO_CC(A[8], m_, (uint32_t)B381_Q8);  MADC_HI_CC(A[9], m_, (uint32_t)B381_Q8);                  \
     MADC_LO_CC(A[10], m_, (uint32_t)B381_Q10); MADC_HI_CC(A[11], m_, (uint32_t)B381_Q10);               \
-    ADDC_CC(A[12], A[12], 0u);           /* A[12] held at most one earlier carry: no carry out */        \
+    ADDC_CC(A[12], A[12], 0u);           /* later rows: A[12] held at most one earlier carry, no carry out */ \
+    if (!(cin)) { ADDC_CC(A[13], A[13], 0u); }  /* row 0: A[12] is word 12 of the INPUT, any value -- 0xffffffff + carry ripples into word 13 */ \
   }
 
 // r = t / 2^(32 ROWS) mod p, result in (t / 2^(32 ROWS), t / 2^(32 ROWS) + p].  Only the low ROWS

@@ -293,6 +293,20 @@ int hs_g2_msm(const uint32_t* pts, const uint8_t* inf, const uint32_t* scalars, 
   return err;
 }
 
+// Montgomery reduction of an arbitrary 26-word value (two's complement, |t| small enough): out = 13 stored words
+int hs_redc(const uint32_t* t26, uint32_t* out13) {
+  Acc t, t2, t3;
+  for (int k = 0; k < NW; k++) { t.c[k] = t26[k]; t2.c[k] = t26[k]; t3.c[k] = t26[k]; }
+#ifdef B381_TRACK_BOUNDS
+  t.cb = t2.cb = t3.cb = 0; t.mag = t2.mag = t3.mag = 100.0;
+#endif
+  Fp r, r2, r3;
+  acc_redc(r, t);
+  acc_redc2(r2, t2, r3, t3);
+  for (int k = 0; k < NL; k++) { out13[k] = (uint32_t)r.l[k]; if (r.l[k] != r2.l[k] || r.l[k] != r3.l[k]) return 1; }
+  return 0;
+}
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

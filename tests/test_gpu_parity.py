@@ -845,3 +845,37 @@ def test_one_cached_q_against_many_p(L, lib, z):
     Q = (util.f2_from_words(q[:24].tolist()), util.f2_from_words(q[24:].tolist()))
     if not inf[1]:
         assert o.f12_eq(o.f12_from_limbs32(a[144:288].cpu().numpy().view(np.uint32).tolist()), o.ark_pairing(P, Q))
+
+
+@pytest.mark.gpu
+def test_regression_redc_carry_pair(L, lib):
+    """the pair (one of 2^20 distinct ones, tools/big_parity.py seed 7) whose final exponentiation hit word 12 = 0xffffffff
+    plus a carry in row 0 of the Montgomery reduction: pairing, Miller loop, final exponentiation and the prepared paths
+    against the Python oracle's values (tests/golden/regress_redc_carry.json)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(util.ROOT, "tests", "golden", "regress_redc_carry.json")))
+    g1 = np.array(g["g1"], dtype=np.uint32); g2 = np.array(g["g2"], dtype=np.uint32)
+    out = np.zeros(144, dtype=np.uint32)
+    L.check(lib.b381_pairing(util.p32(g1), util.p32(g2), None, util.p32(out), 1, L.MODE_ARK))
+    assert out.tolist() == g["pairing"]
+    L.check(lib.b381_miller_loop(util.p32(g1), util.p32(g2), None, util.p32(out), 1, L.MODE_ARK))
+    assert out.tolist() == g["miller_ark"]
+    mil = np.array(g["miller_ark"], dtype=np.uint32)
+    L.check(lib.b381_final_exp(util.p32(mil), util.p32(out), 1))
+    assert out.tolist() == g["pairing"]
+    L.check(lib.b381_pairing(util.p32(g1), util.p32(g2), None, util.p32(out), 1, L.MODE_ZK))
+    assert out.tolist() == g["pairing"]
+    co = np.zeros(L.G2PREP_WORDS, dtype=np.uint32)
+    L.check(lib.b381_g2_prepare(util.p32(g2), util.p32(co), 1, L.MODE_ARK))
+    L.check(lib.b381_pairing_prepared(util.p32(g1), util.p32(co), None, util.p32(out), 1, L.MODE_ARK))
+    assert out.tolist() == g["pairing"]
+    # a full round of copies of the pair: every lane of every warp takes the rare path at once
+    import torch
+    n = 4096
+    d1 = torch.from_numpy(np.tile(g1, n).view(np.int32)).cuda(); d2 = torch.from_numpy(np.tile(g2, n).view(np.int32)).cuda()
+    do = torch.empty(n * 144, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b381_pairing_dev(d1.data_ptr(), d2.data_ptr(), None, do.data_ptr(), n, L.MODE_ARK, st))
+    L.check(lib.b381_check_dev(st))
+    assert np.array_equal(do.cpu().numpy().view(np.uint32).reshape(n, 144), np.tile(np.array(g["pairing"], dtype=np.uint32), (n, 1)))

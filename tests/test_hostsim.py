@@ -4,6 +4,7 @@ by tests/hostsim/hostsim.cpp, checked bit-for-bit against the oracle -- and, in 
 arithmetic asserted along the executed path (control flow is input-independent in ARK/ZK mode, so
 one run covers the worst case of every operation site)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -211,6 +212,50 @@ def test_multi_miller_packed(hs):
         cinf = None if inf is None else (ctypes.c_uint8 * n)(*inf)
         assert hs.hs_multi_miller_packed(g1, pkp, cinf, ctypes.c_size_t(n), out) == 0
         assert o.f12_eq(o.f12_from_limbs32(list(out)), want), inf
+
+
+def test_redc_input_word_patterns(hs):
+    """Montgomery reduction of double-width values whose words are all-ones / zero patterns, word 12 in particular: the
+    rows consume words 0..12, and word 12 = 0xffffffff plus the carry of row 0 must ripple into word 13 (it did not:
+    one wrong pairing in 2^20 distinct pairs, tests/golden/regress_redc_carry.json).  Reference: Python integers."""
+    r = util.rng(4242)
+    R = 1 << 416
+    Rinv = pow(R, -1, o.P)
+    out = u(13)
+    n_bad = 0
+    for trial in range(4000):
+        words = [r.randrange(1 << 32) for _ in range(26)]
+        for k in range(24, 26):
+            words[k] = 0
+        words[23] = r.randrange(1 << 18)                     # t < 2^754: a sum of a few products of values below 2^384 / 4
+        for k in range(26):                                  # sprinkle the patterns that break "no carry out" assumptions
+            c = r.randrange(8)
+            if c == 0 and k < 24:
+                words[k] = 0xFFFFFFFF
+            elif c == 1 and k < 24:
+                words[k] = 0
+        if trial % 2 == 0:
+            words[12] = 0xFFFFFFFF
+        if trial % 8 == 0:
+            words[11] = 0xFFFFFFFF; words[13] = 0xFFFFFFFF
+        t = sum(w << (32 * k) for k, w in enumerate(words))
+        assert hs.hs_redc(A(words), out) == 0, "acc_redc and acc_redc2 disagree"
+        got = sum(int(w) << (32 * k) for k, w in enumerate(out))
+        if got % o.P != t * Rinv % o.P or got > 2 * o.P + (t >> 416):
+            n_bad += 1
+    assert n_bad == 0, "%d of 4000 reductions wrong" % n_bad
+
+
+def test_regression_redc_carry_pair(hs):
+    """the pair and the cyclotomic-square input that exposed the reduction carry, against the Python oracle's values"""
+    import json
+    g = json.load(open(os.path.join(util.ROOT, "tests", "golden", "regress_redc_carry.json")))
+    out = u(144)
+    hs.hs_fp12_cyclotomic_square(A(g["cyclotomic_square_input"]), out)
+    assert list(out) == g["cyclotomic_square"]
+    assert hs.hs_final_exp(A(g["miller_ark"]), out) == 0 and list(out) == g["pairing"]
+    assert hs.hs_miller_loop(A(g["g1"]), A(g["g2"]), 0, out, 0) == 0 and list(out) == g["miller_ark"]
+    assert hs.hs_pairing(A(g["g1"]), A(g["g2"]), 0, out, 0) == 0 and list(out) == g["pairing"]
 
 
 def _triples_words(co):
