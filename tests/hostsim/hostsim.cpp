@@ -307,6 +307,40 @@ int hs_redc(const uint32_t* t26, uint32_t* out13) {
   return 0;
 }
 
+// raw products: t = a * b (12- or 13-word operands) and t = a0 b0 + a1 b1 + a2 b2, 26 words out
+static void set_fp_raw(Fp& r, const uint32_t* w) {
+  for (int k = 0; k < NL; k++) r.l[k] = w[k];
+  B381_SETRANGE(r, 0.0, 9.7);
+}
+int hs_mul_raw(const uint32_t* a13, const uint32_t* b13, int n12, uint32_t* out26) {
+  Fp a, b;
+  set_fp_raw(a, a13); set_fp_raw(b, b13);
+  Acc t;
+  B381_TB(t.mag = 0; t.cb = 0;)
+  if (n12) acc_mul12(t, a, b); else acc_mul(t, a, b);
+  for (int k = 0; k < NW; k++) out26[k] = t.c[k];
+  return 0;
+}
+int hs_mul3_raw(const uint32_t* ops /* a0 b0 a1 b1 a2 b2, 13 words each */, int n12, uint32_t* out26) {
+  Fp v[6];
+  for (int i = 0; i < 6; i++) set_fp_raw(v[i], ops + 13 * i);
+  Acc t;
+  B381_TB(t.mag = 0; t.cb = 0;)
+  if (n12) acc_mul3_12(t, v[0], v[1], v[2], v[3], v[4], v[5]); else acc_mul3(t, v[0], v[1], v[2], v[3], v[4], v[5]);
+  for (int k = 0; k < NW; k++) out26[k] = t.c[k];
+  return 0;
+}
+
+// weak reduction of a 13-word two's-complement value, |v| < 2^20 p
+int hs_wreduce_raw(const uint32_t* in13, uint32_t* out13) {
+  Fp a;
+  for (int k = 0; k < NL; k++) a.l[k] = in13[k];
+  B381_SETRANGE(a, -1000000.0, 1000000.0);
+  fp_wreduce(a);
+  for (int k = 0; k < NL; k++) out13[k] = (uint32_t)a.l[k];
+  return 0;
+}
+
 int hs_tracking(void) {
 #ifdef B381_TRACK_BOUNDS
   return 1;

@@ -246,6 +246,64 @@ def test_redc_input_word_patterns(hs):
     assert n_bad == 0, "%d of 4000 reductions wrong" % n_bad
 
 
+def test_product_word_patterns(hs):
+    """the even / odd carry chains of the 12- and 13-word products and of the fused three-product accumulation on
+    operands made of all-ones / zero / random words (the patterns that stress every "this chain end cannot carry out"
+    argument), against Python integers"""
+    r = util.rng(4343)
+    out = u(26)
+
+    def operand(nwords):
+        w = []
+        for k in range(13):
+            c = r.randrange(4)
+            w.append(0 if k >= nwords else (0xFFFFFFFF if c == 0 else 0 if c == 1 else r.randrange(1 << 32)))
+        if nwords == 13:
+            w[12] = r.randrange(1 << 6)                          # 13-word operands stay far below 2^415
+        return w
+
+    val = lambda w: sum(x << (32 * k) for k, x in enumerate(w))
+    for trial in range(1500):
+        n12 = trial % 2
+        nw = 12 if n12 else 13
+        a, b = operand(nw), operand(nw)
+        if trial % 10 == 0:
+            a = [0xFFFFFFFF] * nw + [0] * (13 - nw) if n12 else a
+            b = [0xFFFFFFFF] * nw + [0] * (13 - nw) if n12 else b
+        hs.hs_mul_raw(A(a), A(b), n12, out)
+        assert val(list(out)) == val(a) * val(b), ("product", trial)
+        ops = [operand(nw) for _ in range(6)]
+        if trial % 10 == 0 and n12:
+            ops = [[0xFFFFFFFF] * 12 + [0]] * 6
+        hs.hs_mul3_raw(A(sum(ops, [])), n12, out)
+        assert val(list(out)) == sum(val(ops[2 * i]) * val(ops[2 * i + 1]) for i in range(3)), ("three products", trial)
+
+
+def test_weak_reduction_word_patterns(hs):
+    """fp_wreduce on values of either sign up to 2^20 p whose words are all-ones / zero patterns, and on the multiples of
+    p and their neighbours: the result is the same residue in [0, 1.02 p)"""
+    r = util.rng(4444)
+    out = u(13)
+    M = 1 << 416
+    cases = []
+    for k in range(-(1 << 20) + 1, 1 << 20, 65521):
+        for d in (-1, 0, 1):
+            cases.append(k * o.P + d)
+    for _ in range(3000):
+        w = []
+        for k in range(13):
+            c = r.randrange(4)
+            w.append(0xFFFFFFFF if c == 0 else 0 if c == 1 else r.randrange(1 << 32))
+        v = sum(x << (32 * k) for k, x in enumerate(w)) % (1 << 400)
+        v = v % ((1 << 20) * o.P)
+        cases.append(v if r.randrange(2) else -v)
+    for v in cases:
+        words = [((v % M) >> (32 * k)) & 0xFFFFFFFF for k in range(13)]
+        hs.hs_wreduce_raw(A(words), out)
+        got = sum(int(x) << (32 * k) for k, x in enumerate(out))
+        assert got % o.P == v % o.P and 0 <= got < o.P * 102 // 100, hex(v)
+
+
 def test_regression_redc_carry_pair(hs):
     """the pair and the cyclotomic-square input that exposed the reduction carry, against the Python oracle's values"""
     import json
