@@ -28,6 +28,11 @@ lib = L.init(0)
 t0 = time.time()
 a, b, p, q = T.device_points(L, lib, n, seed)
 res = {"pairs": n, "seed": seed, "distinct_g1": int(len(np.unique(p.reshape(n, 24), axis=0))), "distinct_g2": int(len(np.unique(q.reshape(n, 48), axis=0)))}
+# the generated points themselves: every one must lie in the prime-order subgroup (a wrong scalar multiplication would not)
+f8 = np.zeros(n, dtype=np.uint8)
+u8 = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+L.check(lib.b381_g1_in_subgroup(L.u32(p)[1], None, u8(f8), n)); res["g1_in_subgroup"] = int(f8.sum())
+L.check(lib.b381_g2_in_subgroup(L.u32(q)[1], None, u8(f8), n)); res["g2_in_subgroup"] = int(f8.sum())
 ref = util.load_ref_lib()
 threads = os.cpu_count() or 8
 out = np.zeros(n * 144, dtype=np.uint32)
@@ -57,4 +62,4 @@ res["multi_miller_packed_equal"] = bool(np.array_equal(o144.cpu().numpy().view(n
 res["seconds"] = round(time.time() - t0, 1)
 res["host_threads"] = threads
 print(json.dumps(res))
-sys.exit(0 if (res["pairing_mismatches"] == 0 and res["miller_mismatches"] == 0 and res["packed_miller_mismatches"] == 0 and res["multi_miller_equal"] and res["multi_miller_packed_equal"]) else 1)
+sys.exit(0 if (res["g1_in_subgroup"] == n and res["g2_in_subgroup"] == n and res["pairing_mismatches"] == 0 and res["miller_mismatches"] == 0 and res["packed_miller_mismatches"] == 0 and res["multi_miller_equal"] and res["multi_miller_packed_equal"]) else 1)
